@@ -1,0 +1,120 @@
+/* b2m.h — thin C ABI of the B200 voxel->mesh engine (libb2m.so).
+ *
+ * Plain pointers and sizes only; no CUDA or torch types in any signature.  Every entry point
+ * returns 0 on success, B2M_FAIL (1, the reference's EXIT_FAILURE) when the reference would have
+ * failed for the same input, or a negative B2M_E* code for CUDA/usage errors (b2m_last_error()
+ * gives the text).  There is NO CPU fallback: without a working CUDA device every call fails.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference/):
+ *   b2m_meshify_device / b2m_meshify_host   meshify()                     src/meshify.c:286-389
+ *   b2m_stage_smooth                        quick_smooth()                src/meshify.c:170-216
+ *   b2m_stage_front                         smooth..edge-darken+bbox      src/meshify.c:299-371
+ *                                           (bwlabel() src/bwlabel.c:478-543, dilate() src/meshify.c:218-264)
+ *   b2m_stage_mc                            marchingCubes()               src/MarchingCubes.c:1086-1143
+ *                                                                         src/oldcubes.c:465-522
+ *   b2m_stage_weld                          unify_vertices() +            src/meshify.c:45-106
+ *                                           remove_degenerate_triangles() src/meshify.c:113-168
+ */
+#ifndef B2M_H
+#define B2M_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2M_OK 0
+#define B2M_FAIL 1          /* reference EXIT_FAILURE semantics (no variability, empty mesh, ...) */
+#define B2M_ECUDA (-1)      /* CUDA runtime error */
+#define B2M_EARG (-2)       /* bad argument (dims out of range, NULL pointers, ...) */
+#define B2M_ENOMEM (-3)     /* device or host allocation failed */
+
+/* marching-cubes back-end: the reference picks this at COMPILE time (src/meshify.c:25-29) */
+#define B2M_BACKEND_LEWINER 0 /* MarchingCubes.c: MC33, or its classic table when original_mc != 0 */
+#define B2M_BACKEND_CLASSIC 1 /* oldcubes.c: FP64 triangle soup semantics; original_mc ignored */
+
+typedef struct b2m_ctx b2m_ctx; /* one per host thread / stream: device, stream, workspace arena */
+
+typedef struct {
+  float isolevel;   /* meshify(isolevel)                                                   */
+  int original_mc;  /* meshify(originalMC): -o                                             */
+  int pre_smooth;   /* -p                                                                  */
+  int only_largest; /* -l                                                                  */
+  int fill_bubbles; /* -b                                                                  */
+  int backend;      /* B2M_BACKEND_*                                                       */
+  int verbose;      /* print the reference's stage lines (with device times) to stdout     */
+} b2m_opts;
+
+#define B2M_NSTAGE 8
+enum { B2M_T_SMOOTH = 0, B2M_T_RANGE, B2M_T_CC, B2M_T_COMPOSE, B2M_T_MC, B2M_T_WELD, B2M_T_DEGEN, B2M_T_TOTAL };
+
+typedef struct {
+  /* mesh, left resident on the device (owned by the ctx; valid until the next call on it) */
+  const void *d_verts; /* nverts x 3 f64 (vec3d layout) */
+  const void *d_tris;  /* ntris x 3 i32 (vec3i layout)  */
+  int nverts, ntris;         /* after weld / degenerate-triangle removal  */
+  int pre_nverts, pre_ntris; /* marching-cubes output (Lewiner: as the reference; classic: soup = 3*pre_ntris) */
+  int nmerged, ndegenerate;  /* vertices merged by the weld, triangles removed */
+  float iso_used;            /* isolevel after the range sanity reset (src/meshify.c:316-319) */
+  float vmin, vmax;          /* intensity range after smoothing (src/meshify.c:306-311) */
+  int lo[3], hi[3];          /* bright bounding box handed to marching cubes (src/meshify.c:368-371) */
+  int iso_reset;             /* 1 if the isolevel was out of range and reset */
+  float ms[B2M_NSTAGE];      /* CUDA-event device time per stage, ms; ms[B2M_T_TOTAL] = whole call */
+  uint64_t launches;         /* kernels launched by this call */
+} b2m_result;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int b2m_create(b2m_ctx **ctx, int device);
+void b2m_destroy(b2m_ctx *ctx);
+const char *b2m_last_error(void);
+const char *b2m_version(void);
+void b2m_set_default_backend(int backend); /* used by meshify(); overrides B2M_CLASSIC_CUBES */
+int b2m_device_count(void);
+
+/* ---- device memory helpers (so that C or ctypes callers need no CUDA bindings) ------------- */
+int b2m_dev_alloc(void **dptr, size_t bytes);
+int b2m_dev_free(void *dptr);
+int b2m_host_alloc(void **hptr, size_t bytes); /* pinned */
+int b2m_host_free(void *hptr);
+int b2m_h2d(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b2m_d2h(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
+int b2m_sync(b2m_ctx *ctx);
+int b2m_flush_l2(b2m_ctx *ctx); /* writes a 256 MiB scratch buffer (benchmark hygiene) */
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* Whole meshify() on a volume already resident in device memory (x fastest, dims = NX,NY,NZ).
+ * d_img is NOT modified.  Results stay on the device (res->d_verts / d_tris).  This is what the
+ * Gvoxel/s metric times (res->ms[B2M_T_TOTAL], CUDA events on the ctx stream). */
+int b2m_meshify_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts,
+                       b2m_result *res);
+
+/* Same, from a HOST volume: H2D copy, device pipeline, D2H into malloc() blocks (*verts: nverts x
+ * 3 f64, *tris: ntris x 3 i32) that the caller free()s.  This is what meshify() calls. */
+int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t dims[3], const b2m_opts *opts,
+                     void **verts, void **tris, b2m_result *res);
+
+/* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
+int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
+
+/* ---- stage hooks (parity tests; all pointers are device pointers unless named h_) ---------- */
+/* quick_smooth: d_out = smooth(d_in) (out of place). Returns B2M_FAIL and copies in->out if a dim < 5 */
+int b2m_stage_smooth(b2m_ctx *ctx, const float *d_in, float *d_out, const int64_t dims[3]);
+/* front half of meshify(): smooth, range, sanity, CC mask, fill/largest, darken, bbox.
+ * d_composed (optional, N f32): the volume handed to marching cubes (the reference's mutated img).
+ * d_mask (optional, N bytes): the bwlabel mask after the optional dilation (mask != 0). */
+int b2m_stage_front(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts,
+                    float *d_composed, uint8_t *d_mask, b2m_result *res);
+/* marching cubes alone on a given (already composed) volume and bbox; mesh left on device in
+ * reference emission order (Lewiner) / edge-owner order (classic, welded across cubes). */
+int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const int lo[3], const int hi[3],
+                 const b2m_opts *opts, b2m_result *res);
+/* weld + degenerate-triangle removal on a host mesh (uploads, runs the device weld, downloads).
+ * h_verts: nv x 3 f64, h_tris: nt x 3 i32, updated in place; *nv,*nt updated. */
+int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *nv, int *nt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2M_H */

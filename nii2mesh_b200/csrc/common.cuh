@@ -1,0 +1,211 @@
+// common.cuh — shared device/host helpers of libb2m (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/b2m.h"
+
+#define B2M_WARP 32
+#define B2M_NUM_SMS 148 /* B200: 2 dies x 74 SMs; grids of persistent kernels are sized from this */
+
+void b2m_set_error(const char *fmt, ...);
+
+#define CU_TRY(call)                                                                              \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      b2m_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));        \
+      return B2M_ECUDA;                                                                           \
+    }                                                                                             \
+  } while (0)
+
+#define B2M_TRY(call)            \
+  do {                           \
+    int r_ = (call);             \
+    if (r_ != B2M_OK) return r_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Workspace arena: named, growable device buffers that persist across calls on one ctx so that a
+// steady-state meshify() performs no cudaMalloc.
+enum {
+  BUF_SMOOTH = 0,  // smoothed volume S (N f32)
+  BUF_FG,          // foreground bit rows (img >= iso)
+  BUF_BG,          // background bit rows (complement, valid x only)
+  BUF_FILL,        // fg | bubbles
+  BUF_LARGEST,     // largest 18-connected cluster bits
+  BUF_KEEP,        // largest | dilate25(largest)
+  BUF_NODES,       // union-find nodes (uint2 {parent, size|faceflag}) : 16 per bit word
+  BUF_SCALARS,     // small device scalar block (b2m_scalars)
+  BUF_SEG,         // MC per-32-voxel segment records (uint4 {xbits,ybits,zbits,vbase})
+  BUF_SEG2,        // MC per-segment {tbase, cbase}
+  BUF_ACTIVE,      // MC active-voxel records (uint4)
+  BUF_VERTS,       // f64 xyz
+  BUF_TRIS,        // i32 xyz
+  BUF_VERTS2,      // compacted vertices
+  BUF_TRIS2,       // compacted triangles
+  BUF_CAND,        // weld candidates (u32 vertex ids)
+  BUF_SORTA,       // sort ping
+  BUF_SORTB,       // sort pong
+  BUF_SORTH,       // sort histograms
+  BUF_REMAP,       // u32 per vertex
+  BUF_FLAGS,       // u32 per vertex / triangle (keep flags -> scanned)
+  BUF_SCAN1,       // scan partials
+  BUF_SCAN2,
+  BUF_TABLES,      // MC case tables blob
+  BUF_L2FLUSH,
+  BUF_TMP0,
+  BUF_TMP1,
+  BUF_INPUT,       // device copy of a host volume (b2m_meshify_host)
+  BUF_COUNT
+};
+
+struct b2m_buf {
+  void *p;
+  size_t cap;
+};
+
+// device-side scalars of one meshify call (one 256-byte block, zeroed per call)
+struct b2m_scalars {
+  unsigned int vmin_enc, vmax_enc;       // order-preserving encodings of f32 min/max
+  unsigned int cmin_enc;                 // min of the composed volume (lazy)
+  int lo[3], hi[3];                      // bright bbox (raw, before the +-1/+2 widening)
+  unsigned long long best_fg;            // (size << 32) | ~rootslot  of the largest fg cluster
+  unsigned int nroots_fg, nroots_bg;     // number of components
+  unsigned int n_active;                 // MC active records appended
+  unsigned int n_cand;                   // weld candidates appended
+  unsigned int n_removed;                // vertices merged away
+  unsigned int tot_v, tot_t, tot_c;      // MC totals (edge vertices, triangles, centroid vertices)
+  unsigned int n_tri_kept;               // triangles surviving the degenerate test
+  unsigned int overflow;                 // any capacity overflow flag
+  unsigned int n_clusters;               // weld: clusters formed among the candidates
+  unsigned long long first_cube;         // min (row << 16 | x) over active cubes (classic pts[0])
+  double pts0[3];                        // classic: first soup vertex (the weld's key origin)
+  unsigned int pad[8];
+};
+
+struct b2m_ctx {
+  int device;
+  cudaStream_t stream;
+  b2m_buf buf[BUF_COUNT];
+  cudaEvent_t ev[2 * B2M_NSTAGE + 2];
+  b2m_scalars *h_scalars;  // pinned mirror
+  uint64_t launches;
+  int tables_ready;
+  int sm_count;
+  unsigned ev_mask;        // which stage event pairs were recorded in the current call
+};
+
+int b2m_reserve(b2m_ctx *ctx, int which, size_t bytes);
+template <typename T>
+static inline T *b2m_ptr(b2m_ctx *ctx, int which) {
+  return reinterpret_cast<T *>(ctx->buf[which].p);
+}
+int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
+
+#define B2M_LAUNCHED(ctx) ((ctx)->launches++)
+
+static inline unsigned int b2m_cdiv(size_t a, size_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving f32 <-> u32 (for atomicMin/atomicMax on floats)
+__host__ __device__ static inline unsigned int f32_enc(float f) {
+  unsigned int u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(f);
+#else
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ static inline float f32_dec(unsigned int e) {
+  unsigned int u = (e & 0x80000000u) ? (e & 0x7fffffffu) : ~e;
+  float f;
+#ifdef __CUDA_ARCH__
+  f = __uint_as_float(u);
+#else
+  memcpy(&f, &u, 4);
+#endif
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// volume geometry shared by the kernels
+struct b2m_geom {
+  int nx, ny, nz;      // volume dims
+  int w;               // 32-bit words per bit row = ceil(nx/32)
+  long long nxy;       // nx*ny
+  long long n;         // voxels
+  long long nrows;     // ny*nz
+  long long nwords;    // nrows*w
+};
+static inline b2m_geom b2m_make_geom(const int64_t dims[3]) {
+  b2m_geom g;
+  g.nx = (int)dims[0]; g.ny = (int)dims[1]; g.nz = (int)dims[2];
+  g.w = (g.nx + 31) / 32;
+  g.nxy = (long long)g.nx * g.ny;
+  g.n = g.nxy * g.nz;
+  g.nrows = (long long)g.ny * g.nz;
+  g.nwords = g.nrows * g.w;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// composed value of one voxel = what the reference's mutated img holds when marching cubes runs
+// (/root/reference/src/meshify.c:332-365): bubble fill to >= iso, non-kept voxels to mn, faces
+// darkened to <= edge_max.  Never materialised on the hot path: S plus two bit rows.
+struct compose_params {
+  const float *S;
+  const uint32_t *fill;
+  const uint32_t *keep;
+  int nx, ny, nz, w;
+  float iso, mn, edge_max;
+};
+__device__ __forceinline__ float composed_value(const compose_params &c, int x, int y, int z) {
+  size_t row = (size_t)z * c.ny + y;
+  float v = __ldg(c.S + row * c.nx + x);
+  if (c.fill || c.keep) {
+    size_t word = row * c.w + (x >> 5);
+    if (c.fill && ((__ldg(c.fill + word) >> (x & 31)) & 1u)) v = fmaxf(v, c.iso);
+    if (c.keep && !((__ldg(c.keep + word) >> (x & 31)) & 1u)) v = c.mn;
+  }
+  if (x == 0 || y == 0 || z == 0 || x == c.nx - 1 || y == c.ny - 1 || z == c.nz - 1) v = fminf(c.edge_max, v);
+  return v;
+}
+
+// stages implemented across the .cu files ------------------------------------------------------
+int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom &g, b2m_scalars *d_sc);
+int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, b2m_scalars *d_sc);
+int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg);
+
+struct b2m_front_out {
+  const float *S;          // smoothed (or original) volume
+  const uint32_t *fill;    // nullptr or fg|bubbles bit rows
+  const uint32_t *keep;    // nullptr or largest|dilated bit rows
+  float iso, vmin, vmax, edge_max;
+  int lo[3], hi[3];        // widened bbox as handed to marching cubes
+  int iso_reset;
+};
+int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc, b2m_front_out *fo);
+int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m_opts *o, b2m_front_out *fo,
+                  b2m_result *res);
+int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out *fo, float *d_composed,
+                            uint8_t *d_mask, b2m_scalars *d_sc, int want_min);
+
+struct b2m_mesh_dev {
+  double *verts;  // BUF_VERTS
+  int *tris;      // BUF_TRIS
+  unsigned int nv, nt;   // pre-weld counts
+  unsigned int nv_edge;  // edge vertices (centroid vertices follow)
+  unsigned int ncand;    // weld candidates in BUF_CAND
+};
+int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_front_out *fo, b2m_mesh_dev *mesh);
+int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backend, b2m_result *res);
+
+// generic primitives (scan.cu)
+int b2m_exclusive_scan_u32(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);
+int b2m_sort_u64(b2m_ctx *ctx, uint64_t *d_keys, size_t n, int key_bits);  // ascending, in place (uses BUF_SORTB/H)

@@ -1,0 +1,159 @@
+// ctx.cu — context, workspace arena, memory helpers of libb2m.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+static int g_default_backend = -1;
+
+void b2m_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *b2m_last_error(void) { return g_err; }
+extern "C" const char *b2m_version(void) { return "b2m 0.1 (sm_100a)"; }
+extern "C" void b2m_set_default_backend(int backend) { g_default_backend = backend; }
+extern "C" int b2m_get_default_backend(void) {
+  if (g_default_backend >= 0) return g_default_backend;
+  const char *e = getenv("B2M_CLASSIC_CUBES");
+  return (e && atoi(e) != 0) ? B2M_BACKEND_CLASSIC : B2M_BACKEND_LEWINER;
+}
+
+extern "C" int b2m_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+extern "C" int b2m_create(b2m_ctx **out, int device) {
+  if (!out) return B2M_EARG;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    b2m_set_error("no CUDA device available (%s): libb2m has no CPU fallback", cudaGetErrorString(e));
+    return B2M_ECUDA;
+  }
+  if (device < 0 || device >= n) {
+    b2m_set_error("device %d out of range (0..%d)", device, n - 1);
+    return B2M_EARG;
+  }
+  CU_TRY(cudaSetDevice(device));
+  b2m_ctx *c = (b2m_ctx *)calloc(1, sizeof(b2m_ctx));
+  if (!c) return B2M_ENOMEM;
+  c->device = device;
+  CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); i++) CU_TRY(cudaEventCreate(&c->ev[i]));
+  CU_TRY(cudaMallocHost((void **)&c->h_scalars, sizeof(b2m_scalars)));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return B2M_OK;
+}
+
+extern "C" void b2m_destroy(b2m_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < BUF_COUNT; i++)
+    if (c->buf[i].p) cudaFree(c->buf[i].p);
+  for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); i++) cudaEventDestroy(c->ev[i]);
+  cudaFreeHost(c->h_scalars);
+  cudaStreamDestroy(c->stream);
+  free(c);
+}
+
+int b2m_reserve(b2m_ctx *ctx, int which, size_t bytes) {
+  b2m_buf &b = ctx->buf[which];
+  if (bytes < 256) bytes = 256;
+  if (b.cap >= bytes) return B2M_OK;
+  if (b.p) {
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    CU_TRY(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes + bytes / 16;  // small head-room so near-equal sizes do not thrash
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    b2m_set_error("cudaMalloc(%zu bytes) for workspace %d failed: %s", want, which, cudaGetErrorString(e));
+    b.p = nullptr;
+    return B2M_ENOMEM;
+  }
+  b.cap = want;
+  return B2M_OK;
+}
+
+int b2m_fetch_scalars(b2m_ctx *ctx) {
+  CU_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->buf[BUF_SCALARS].p, sizeof(b2m_scalars), cudaMemcpyDeviceToHost,
+                         ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+extern "C" int b2m_dev_alloc(void **dptr, size_t bytes) {
+  if (!dptr) return B2M_EARG;
+  cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    b2m_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return B2M_ENOMEM;
+  }
+  return B2M_OK;
+}
+extern "C" int b2m_dev_free(void *dptr) {
+  CU_TRY(cudaFree(dptr));
+  return B2M_OK;
+}
+extern "C" int b2m_host_alloc(void **hptr, size_t bytes) {
+  if (!hptr) return B2M_EARG;
+  cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    b2m_set_error("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return B2M_ENOMEM;
+  }
+  return B2M_OK;
+}
+extern "C" int b2m_host_free(void *hptr) {
+  CU_TRY(cudaFreeHost(hptr));
+  return B2M_OK;
+}
+extern "C" int b2m_h2d(b2m_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+extern "C" int b2m_d2h(b2m_ctx *ctx, void *dst, const void *src, size_t bytes) {
+  if (!ctx) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+extern "C" int b2m_sync(b2m_ctx *ctx) {
+  if (!ctx) return B2M_EARG;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+__global__ void k_fill_u32(uint4 *p, size_t n16, unsigned int v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
+extern "C" int b2m_flush_l2(b2m_ctx *ctx) {
+  if (!ctx) return B2M_EARG;
+  const size_t bytes = 256u << 20;  // > 126 MB L2
+  B2M_TRY(b2m_reserve(ctx, BUF_L2FLUSH, bytes));
+  k_fill_u32<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b2m_ptr<uint4>(ctx, BUF_L2FLUSH), bytes / 16, 0x5a5a5a5au);
+  CU_TRY(cudaGetLastError());
+  return B2M_OK;
+}

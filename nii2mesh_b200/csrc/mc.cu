@@ -1,0 +1,639 @@
+// mc.cu — kernel 3: marching cubes as classify -> prefix scan -> compact emit.
+//
+// Three reference flavours behind one runtime switch (the reference picks at compile time,
+// /root/reference/src/meshify.c:25-29):
+//   backend LEWINER, original_mc = 0 : MC33 with face/interior ambiguity tests
+//        src/MarchingCubes.c:116-155 (cube loop), :235-270 (edge vertices), :276-295 (test_face),
+//        :301-453 (test_interior), :458-795 (process_cube), :803-859 (add_triangle),
+//        :935-1026 (edge vertex = (float)i + c0/(c0-c1)), :1029-1082 (centroid vertex),
+//        :1086-1143 (sub-volume copy with -isolevel, export with +lo in f32, reversed winding)
+//   backend LEWINER, original_mc = 1 : same code, `casesClassic` table (:471-477)
+//   backend CLASSIC                  : src/oldcubes.c:465-522 / :50-463 / :22-40 — FP64 positions
+//        p1 + mu*(p2-p1); the reference emits a triangle SOUP which its weld then merges; here
+//        vertices are born welded per grid edge (edge-keyed), taking the FP64 variant of the soup
+//        copy with the highest soup index, which is the one the reference's weld keeps
+//        (src/meshify.c:99-100).
+//
+// The composed volume (bubble fill, largest-cluster mask, darkened faces) is never materialised:
+// every load goes through composed_value() (S + two bit rows), see cc.cu.
+//
+// Output order = the reference's emission order: edge vertices in raster order of their owner
+// voxel (x, then y, then z edge per voxel), then centroid vertices in cube raster order;
+// triangles in cube raster order.  That is obtained from an exclusive scan over per-32-voxel
+// segment counts; the emit pass runs only over the compacted list of active voxels.
+#include "common.cuh"
+
+#define MCT_NO_BLOB
+#include "mc_tables.inc"
+#undef MCT_NO_BLOB
+
+
+struct mc_params {
+  compose_params c;
+  int lo0, lo1, lo2;
+  int sx, sy, sz;   // sub-volume size in voxels
+  int segs;         // 32-voxel segments per sub-volume row
+  float pad;        // Lewiner: value of sub-volume voxels that fall outside the volume (already - iso)
+  int classic;      // backend == CLASSIC
+  int original_mc;
+  const signed char *tab;
+  uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks
+  uint32_t *segv, *segt, *segc;  // per segment counts -> exclusive prefix (in place)
+  uint4 *active;
+  unsigned int active_cap;
+  b2m_scalars *sc;
+};
+
+// value of sub-volume voxel (x,y,z).  Lewiner: img[j]-iso with the reference's linear-index-only
+// guard (row wrap quirk, src/MarchingCubes.c:1106-1115), clamped away from zero (:132,:252-255).
+// Classic: the raw composed value.
+__device__ __forceinline__ float mc_data(const mc_params &p, int x, int y, int z) {
+  int gx = p.lo0 + x, gy = p.lo1 + y, gz = p.lo2 + z;
+  if (p.classic) return composed_value(p.c, gx, gy, gz);
+  if (gx >= p.c.nx) { gx -= p.c.nx; gy++; }
+  if (gy >= p.c.ny) { gy -= p.c.ny; gz++; }
+  float v = (gz >= p.c.nz) ? p.pad : composed_value(p.c, gx, gy, gz) - p.c.iso;
+  if (fabsf(v) < FLT_EPSILON) v = FLT_EPSILON;
+  return v;
+}
+__device__ __forceinline__ bool mc_inside(const mc_params &p, float v) { return p.classic ? (v < p.c.iso) : (v > 0.0f); }
+
+// ---- MC33 decision procedure ---------------------------------------------------------------
+__device__ const signed char MC_FACE_Q[6][4] = {{0, 4, 5, 1}, {1, 5, 6, 2}, {2, 6, 7, 3}, {3, 7, 4, 0}, {0, 3, 2, 1}, {4, 7, 6, 5}};
+// rows {e0,e1, B0,B1, C0,C1, D0,D1}: the twelve reference-edge slices of test_interior (:335-420)
+__device__ const signed char MC_EDGE_SLICE[12][8] = {
+    {0, 1, 3, 2, 7, 6, 4, 5}, {1, 2, 0, 3, 4, 7, 5, 6}, {2, 3, 1, 0, 5, 4, 6, 7}, {3, 0, 2, 1, 6, 5, 7, 4},
+    {4, 5, 7, 6, 3, 2, 0, 1}, {5, 6, 4, 7, 0, 3, 1, 2}, {6, 7, 5, 4, 1, 0, 2, 3}, {7, 4, 6, 5, 2, 1, 3, 0},
+    {0, 4, 3, 7, 2, 6, 1, 5}, {1, 5, 0, 4, 3, 7, 2, 6}, {2, 6, 1, 5, 0, 4, 3, 7}, {3, 7, 2, 6, 1, 5, 0, 4}};
+
+__device__ const signed char MC_EDGE_A[12] = {0, 1, 2, 3, 4, 5, 6, 7, 0, 1, 2, 3};
+__device__ const signed char MC_EDGE_B[12] = {1, 2, 3, 0, 5, 6, 7, 4, 4, 5, 6, 7};
+
+__device__ __forceinline__ bool t_face(const float *c, int f) {  // src/MarchingCubes.c:276-295
+  const signed char *q = MC_FACE_Q[(f < 0 ? -f : f) - 1];
+  float A = c[q[0]], B = c[q[1]], C = c[q[2]], D = c[q[3]];
+  float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, D));
+  if (fabsf(det) < FLT_EPSILON) return f >= 0;
+  return __fmul_rn(__fmul_rn((float)f, A), det) >= 0.0f;
+}
+
+__device__ __forceinline__ float lerp_rn(float a, float b, float t) {  // a + (b - a) * t, no contraction
+  return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+}
+
+__device__ bool t_interior(const float *c, int kase, int refedge, int s) {  // :301-453
+  float t, At = 0.f, Bt = 0.f, Ct = 0.f, Dt = 0.f;
+  if (kase == 4 || kase == 10) {
+    float d40 = __fsub_rn(c[4], c[0]), d62 = __fsub_rn(c[6], c[2]), d73 = __fsub_rn(c[7], c[3]), d51 = __fsub_rn(c[5], c[1]);
+    float a = __fsub_rn(__fmul_rn(d40, d62), __fmul_rn(d73, d51));
+    float b = __fmul_rn(c[2], d40);
+    b = __fadd_rn(b, __fmul_rn(c[0], d62));
+    b = __fsub_rn(b, __fmul_rn(c[1], d73));
+    b = __fsub_rn(b, __fmul_rn(c[3], d51));
+    t = __fdiv_rn(-b, __fmul_rn(2.0f, a));
+    if (t < 0.f || t > 1.f) return s > 0;
+    At = __fadd_rn(c[0], __fmul_rn(d40, t));
+    Bt = __fadd_rn(c[3], __fmul_rn(d73, t));
+    Ct = __fadd_rn(c[2], __fmul_rn(d62, t));
+    Dt = __fadd_rn(c[1], __fmul_rn(d51, t));
+  } else if (refedge >= 0 && refedge < 12) {
+    const signed char *r = MC_EDGE_SLICE[refedge];
+    t = __fdiv_rn(c[r[0]], __fsub_rn(c[r[0]], c[r[1]]));
+    At = 0.f;
+    Bt = lerp_rn(c[r[2]], c[r[3]], t);
+    Ct = lerp_rn(c[r[4]], c[r[5]], t);
+    Dt = lerp_rn(c[r[6]], c[r[7]], t);
+  }
+  int test = (At >= 0.f ? 1 : 0) | (Bt >= 0.f ? 2 : 0) | (Ct >= 0.f ? 4 : 0) | (Dt >= 0.f ? 8 : 0);
+  float det = __fsub_rn(__fmul_rn(At, Ct), __fmul_rn(Bt, Dt));
+  switch (test) {
+    case 5: return (det < FLT_EPSILON) ? s > 0 : s < 0;
+    case 10: return (det >= FLT_EPSILON) ? s > 0 : s < 0;
+    case 7: case 11: case 13: case 14: case 15: return s < 0;
+    default: return s > 0;
+  }
+}
+
+#define TROW(name, cfg) (MCT_##name + (cfg) * MCT_##name##_ROW)
+#define TSUB(name, cfg, sub) (MCT_##name + (cfg) * MCT_##name##_ROW + (sub) * MCT_##name##_SUB)
+#define PICK(off_, n_, c_) do { off = (off_); ntri = (n_); hasc = (c_); return; } while (0)
+
+// src/MarchingCubes.c:458-795.  c = clamped corner values; lut bit p = c[p] > 0.
+__device__ void mc33_select(const signed char *__restrict__ tab, const float *c, int lut, int original_mc, int &off,
+                            int &ntri, int &hasc) {
+  if (original_mc) {
+    int o = MCT_casesClassic + 16 * lut, n = 0;
+    while (n < 5 && tab[o + 3 * n] != -1) n++;
+    PICK(o, n, 0);
+  }
+  const int kase = tab[MCT_cases + 2 * lut], cfg = tab[MCT_cases + 2 * lut + 1];
+  switch (kase) {
+    case 1: PICK(TROW(tiling1, cfg), 1, 0);
+    case 2: PICK(TROW(tiling2, cfg), 2, 0);
+    case 3:
+      if (t_face(c, tab[MCT_test3 + cfg])) PICK(TROW(tiling3_2, cfg), 4, 0);
+      PICK(TROW(tiling3_1, cfg), 2, 0);
+    case 4:
+      if (t_interior(c, 4, -1, tab[MCT_test4 + cfg])) PICK(TROW(tiling4_1, cfg), 2, 0);
+      PICK(TROW(tiling4_2, cfg), 6, 0);
+    case 5: PICK(TROW(tiling5, cfg), 3, 0);
+    case 6: {
+      const signed char *t = tab + TROW(test6, cfg);
+      if (t_face(c, t[0])) PICK(TROW(tiling6_2, cfg), 5, 0);
+      if (t_interior(c, 6, t[2], t[1])) PICK(TROW(tiling6_1_1, cfg), 3, 0);
+      PICK(TROW(tiling6_1_2, cfg), 9, 1);
+    }
+    case 7: {
+      const signed char *t = tab + TROW(test7, cfg);
+      int sub = (t_face(c, t[0]) ? 1 : 0) | (t_face(c, t[1]) ? 2 : 0) | (t_face(c, t[2]) ? 4 : 0);
+      switch (sub) {
+        case 0: PICK(TROW(tiling7_1, cfg), 3, 0);
+        case 1: PICK(TSUB(tiling7_2, cfg, 0), 5, 0);
+        case 2: PICK(TSUB(tiling7_2, cfg, 1), 5, 0);
+        case 3: PICK(TSUB(tiling7_3, cfg, 0), 9, 1);
+        case 4: PICK(TSUB(tiling7_2, cfg, 2), 5, 0);
+        case 5: PICK(TSUB(tiling7_3, cfg, 1), 9, 1);
+        case 6: PICK(TSUB(tiling7_3, cfg, 2), 9, 1);
+        default:
+          if (t_interior(c, 7, t[4], t[3])) PICK(TROW(tiling7_4_2, cfg), 9, 0);
+          PICK(TROW(tiling7_4_1, cfg), 5, 0);
+      }
+    }
+    case 8: PICK(TROW(tiling8, cfg), 2, 0);
+    case 9: PICK(TROW(tiling9, cfg), 4, 0);
+    case 10: {
+      const signed char *t = tab + TROW(test10, cfg);
+      bool f0 = t_face(c, t[0]), f1 = t_face(c, t[1]);
+      if (f0 && f1) PICK(TROW(tiling10_1_1_, cfg), 4, 0);
+      if (f0) PICK(TROW(tiling10_2, cfg), 8, 1);
+      if (f1) PICK(TROW(tiling10_2_, cfg), 8, 1);
+      if (t_interior(c, 10, -1, t[2])) PICK(TROW(tiling10_1_1, cfg), 4, 0);
+      PICK(TROW(tiling10_1_2, cfg), 8, 0);
+    }
+    case 11: PICK(TROW(tiling11, cfg), 4, 0);
+    case 12: {
+      const signed char *t = tab + TROW(test12, cfg);
+      bool f0 = t_face(c, t[0]), f1 = t_face(c, t[1]);
+      if (f0 && f1) PICK(TROW(tiling12_1_1_, cfg), 4, 0);
+      if (f0) PICK(TROW(tiling12_2, cfg), 8, 1);
+      if (f1) PICK(TROW(tiling12_2_, cfg), 8, 1);
+      if (t_interior(c, 12, t[3], t[2])) PICK(TROW(tiling12_1_1, cfg), 4, 0);
+      PICK(TROW(tiling12_1_2, cfg), 8, 0);
+    }
+    case 13: {
+      const signed char *t = tab + TROW(test13, cfg);
+      int sub = 0;
+#pragma unroll
+      for (int b = 0; b < 6; b++)
+        if (t_face(c, t[b])) sub |= 1 << b;
+      const int sc = tab[MCT_subconfig13 + sub];
+      if (sc == 0) PICK(TROW(tiling13_1, cfg), 4, 0);
+      if (sc >= 1 && sc <= 6) PICK(TSUB(tiling13_2, cfg, sc - 1), 6, 0);
+      if (sc >= 7 && sc <= 18) PICK(TSUB(tiling13_3, cfg, sc - 7), 10, 1);
+      if (sc >= 19 && sc <= 22) PICK(TSUB(tiling13_4, cfg, sc - 19), 12, 1);
+      if (sc >= 23 && sc <= 26) {
+        const int k = sc - 23;
+        const int refedge = tab[TSUB(tiling13_5_1, cfg, k)];
+        if (t_interior(c, 13, refedge, t[6])) PICK(TSUB(tiling13_5_1, cfg, k), 6, 0);
+        PICK(TSUB(tiling13_5_2, cfg, k), 10, 0);
+      }
+      if (sc >= 27 && sc <= 38) PICK(TSUB(tiling13_3_, cfg, sc - 27), 10, 1);
+      if (sc >= 39 && sc <= 44) PICK(TSUB(tiling13_2_, cfg, sc - 39), 6, 0);
+      if (sc == 45) PICK(TROW(tiling13_1_, cfg), 4, 0);
+      PICK(0, 0, 0);  // "Impossible case 13?" (:785): no triangles
+    }
+    case 14: PICK(TROW(tiling14, cfg), 4, 0);
+    default: PICK(0, 0, 0);
+  }
+}
+
+// ---- pass A: classify ------------------------------------------------------------------------
+// One warp per 32-voxel segment of a sub-volume row; a CTA covers 8 consecutive rows so that the
+// y+1 row of warp k is the y row of warp k+1 (L1 reuse); z+1 rows are re-read through L2.
+#define MCA_ROWS 8
+__global__ void __launch_bounds__(32 * MCA_ROWS) k_mc_classify(mc_params p) {
+  const unsigned lane = threadIdx.x & 31;
+  const int seg = blockIdx.x;
+  const int y = blockIdx.y * MCA_ROWS + (threadIdx.x >> 5);
+  const int z = blockIdx.z;
+  if (y >= p.sy) return;  // whole warp
+  const int x = seg * 32 + (int)lane;
+  const size_t row = (size_t)z * p.sy + y;
+  const bool vx = x < p.sx, vy1 = y + 1 < p.sy, vz1 = z + 1 < p.sz;
+  // this lane's column at the four rows (y,z) (y+1,z) (y,z+1) (y+1,z+1); lane 0 also fetches x+32
+  float d00 = 0.f, d10 = 0.f, d01 = 0.f, d11 = 0.f, e00 = 0.f, e10 = 0.f, e01 = 0.f, e11 = 0.f;
+  if (vx) {
+    d00 = mc_data(p, x, y, z);
+    if (vy1) d10 = mc_data(p, x, y + 1, z);
+    if (vz1) d01 = mc_data(p, x, y, z + 1);
+    if (vy1 && vz1) d11 = mc_data(p, x, y + 1, z + 1);
+  }
+  const int xe = seg * 32 + 32;
+  if (lane == 0 && xe < p.sx) {
+    e00 = mc_data(p, xe, y, z);
+    if (vy1) e10 = mc_data(p, xe, y + 1, z);
+    if (vz1) e01 = mc_data(p, xe, y, z + 1);
+    if (vy1 && vz1) e11 = mc_data(p, xe, y + 1, z + 1);
+  }
+  float c[8];
+  c[0] = d00; c[3] = d10; c[4] = d01; c[7] = d11;
+  {
+    float n00 = __shfl_down_sync(0xffffffffu, d00, 1), n10 = __shfl_down_sync(0xffffffffu, d10, 1);
+    float n01 = __shfl_down_sync(0xffffffffu, d01, 1), n11 = __shfl_down_sync(0xffffffffu, d11, 1);
+    float x00 = __shfl_sync(0xffffffffu, e00, 0), x10 = __shfl_sync(0xffffffffu, e10, 0);
+    float x01 = __shfl_sync(0xffffffffu, e01, 0), x11 = __shfl_sync(0xffffffffu, e11, 0);
+    c[1] = lane == 31 ? x00 : n00; c[2] = lane == 31 ? x10 : n10;
+    c[5] = lane == 31 ? x01 : n01; c[6] = lane == 31 ? x11 : n11;
+  }
+  const bool vx1 = x + 1 < p.sx;
+  const bool in0 = mc_inside(p, c[0]);
+  const bool ex = vx && vx1 && (in0 != mc_inside(p, c[1]));
+  const bool ey = vx && vy1 && (in0 != mc_inside(p, c[3]));
+  const bool ez = vx && vz1 && (in0 != mc_inside(p, c[4]));
+  int ntri = 0, hasc = 0, off = 0, lut = 0;
+  if (vx1 && vy1 && vz1) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) lut |= mc_inside(p, c[q]) ? (1 << q) : 0;
+    if (lut != 0 && lut != 255) {
+      if (p.classic) {
+        int o = MCT_casesClassic + 16 * lut, n = 0;
+        while (n < 5 && p.tab[o + 3 * n] != -1) n++;
+        off = o; ntri = n;
+      } else {
+        mc33_select(p.tab, c, lut, p.original_mc, off, ntri, hasc);
+      }
+    }
+  }
+  const unsigned xb = __ballot_sync(0xffffffffu, ex), yb = __ballot_sync(0xffffffffu, ey), zb = __ballot_sync(0xffffffffu, ez);
+  const int nv = (int)ex + (int)ey + (int)ez;
+  // warp exclusive prefixes of (nv, ntri, hasc)
+  int pv = nv, pt = ntri, pc = hasc;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int a = __shfl_up_sync(0xffffffffu, pv, d), b = __shfl_up_sync(0xffffffffu, pt, d), cc = __shfl_up_sync(0xffffffffu, pc, d);
+    if (lane >= (unsigned)d) { pv += a; pt += b; pc += cc; }
+  }
+  const int tv = __shfl_sync(0xffffffffu, pv, 31), tt = __shfl_sync(0xffffffffu, pt, 31), tc = __shfl_sync(0xffffffffu, pc, 31);
+  pv -= nv; pt -= ntri; pc -= hasc;
+  const size_t sidx = row * p.segs + seg;
+  if (lane == 0) {
+    p.segbits[sidx] = make_uint4(xb, yb, zb, 0u);
+    p.segv[sidx] = (uint32_t)tv;
+    p.segt[sidx] = (uint32_t)tt;
+    p.segc[sidx] = (uint32_t)tc;
+  }
+  if (p.classic) {  // first active cube in raster order: its first soup vertex is the weld's pts[0]
+    unsigned long long key = ntri > 0 ? (((unsigned long long)row << 16) | (unsigned long long)x) : ~0ull;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+      key = o < key ? o : key;
+    }
+    if (lane == 0 && key != ~0ull && key < *(volatile unsigned long long *)&p.sc->first_cube)
+      atomicMin(&p.sc->first_cube, key);
+  }
+  const bool act = nv > 0 || ntri > 0;
+  const unsigned am = __ballot_sync(0xffffffffu, act);
+  if (am) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&p.sc->n_active, (unsigned)__popc(am));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (act) {
+      unsigned pos = base + __popc(am & ((1u << lane) - 1u));
+      if (pos < p.active_cap) {
+        uint4 r;
+        r.x = (uint32_t)row;
+        r.y = (uint32_t)x | ((uint32_t)ex << 16) | ((uint32_t)ey << 17) | ((uint32_t)ez << 18) | ((uint32_t)ntri << 19) |
+              ((uint32_t)hasc << 23) | ((uint32_t)pc << 24);
+        r.z = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)off << 16);
+        r.w = (uint32_t)lut;
+        p.active[pos] = r;
+      }
+    }
+  }
+}
+
+// ---- pass B: emit ------------------------------------------------------------------------------
+struct mc_emit_params {
+  double *verts;
+  int *tris;
+  uint32_t *cand;
+  unsigned int cand_cap;
+  unsigned int n_active;
+  unsigned int nv_edge;  // total edge vertices (centroid vertices are numbered after them)
+  unsigned long long first_cube;  // classic: (row << 16 | x) of the first active cube
+};
+
+// index of the edge vertex owned by sub-volume voxel (x,row) on `axis`
+__device__ __forceinline__ uint32_t mc_vidx(const mc_params &p, size_t row, int x, int axis) {
+  size_t s = row * p.segs + (x >> 5);
+  uint4 b = __ldg(p.segbits + s);
+  unsigned lane = x & 31, m = (1u << lane) - 1u;
+  uint32_t n = __ldg(p.segv + s) + __popc(b.x & m) + __popc(b.y & m) + __popc(b.z & m);
+  if (axis >= 1) n += (b.x >> lane) & 1u;
+  if (axis == 2) n += (b.y >> lane) & 1u;
+  return n;
+}
+
+__device__ __forceinline__ void push_cand(const mc_params &p, const mc_emit_params &e, uint32_t vid) {
+  unsigned pos = atomicAdd(&p.sc->n_cand, 1u);
+  if (pos < e.cand_cap) e.cand[pos] = vid;
+}
+
+// Lewiner edge vertex: u = c0/(c0-c1) (0.5 when the denominator is zero), local f32 coordinate
+// (float)i + u, exported as (double)(float)(local + (float)lo)   (src/MarchingCubes.c:943-949,:1127-1129)
+__device__ __forceinline__ float lew_u(float c0, float c1) {
+  float den = __fsub_rn(c0, c1);
+  return den != 0.0f ? __fdiv_rn(c0, den) : 0.5f;
+}
+__device__ __forceinline__ bool near_int(float f, float tol) { return fabsf(__fsub_rn(f, rintf(f))) < tol; }
+__device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f - rint(f)) < tol; }
+
+__global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= e.n_active) return;
+  const uint4 r = p.active[i];
+  const size_t row = r.x;
+  const int x = r.y & 0xffff;
+  const bool ex = (r.y >> 16) & 1, ey = (r.y >> 17) & 1, ez = (r.y >> 18) & 1;
+  const int ntri = (r.y >> 19) & 15, hasc = (r.y >> 23) & 1, pc = (r.y >> 24) & 31;
+  const int pv = r.z & 127, pt = (r.z >> 7) & 511, off = (int)(r.z >> 16);
+  const int z = (int)(row / p.sy), y = (int)(row - (size_t)z * p.sy);
+  const size_t sidx = row * p.segs + (x >> 5);
+  // corner values (only the ones that exist inside the sub-volume)
+  const bool vx1 = x + 1 < p.sx, vy1 = y + 1 < p.sy, vz1 = z + 1 < p.sz;
+  float c[8];
+  c[0] = mc_data(p, x, y, z);
+  c[1] = vx1 ? mc_data(p, x + 1, y, z) : c[0];
+  c[3] = vy1 ? mc_data(p, x, y + 1, z) : c[0];
+  c[4] = vz1 ? mc_data(p, x, y, z + 1) : c[0];
+  if (ntri) {
+    c[2] = mc_data(p, x + 1, y + 1, z);
+    c[5] = mc_data(p, x + 1, y, z + 1);
+    c[6] = mc_data(p, x + 1, y + 1, z + 1);
+    c[7] = mc_data(p, x, y + 1, z + 1);
+  } else {
+    c[2] = c[5] = c[6] = c[7] = c[0];
+  }
+  const float flo0 = (float)p.lo0, flo1 = (float)p.lo1, flo2 = (float)p.lo2;
+  // ---- own edge vertices ----
+  if (ex | ey | ez) {
+    uint32_t vid = __ldg(p.segv + sidx) + (uint32_t)pv;
+    if (!p.classic) {
+      const float fx = (float)x, fy = (float)y, fz = (float)z;
+      if (ex) {
+        float px = __fadd_rn(__fadd_rn(fx, lew_u(c[0], c[1])), flo0);
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = (double)px; o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)__fadd_rn(fz, flo2);
+        if (near_int(px, 2e-5f)) push_cand(p, e, vid);
+        vid++;
+      }
+      if (ey) {
+        float py = __fadd_rn(__fadd_rn(fy, lew_u(c[0], c[3])), flo1);
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)py; o[2] = (double)__fadd_rn(fz, flo2);
+        if (near_int(py, 2e-5f)) push_cand(p, e, vid);
+        vid++;
+      }
+      if (ez) {
+        float pz = __fadd_rn(__fadd_rn(fz, lew_u(c[0], c[4])), flo2);
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)pz;
+        if (near_int(pz, 2e-5f)) push_cand(p, e, vid);
+      }
+    } else {
+      // classic: FP64, mu = (iso - v1)/(v2 - v1), p = p1 + mu*(p2-p1) (src/oldcubes.c:35-38) with the
+      // direction of the LAST cube (raster order) that touches the edge: that soup copy has the
+      // highest index, so its coordinates survive the reference's weld (src/meshify.c:99-100).
+      const double iso = (double)p.c.iso;
+      const double gx = (double)(p.lo0 + x), gy = (double)(p.lo1 + y), gz = (double)(p.lo2 + z);
+      const double v0 = (double)c[0];
+      if (ex) {
+        const double v1 = (double)c[1];
+        // touching cubes, last in raster order: layer (z or z-1), then row y if valid (edge 0/4: +x) else y-1 (edge 2/6: -x)
+        const bool plus = y <= p.sy - 2;
+        double px = plus ? __dadd_rn(gx, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)))
+                         : __dadd_rn(gx + 1.0, __dmul_rn(__ddiv_rn(__dsub_rn(iso, v1), __dsub_rn(v0, v1)), -1.0));
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = px; o[1] = gy; o[2] = gz;
+        if (near_int_d(px, 2e-5)) push_cand(p, e, vid);
+        vid++;
+      }
+      if (ey) {
+        const double v1 = (double)c[3];
+        // last toucher: column x if valid (edge 3/7: from y+1 down to y, "-y") else x-1 (edge 1/5: +y)
+        const bool minus = x <= p.sx - 2;
+        double py = minus ? __dadd_rn(gy + 1.0, __dmul_rn(__ddiv_rn(__dsub_rn(iso, v1), __dsub_rn(v0, v1)), -1.0))
+                          : __dadd_rn(gy, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = gx; o[1] = py; o[2] = gz;
+        if (near_int_d(py, 2e-5)) push_cand(p, e, vid);
+        vid++;
+      }
+      if (ez) {
+        const double v1 = (double)c[4];
+        double pz = __dadd_rn(gz, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
+        double *o = e.verts + 3 * (size_t)vid;
+        o[0] = gx; o[1] = gy; o[2] = pz;
+        if (near_int_d(pz, 2e-5)) push_cand(p, e, vid);
+      }
+    }
+  }
+  if (!ntri) return;
+  // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
+  const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
+  uint32_t ev[13];
+  const bool in0 = mc_inside(p, c[0]), in1 = mc_inside(p, c[1]), in2 = mc_inside(p, c[2]), in3 = mc_inside(p, c[3]);
+  const bool in4 = mc_inside(p, c[4]), in5 = mc_inside(p, c[5]), in6 = mc_inside(p, c[6]), in7 = mc_inside(p, c[7]);
+  ev[0] = in0 != in1 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
+  ev[1] = in1 != in2 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
+  ev[2] = in3 != in2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
+  ev[3] = in0 != in3 ? mc_vidx(p, row, x, 1) : 0xffffffffu;
+  ev[4] = in4 != in5 ? mc_vidx(p, rowZ, x, 0) : 0xffffffffu;
+  ev[5] = in5 != in6 ? mc_vidx(p, rowZ, x + 1, 1) : 0xffffffffu;
+  ev[6] = in7 != in6 ? mc_vidx(p, rowYZ, x, 0) : 0xffffffffu;
+  ev[7] = in4 != in7 ? mc_vidx(p, rowZ, x, 1) : 0xffffffffu;
+  ev[8] = in0 != in4 ? mc_vidx(p, row, x, 2) : 0xffffffffu;
+  ev[9] = in1 != in5 ? mc_vidx(p, row, x + 1, 2) : 0xffffffffu;
+  ev[10] = in2 != in6 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
+  ev[11] = in3 != in7 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
+  ev[12] = 0xffffffffu;
+  if (hasc) {
+    // centroid of the cube's existing edge vertices, summed in edge-code order in f32 local
+    // coordinates, divided by the f32 count (src/MarchingCubes.c:1042-1071); then + lo in f32.
+    const float fx = (float)x, fy = (float)y, fz = (float)z;
+    const float fx1 = (float)(x + 1), fy1 = (float)(y + 1), fz1 = (float)(z + 1);
+    float sx = 0.f, sy = 0.f, sz = 0.f, u = 0.f;
+#define ACC(px_, py_, pz_) do { u = __fadd_rn(u, 1.0f); sx = __fadd_rn(sx, (px_)); sy = __fadd_rn(sy, (py_)); sz = __fadd_rn(sz, (pz_)); } while (0)
+    if (in0 != in1) ACC(__fadd_rn(fx, lew_u(c[0], c[1])), fy, fz);
+    if (in1 != in2) ACC(fx1, __fadd_rn(fy, lew_u(c[1], c[2])), fz);
+    if (in3 != in2) ACC(__fadd_rn(fx, lew_u(c[3], c[2])), fy1, fz);
+    if (in0 != in3) ACC(fx, __fadd_rn(fy, lew_u(c[0], c[3])), fz);
+    if (in4 != in5) ACC(__fadd_rn(fx, lew_u(c[4], c[5])), fy, fz1);
+    if (in5 != in6) ACC(fx1, __fadd_rn(fy, lew_u(c[5], c[6])), fz1);
+    if (in7 != in6) ACC(__fadd_rn(fx, lew_u(c[7], c[6])), fy1, fz1);
+    if (in4 != in7) ACC(fx, __fadd_rn(fy, lew_u(c[4], c[7])), fz1);
+    if (in0 != in4) ACC(fx, fy, __fadd_rn(fz, lew_u(c[0], c[4])));
+    if (in1 != in5) ACC(fx1, fy, __fadd_rn(fz, lew_u(c[1], c[5])));
+    if (in2 != in6) ACC(fx1, fy1, __fadd_rn(fz, lew_u(c[2], c[6])));
+    if (in3 != in7) ACC(fx, fy1, __fadd_rn(fz, lew_u(c[3], c[7])));
+#undef ACC
+    if (u > 0.f) { sx = __fdiv_rn(sx, u); sy = __fdiv_rn(sy, u); sz = __fdiv_rn(sz, u); }
+    const float ox = __fadd_rn(sx, flo0), oy = __fadd_rn(sy, flo1), oz = __fadd_rn(sz, flo2);
+    const uint32_t vid = e.nv_edge + __ldg(p.segc + sidx) + (uint32_t)pc;
+    double *o = e.verts + 3 * (size_t)vid;
+    o[0] = (double)ox; o[1] = (double)oy; o[2] = (double)oz;
+    if (near_int(ox, 1e-4f) || near_int(oy, 1e-4f) || near_int(oz, 1e-4f)) push_cand(p, e, vid);
+    ev[12] = vid;
+  }
+  if (p.classic && (((unsigned long long)row << 16) | (unsigned long long)x) == e.first_cube) {
+    // pts[0] of the reference's soup: first table edge of the first active cube, interpolated in
+    // THAT cube's direction (src/oldcubes.c:428-451, :22-40)
+    const int a0 = p.tab[off];
+    const int ca = MC_EDGE_A[a0], cb = MC_EDGE_B[a0];
+    const double iso = (double)p.c.iso;
+    const double mu = __ddiv_rn(__dsub_rn(iso, (double)c[ca]), __dsub_rn((double)c[cb], (double)c[ca]));
+    const double ax = (double)(p.lo0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + z + (ca >> 2));
+    const double bx = (double)(p.lo0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + z + (cb >> 2));
+    p.sc->pts0[0] = __dadd_rn(ax, __dmul_rn(mu, bx - ax));
+    p.sc->pts0[1] = __dadd_rn(ay, __dmul_rn(mu, by - ay));
+    p.sc->pts0[2] = __dadd_rn(az, __dmul_rn(mu, bz - az));
+  }
+  // ---- triangles ----
+  int *t = e.tris + 3 * ((size_t)__ldg(p.segt + sidx) + (size_t)pt);
+  const signed char *tl = p.tab + off;
+  for (int k = 0; k < ntri; k++) {
+    int a = tl[3 * k], b = tl[3 * k + 1], cc = tl[3 * k + 2];
+    if (p.classic) { t[3 * k] = (int)ev[a]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[cc]; }
+    else { t[3 * k] = (int)ev[cc]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[a]; }  // reversed (:1134-1136)
+  }
+}
+
+static int upload_tables(b2m_ctx *ctx) {
+  if (ctx->tables_ready) return B2M_OK;
+  extern const signed char *b2m_mc_table_blob(void);
+  B2M_TRY(b2m_reserve(ctx, BUF_TABLES, MCT_TOTAL));
+  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_TABLES].p, b2m_mc_table_blob(), MCT_TOTAL, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->tables_ready = 1;
+  return B2M_OK;
+}
+
+int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_front_out *fo, b2m_mesh_dev *mesh) {
+  B2M_TRY(upload_tables(ctx));
+  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  mc_params p;
+  memset(&p, 0, sizeof(p));
+  p.c.S = fo->S; p.c.fill = fo->fill; p.c.keep = fo->keep;
+  p.c.nx = g.nx; p.c.ny = g.ny; p.c.nz = g.nz; p.c.w = g.w;
+  p.c.iso = fo->iso; p.c.mn = fo->vmin; p.c.edge_max = fo->edge_max;
+  p.classic = o->backend == B2M_BACKEND_CLASSIC;
+  p.original_mc = o->original_mc != 0;
+  p.lo0 = fo->lo[0]; p.lo1 = fo->lo[1]; p.lo2 = fo->lo[2];
+  if (p.classic) {  // voxels lo .. hi-1 (src/oldcubes.c:475-478)
+    p.sx = fo->hi[0] - fo->lo[0]; p.sy = fo->hi[1] - fo->lo[1]; p.sz = fo->hi[2] - fo->lo[2];
+  } else {          // hi-lo+1 voxels: one more than the volume can supply when hi == dim (src/MarchingCubes.c:1088-1090)
+    p.sx = fo->hi[0] - fo->lo[0] + 1; p.sy = fo->hi[1] - fo->lo[1] + 1; p.sz = fo->hi[2] - fo->lo[2] + 1;
+  }
+  mesh->nv = mesh->nt = mesh->nv_edge = mesh->ncand = 0;
+  if (p.sx < 2 || p.sy < 2 || p.sz < 2) return B2M_FAIL;
+  p.segs = (p.sx + 31) / 32;
+  p.tab = b2m_ptr<signed char>(ctx, BUF_TABLES);
+  p.sc = d_sc;
+  // pad value: (min of the composed volume) - iso (src/MarchingCubes.c:1097-1102).  It is only ever
+  // read when hi == dim on some axis, and it only matters when a face voxel can be bright, i.e.
+  // when edge_max >= iso; otherwise any "outside" value gives the same mesh and we skip the
+  // extra reduction pass over the volume.
+  p.pad = fo->vmin - fo->iso;
+  if (!p.classic) {
+    bool touched = fo->hi[0] == g.nx || fo->hi[1] == g.ny || fo->hi[2] == g.nz;
+    if (touched && !(fo->edge_max < fo->iso)) {
+      ctx->h_scalars->cmin_enc = 0xffffffffu;
+      CU_TRY(cudaMemcpyAsync(&d_sc->cmin_enc, &ctx->h_scalars->cmin_enc, 4, cudaMemcpyHostToDevice, ctx->stream));
+      B2M_TRY(b2m_compose_materialize(ctx, g, fo, nullptr, nullptr, d_sc, 1));
+      B2M_TRY(b2m_fetch_scalars(ctx));
+      p.pad = f32_dec(ctx->h_scalars->cmin_enc) - fo->iso;
+    }
+  }
+  const size_t nrows = (size_t)p.sy * p.sz;
+  const size_t nseg = nrows * p.segs;
+  const size_t nvox = nrows * p.sx;
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG, nseg * sizeof(uint4)));
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, nseg * 3 * sizeof(uint32_t)));
+  p.segbits = b2m_ptr<uint4>(ctx, BUF_SEG);
+  p.segv = b2m_ptr<uint32_t>(ctx, BUF_SEG2);
+  p.segt = p.segv + nseg;
+  p.segc = p.segt + nseg;
+  size_t cap = nvox / 8 + 65536;
+  if (cap > nvox) cap = nvox;
+  unsigned n_active = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    B2M_TRY(b2m_reserve(ctx, BUF_ACTIVE, cap * sizeof(uint4)));
+    p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
+    p.active_cap = (unsigned)cap;
+    CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
+    dim3 grid(p.segs, b2m_cdiv(p.sy, MCA_ROWS), p.sz);
+    k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p);
+    B2M_LAUNCHED(ctx);
+    CU_TRY(cudaGetLastError());
+    if (attempt == 0) {
+      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
+      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segt, p.segt, nseg, &d_sc->tot_t));
+      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segc, p.segc, nseg, &d_sc->tot_c));
+    }
+    B2M_TRY(b2m_fetch_scalars(ctx));
+    n_active = ctx->h_scalars->n_active;
+    if (n_active <= cap) break;
+    if (attempt == 1) { b2m_set_error("mc: active list overflow"); return B2M_ECUDA; }
+    // rare: more active voxels than the first guess; redo the classification with an exact capacity.
+    // (segment counts were scanned in place, so they are recomputed and rescanned as well)
+    cap = n_active;
+    B2M_TRY(b2m_reserve(ctx, BUF_ACTIVE, cap * sizeof(uint4)));
+    p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
+    p.active_cap = (unsigned)cap;
+    CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
+    k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p);
+    B2M_LAUNCHED(ctx);
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segt, p.segt, nseg, &d_sc->tot_t));
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segc, p.segc, nseg, &d_sc->tot_c));
+    B2M_TRY(b2m_fetch_scalars(ctx));
+    n_active = ctx->h_scalars->n_active;
+    break;
+  }
+  const unsigned tot_v = ctx->h_scalars->tot_v, tot_t = ctx->h_scalars->tot_t, tot_c = ctx->h_scalars->tot_c;
+  mesh->nv_edge = tot_v;
+  mesh->nv = tot_v + tot_c;
+  mesh->nt = tot_t;
+  if ((unsigned long long)tot_v + tot_c > 0x7fffffffull || tot_t > 0x7fffffffu) {
+    b2m_set_error("mesh exceeds the int counts of the meshify() API");
+    return B2M_EARG;
+  }
+  // reference failure rule: < 3 vertices or < 1 triangle (src/MarchingCubes.c:1119, src/oldcubes.c:497)
+  if (p.classic ? (3ull * tot_t < 3) : (mesh->nv < 3 || tot_t < 1)) return B2M_FAIL;
+  B2M_TRY(b2m_reserve(ctx, BUF_VERTS, (size_t)mesh->nv * 24));
+  B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)mesh->nt * 12));
+  size_t ccap = (size_t)mesh->nv / 16 + 4096;
+  mc_emit_params e;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    B2M_TRY(b2m_reserve(ctx, BUF_CAND, ccap * 4));
+    e.verts = b2m_ptr<double>(ctx, BUF_VERTS);
+    e.tris = b2m_ptr<int>(ctx, BUF_TRIS);
+    e.cand = b2m_ptr<uint32_t>(ctx, BUF_CAND);
+    e.cand_cap = (unsigned)ccap;
+    e.n_active = n_active;
+    e.nv_edge = tot_v;
+    e.first_cube = ctx->h_scalars->first_cube;
+    CU_TRY(cudaMemsetAsync(&d_sc->n_cand, 0, 4, ctx->stream));
+    k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e);
+    B2M_LAUNCHED(ctx);
+    CU_TRY(cudaGetLastError());
+    B2M_TRY(b2m_fetch_scalars(ctx));
+    if (ctx->h_scalars->n_cand <= ccap) break;
+    ccap = ctx->h_scalars->n_cand;
+  }
+  mesh->ncand = ctx->h_scalars->n_cand;
+  mesh->verts = b2m_ptr<double>(ctx, BUF_VERTS);
+  mesh->tris = b2m_ptr<int>(ctx, BUF_TRIS);
+  return B2M_OK;
+}

@@ -1,0 +1,303 @@
+// pipeline.cu — orchestration of the hot path behind the C ABI (include/b2m.h):
+// b2m_meshify_device() = the reference's meshify() (/root/reference/src/meshify.c:286-389) on a
+// device-resident volume; b2m_meshify_host() adds the H2D / D2H copies; stage hooks for parity.
+#include <limits.h>
+
+#include "common.cuh"
+
+extern "C" int b2m_get_default_backend(void);
+
+static int stage_begin(b2m_ctx *ctx, int st) {
+  CU_TRY(cudaEventRecord(ctx->ev[2 * st], ctx->stream));
+  return B2M_OK;
+}
+static int stage_end(b2m_ctx *ctx, int st) {
+  CU_TRY(cudaEventRecord(ctx->ev[2 * st + 1], ctx->stream));
+  ctx->ev_mask |= 1u << st;
+  return B2M_OK;
+}
+
+static int collect_times(b2m_ctx *ctx, b2m_result *res) {
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int st = 0; st < B2M_NSTAGE; st++) {
+    res->ms[st] = 0.f;
+    if (ctx->ev_mask & (1u << st)) CU_TRY(cudaEventElapsedTime(&res->ms[st], ctx->ev[2 * st], ctx->ev[2 * st + 1]));
+  }
+  res->launches = ctx->launches;
+  return B2M_OK;
+}
+
+static int check_dims(const int64_t dims[3]) {
+  for (int a = 0; a < 3; a++)
+    if (dims[a] < 1 || dims[a] > 32767) {
+      b2m_set_error("dims[%d] = %lld outside 1..32767 (meshify.h uses short dim[3])", a, (long long)dims[a]);
+      return B2M_EARG;
+    }
+  if ((long long)dims[0] * dims[1] * dims[2] > 0x7fffffffll) {
+    b2m_set_error("more than 2^31-1 voxels: the meshify() API counts vertices/voxels in int");
+    return B2M_EARG;
+  }
+  return B2M_OK;
+}
+
+// smooth -> range -> isolevel sanity -> CC masks -> bright bbox.  src/meshify.c:299-371
+int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m_opts *o, b2m_front_out *fo,
+                  b2m_result *res) {
+  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  b2m_scalars *h = ctx->h_scalars;
+  memset(h, 0, sizeof(*h));
+  h->vmin_enc = 0xffffffffu; h->vmax_enc = 0u; h->cmin_enc = 0xffffffffu;
+  for (int a = 0; a < 3; a++) { h->lo[a] = INT_MAX; h->hi[a] = -1; }
+  h->first_cube = ~0ull;
+  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+
+  const bool smooth = o->pre_smooth && g.nx >= 5 && g.ny >= 5 && g.nz >= 5;  // meshify.c:171
+  if (smooth) {
+    B2M_TRY(stage_begin(ctx, B2M_T_SMOOTH));
+    B2M_TRY(b2m_reserve(ctx, BUF_SMOOTH, (size_t)g.n * 4));
+    float *S = b2m_ptr<float>(ctx, BUF_SMOOTH);
+    B2M_TRY(b2m_smooth_run(ctx, d_img, S, g, d_sc));  // range reduction fused
+    fo->S = S;
+    B2M_TRY(stage_end(ctx, B2M_T_SMOOTH));
+  } else {
+    B2M_TRY(stage_begin(ctx, B2M_T_RANGE));
+    fo->S = d_img;
+    B2M_TRY(b2m_minmax_run(ctx, d_img, g, d_sc));
+    B2M_TRY(stage_end(ctx, B2M_T_RANGE));
+  }
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  const float mn = f32_dec(h->vmin_enc), mx = f32_dec(h->vmax_enc);
+  if (o->verbose && smooth) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_SMOOTH], ctx->ev[2 * B2M_T_SMOOTH + 1]);
+    printf("pre-smooth: %ld ms\n", lroundf(ms));
+  }
+  if (mn == mx) {  // meshify.c:312-315
+    printf("Error: No variability in image intensity.\n");
+    return B2M_FAIL;
+  }
+  float iso = o->isolevel;
+  fo->iso_reset = 0;
+  if (iso <= mn || iso > mx) {  // meshify.c:316-319
+    iso = (float)(0.5 * (double)(mn + mx));
+    fo->iso_reset = 1;
+    printf("Suggested isolevel out of range. Intensity range %g..%g, setting isolevel to %g\n", mn, mx, iso);
+  }
+  if (o->verbose) printf("intensity range %g..%g, isolevel %g\n", mn, mx, iso);
+  fo->iso = iso; fo->vmin = mn; fo->vmax = mx;
+  fo->edge_max = (float)(0.75 * (double)(mn + iso));  // meshify.c:346: f32 add, double multiply, f32 store
+
+  const bool cc = o->only_largest || o->fill_bubbles;
+  B2M_TRY(stage_begin(ctx, cc ? B2M_T_CC : B2M_T_COMPOSE));
+  B2M_TRY(b2m_cc_run(ctx, g, o, d_sc, fo));
+  B2M_TRY(stage_end(ctx, cc ? B2M_T_CC : B2M_T_COMPOSE));
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  if (o->verbose && cc) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_CC], ctx->ev[2 * B2M_T_CC + 1]);
+    printf("voxel clustering (largest cluster, bubbles): %ld ms\n", lroundf(ms));
+  }
+  const int dims[3] = {g.nx, g.ny, g.nz};
+  for (int a = 0; a < 3; a++) {  // meshify.c:368-371
+    int lo = h->lo[a], hi = h->hi[a];
+    if (hi < 0) { lo = dims[a]; hi = 0; }  // no bright voxel at all (cannot happen: iso <= max)
+    fo->lo[a] = lo - 1 > 0 ? lo - 1 : 0;
+    fo->hi[a] = hi + 2 < dims[a] ? hi + 2 : dims[a];
+  }
+  if (res) {
+    res->iso_used = iso; res->vmin = mn; res->vmax = mx; res->iso_reset = fo->iso_reset;
+    for (int a = 0; a < 3; a++) { res->lo[a] = fo->lo[a]; res->hi[a] = fo->hi[a]; }
+  }
+  return B2M_OK;
+}
+
+static int meshify_device_impl(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *o,
+                               b2m_result *res) {
+  b2m_geom g = b2m_make_geom(dims);
+  b2m_front_out fo;
+  memset(&fo, 0, sizeof(fo));
+  B2M_TRY(stage_begin(ctx, B2M_T_TOTAL));
+  B2M_TRY(b2m_front_run(ctx, d_img, g, o, &fo, res));
+  b2m_mesh_dev mesh;
+  memset(&mesh, 0, sizeof(mesh));
+  B2M_TRY(stage_begin(ctx, B2M_T_MC));
+  int rc = b2m_mc_run(ctx, g, o, &fo, &mesh);
+  if (rc != B2M_OK) {
+    if (rc == B2M_FAIL && o->backend == B2M_BACKEND_CLASSIC)
+      printf("marching cubes failed to identify triangles with an isolevel of %g\n", fo.iso);
+    return rc;
+  }
+  B2M_TRY(stage_end(ctx, B2M_T_MC));
+  res->pre_nverts = o->backend == B2M_BACKEND_CLASSIC ? (int)(3 * mesh.nt) : (int)mesh.nv;
+  res->pre_ntris = (int)mesh.nt;
+  if (o->verbose) {
+    float ms = 0.f;
+    cudaEventSynchronize(ctx->ev[2 * B2M_T_MC + 1]);
+    cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_MC], ctx->ev[2 * B2M_T_MC + 1]);
+    printf("marching cubes (%dx%dx%d): %ld ms\n", g.nx, g.ny, g.nz, lroundf(ms));
+  }
+  B2M_TRY(b2m_weld_run(ctx, &mesh, 0, o->backend, res));
+  ctx->ev_mask |= (1u << B2M_T_WELD) | (1u << B2M_T_DEGEN);
+  B2M_TRY(stage_end(ctx, B2M_T_TOTAL));
+  B2M_TRY(collect_times(ctx, res));
+  if (o->verbose) {
+    if (res->nmerged) printf("vertex welding %d -> %d: %ld ms\n", res->pre_nverts, res->nverts, lroundf(res->ms[B2M_T_WELD]));
+    else printf("Unify vertices found no shared vertices\n");
+    if (res->ndegenerate)
+      printf("remove degenerate triangles %d -> %d: %ld ms\n", res->pre_ntris, res->ntris, lroundf(res->ms[B2M_T_DEGEN]));
+  }
+  if (res->nverts < 3) return B2M_FAIL;  // meshify.c:382
+  return B2M_OK;
+}
+
+extern "C" int b2m_meshify_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts,
+                                  b2m_result *res) {
+  if (!ctx || !d_img || !dims || !opts || !res) { b2m_set_error("null argument"); return B2M_EARG; }
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  memset(res, 0, sizeof(*res));
+  ctx->launches = 0;
+  ctx->ev_mask = 0;
+  int rc = meshify_device_impl(ctx, d_img, dims, opts, res);
+  if (rc != B2M_OK) cudaStreamSynchronize(ctx->stream);
+  return rc;
+}
+
+extern "C" int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris) {
+  if (!ctx || !res) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  if (h_verts && res->nverts)
+    CU_TRY(cudaMemcpyAsync(h_verts, res->d_verts, (size_t)res->nverts * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_tris && res->ntris)
+    CU_TRY(cudaMemcpyAsync(h_tris, res->d_tris, (size_t)res->ntris * 12, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t dims[3], const b2m_opts *opts,
+                                void **verts, void **tris, b2m_result *res) {
+  if (!ctx || !h_img || !dims || !opts || !res || !verts || !tris) { b2m_set_error("null argument"); return B2M_EARG; }
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  B2M_TRY(b2m_reserve(ctx, BUF_INPUT, n * 4));
+  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_INPUT].p, h_img, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  B2M_TRY(b2m_meshify_device(ctx, b2m_ptr<float>(ctx, BUF_INPUT), dims, opts, res));
+  void *v = malloc((size_t)res->nverts * 24 + 8), *t = malloc((size_t)res->ntris * 12 + 8);
+  if (!v || !t) { free(v); free(t); b2m_set_error("malloc of the output mesh failed"); return B2M_ENOMEM; }
+  int rc = b2m_fetch_mesh(ctx, res, v, t);
+  if (rc != B2M_OK) { free(v); free(t); return rc; }
+  *verts = v;
+  *tris = t;
+  return B2M_OK;
+}
+
+// ---- stage hooks ---------------------------------------------------------------------------------
+extern "C" int b2m_stage_smooth(b2m_ctx *ctx, const float *d_in, float *d_out, const int64_t dims[3]) {
+  if (!ctx || !d_in || !d_out || !dims) return B2M_EARG;
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  b2m_geom g = b2m_make_geom(dims);
+  if (g.nx < 5 || g.ny < 5 || g.nz < 5) {
+    CU_TRY(cudaMemcpyAsync(d_out, d_in, (size_t)g.n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2M_FAIL;
+  }
+  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  b2m_scalars *h = ctx->h_scalars;
+  memset(h, 0, sizeof(*h));
+  h->vmin_enc = 0xffffffffu;
+  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+  B2M_TRY(b2m_smooth_run(ctx, d_in, d_out, g, d_sc));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+extern "C" int b2m_stage_front(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts,
+                               float *d_composed, uint8_t *d_mask, b2m_result *res) {
+  if (!ctx || !d_img || !dims || !opts || !res) return B2M_EARG;
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  memset(res, 0, sizeof(*res));
+  ctx->launches = 0;
+  ctx->ev_mask = 0;
+  b2m_geom g = b2m_make_geom(dims);
+  b2m_front_out fo;
+  memset(&fo, 0, sizeof(fo));
+  B2M_TRY(b2m_front_run(ctx, d_img, g, opts, &fo, res));
+  if (d_composed || d_mask)
+    B2M_TRY(b2m_compose_materialize(ctx, g, &fo, d_composed, d_mask, b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS), 0));
+  B2M_TRY(collect_times(ctx, res));
+  return B2M_OK;
+}
+
+extern "C" int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const int lo[3], const int hi[3],
+                            const b2m_opts *opts, b2m_result *res) {
+  if (!ctx || !d_img || !dims || !opts || !res || !lo || !hi) return B2M_EARG;
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  memset(res, 0, sizeof(*res));
+  ctx->launches = 0;
+  ctx->ev_mask = 0;
+  b2m_geom g = b2m_make_geom(dims);
+  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  b2m_scalars *h = ctx->h_scalars;
+  memset(h, 0, sizeof(*h));
+  h->vmin_enc = 0xffffffffu; h->cmin_enc = 0xffffffffu; h->first_cube = ~0ull;
+  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+  // the volume is taken as already composed: no fill/keep masks, no darkening (edge_max = +inf);
+  // the pad value needs the true minimum (src/MarchingCubes.c:1097-1100)
+  B2M_TRY(b2m_minmax_run(ctx, d_img, g, d_sc));
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  b2m_front_out fo;
+  memset(&fo, 0, sizeof(fo));
+  fo.S = d_img;
+  fo.iso = opts->isolevel;
+  fo.vmin = f32_dec(h->vmin_enc);
+  fo.vmax = f32_dec(h->vmax_enc);
+  fo.edge_max = INFINITY;
+  for (int a = 0; a < 3; a++) {
+    if (lo[a] < 0 || hi[a] > dims[a] || lo[a] > hi[a]) { b2m_set_error("bad bbox"); return B2M_EARG; }
+    fo.lo[a] = lo[a]; fo.hi[a] = hi[a];
+  }
+  b2m_mesh_dev mesh;
+  memset(&mesh, 0, sizeof(mesh));
+  B2M_TRY(stage_begin(ctx, B2M_T_MC));
+  int rc = b2m_mc_run(ctx, g, opts, &fo, &mesh);
+  if (rc != B2M_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
+  B2M_TRY(stage_end(ctx, B2M_T_MC));
+  res->nverts = (int)mesh.nv; res->ntris = (int)mesh.nt;
+  res->pre_nverts = (int)mesh.nv; res->pre_ntris = (int)mesh.nt;
+  res->d_verts = mesh.verts; res->d_tris = mesh.tris;
+  res->iso_used = fo.iso; res->vmin = fo.vmin; res->vmax = fo.vmax;
+  B2M_TRY(collect_times(ctx, res));
+  return B2M_OK;
+}
+
+extern "C" int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *nv, int *nt) {
+  if (!ctx || !h_verts || !h_tris || !nv || !nt || *nv < 1 || *nt < 1) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  ctx->launches = 0;
+  ctx->ev_mask = 0;
+  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  CU_TRY(cudaMemsetAsync(ctx->buf[BUF_SCALARS].p, 0, sizeof(b2m_scalars), ctx->stream));
+  B2M_TRY(b2m_reserve(ctx, BUF_VERTS, (size_t)*nv * 24));
+  B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)*nt * 12));
+  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_VERTS].p, h_verts, (size_t)*nv * 24, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_TRIS].p, h_tris, (size_t)*nt * 12, cudaMemcpyHostToDevice, ctx->stream));
+  b2m_mesh_dev mesh;
+  memset(&mesh, 0, sizeof(mesh));
+  mesh.verts = b2m_ptr<double>(ctx, BUF_VERTS);
+  mesh.tris = b2m_ptr<int>(ctx, BUF_TRIS);
+  mesh.nv = (unsigned)*nv; mesh.nt = (unsigned)*nt; mesh.nv_edge = mesh.nv;
+  b2m_result res;
+  memset(&res, 0, sizeof(res));
+  B2M_TRY(b2m_weld_run(ctx, &mesh, 1, B2M_BACKEND_LEWINER, &res));
+  B2M_TRY(b2m_fetch_mesh(ctx, &res, h_verts, h_tris));
+  *nv = res.nverts;
+  *nt = res.ntris;
+  return B2M_OK;
+}

@@ -1,0 +1,233 @@
+"""ctypes binding of libb2m.so — the host-side mirror of the reference interface in Python.
+
+`Engine.meshify()` has the argument meaning of the reference's meshify()
+(/root/reference/src/meshify.h:9): volume, isolevel, originalMC, preSmooth, onlyLargest,
+fillBubbles; it returns (verts[np,3] f64, tris[nt,3] i32) like the reference's malloc'd vec3d/vec3i
+arrays.  There is no CPU fallback: constructing an Engine without a CUDA device raises.
+"""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIBPATH = HERE / "libb2m.so"
+
+BACKEND_LEWINER, BACKEND_CLASSIC = 0, 1
+STAGES = ("smooth", "range", "cc", "compose", "mc", "weld", "degen", "total")
+
+
+class Opts(C.Structure):
+    _fields_ = [("isolevel", C.c_float), ("original_mc", C.c_int), ("pre_smooth", C.c_int), ("only_largest", C.c_int),
+                ("fill_bubbles", C.c_int), ("backend", C.c_int), ("verbose", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("d_verts", C.c_void_p), ("d_tris", C.c_void_p), ("nverts", C.c_int), ("ntris", C.c_int),
+                ("pre_nverts", C.c_int), ("pre_ntris", C.c_int), ("nmerged", C.c_int), ("ndegenerate", C.c_int),
+                ("iso_used", C.c_float), ("vmin", C.c_float), ("vmax", C.c_float), ("lo", C.c_int * 3),
+                ("hi", C.c_int * 3), ("iso_reset", C.c_int), ("ms", C.c_float * 8), ("launches", C.c_uint64)]
+
+    def times(self):
+        return {k: float(self.ms[i]) for i, k in enumerate(STAGES)}
+
+
+class B2MError(RuntimeError):
+    pass
+
+
+class MeshifyFailure(B2MError):
+    """the reference's EXIT_FAILURE (no variability, empty mesh, < 3 vertices)"""
+
+
+_lib = None
+
+
+def load():
+    """dlopen libb2m.so (must have been built: python -m nii2mesh_b200.build). Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIBPATH.exists():
+        raise B2MError(f"{LIBPATH} is missing: build it with `python -m nii2mesh_b200.build` (no CPU fallback exists)")
+    L = C.CDLL(str(LIBPATH))
+    vp, i64p = C.c_void_p, C.POINTER(C.c_int64)
+    L.b2m_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.b2m_destroy.argtypes = [vp]
+    L.b2m_destroy.restype = None
+    L.b2m_last_error.restype = C.c_char_p
+    L.b2m_version.restype = C.c_char_p
+    L.b2m_set_default_backend.argtypes = [C.c_int]
+    L.b2m_set_default_backend.restype = None
+    L.b2m_dev_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.b2m_dev_free.argtypes = [vp]
+    L.b2m_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.b2m_host_free.argtypes = [vp]
+    L.b2m_h2d.argtypes = [vp, vp, vp, C.c_size_t]
+    L.b2m_d2h.argtypes = [vp, vp, vp, C.c_size_t]
+    L.b2m_sync.argtypes = [vp]
+    L.b2m_flush_l2.argtypes = [vp]
+    L.b2m_meshify_device.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(Result)]
+    L.b2m_meshify_host.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
+    L.b2m_fetch_mesh.argtypes = [vp, C.POINTER(Result), vp, vp]
+    L.b2m_stage_smooth.argtypes = [vp, vp, vp, i64p]
+    L.b2m_stage_front.argtypes = [vp, vp, i64p, C.POINTER(Opts), vp, vp, C.POINTER(Result)]
+    L.b2m_stage_mc.argtypes = [vp, vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Opts), C.POINTER(Result)]
+    L.b2m_stage_weld.argtypes = [vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [C.c_void_p]
+
+
+def _dims(vol_shape):
+    nz, ny, nx = vol_shape
+    return (C.c_int64 * 3)(nx, ny, nz)
+
+
+class DeviceVolume:
+    """a float32 volume resident in device memory"""
+
+    def __init__(self, eng, shape, ptr):
+        self.eng, self.shape, self.ptr = eng, tuple(shape), ptr
+        self.nbytes = int(np.prod(shape)) * 4
+
+    def free(self):
+        if self.ptr:
+            self.eng.lib.b2m_dev_free(self.ptr)
+            self.ptr = None
+
+    def to_host(self):
+        out = np.empty(self.shape, np.float32)
+        self.eng._chk(self.eng.lib.b2m_d2h(self.eng.ctx, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = load()
+        self.ctx = C.c_void_p()
+        rc = self.lib.b2m_create(C.byref(self.ctx), device)
+        if rc != 0:
+            raise B2MError(f"b2m_create failed ({rc}): {self.lib.b2m_last_error().decode()}")
+
+    def close(self):
+        if self.ctx:
+            self.lib.b2m_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc == 1:
+            raise MeshifyFailure("meshify failed (reference EXIT_FAILURE semantics)")
+        if rc != 0:
+            raise B2MError(f"libb2m error {rc}: {self.lib.b2m_last_error().decode()}")
+
+    # ---- memory ----
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self._chk(self.lib.b2m_dev_alloc(C.byref(p), nbytes))
+        return p
+
+    def upload(self, vol):
+        vol = np.ascontiguousarray(vol, dtype=np.float32)
+        p = self.alloc(vol.nbytes)
+        self._chk(self.lib.b2m_h2d(self.ctx, p, vol.ctypes.data, vol.nbytes))
+        return DeviceVolume(self, vol.shape, p)
+
+    def download(self, ptr, shape, dtype):
+        out = np.empty(shape, dtype)
+        self._chk(self.lib.b2m_d2h(self.ctx, out.ctypes.data, ptr, out.nbytes))
+        return out
+
+    @staticmethod
+    def _opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend, verbose=False):
+        return Opts(float(iso), int(original_mc), int(pre_smooth), int(only_largest), int(fill_bubbles), int(backend),
+                    int(verbose))
+
+    # ---- hot path ----
+    def meshify_device(self, dvol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False,
+                       backend=BACKEND_LEWINER, fetch=True, verbose=False):
+        """volume already on the device; returns (verts, tris, Result) (verts/tris None if fetch=False)"""
+        o = self._opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend, verbose)
+        r = Result()
+        self._chk(self.lib.b2m_meshify_device(self.ctx, dvol.ptr, _dims(dvol.shape), C.byref(o), C.byref(r)))
+        if not fetch:
+            return None, None, r
+        v = np.empty((r.nverts, 3), np.float64)
+        t = np.empty((r.ntris, 3), np.int32)
+        self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
+        return v, t, r
+
+    def meshify(self, vol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False,
+                backend=BACKEND_LEWINER, verbose=False):
+        """host volume in, host mesh out (H2D + device pipeline + D2H), like the reference's meshify()."""
+        vol = np.ascontiguousarray(vol, dtype=np.float32)
+        o = self._opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend, verbose)
+        r = Result()
+        pv, pt = C.c_void_p(), C.c_void_p()
+        self._chk(self.lib.b2m_meshify_host(self.ctx, vol.ctypes.data, _dims(vol.shape), C.byref(o), C.byref(pv),
+                                            C.byref(pt), C.byref(r)))
+        v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(r.nverts, 3)).copy()
+        t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(r.ntris, 3)).copy()
+        _libc.free(pv)
+        _libc.free(pt)
+        return v, t, r
+
+    # ---- stage hooks ----
+    def smooth(self, vol):
+        d_in = self.upload(vol)
+        d_out = DeviceVolume(self, d_in.shape, self.alloc(d_in.nbytes))
+        rc = self.lib.b2m_stage_smooth(self.ctx, d_in.ptr, d_out.ptr, _dims(d_in.shape))
+        if rc not in (0, 1):
+            self._chk(rc)
+        out = d_out.to_host()
+        d_in.free()
+        d_out.free()
+        return out
+
+    def front(self, vol, iso, pre_smooth=True, only_largest=True, fill_bubbles=False):
+        """returns dict(img=composed volume, mask (uint8), iso, lo, hi, mn, mx)"""
+        d_in = self.upload(vol)
+        n = int(np.prod(d_in.shape))
+        d_c = self.alloc(n * 4)
+        d_m = self.alloc(n)
+        o = self._opts(iso, 0, pre_smooth, only_largest, fill_bubbles, 0)
+        r = Result()
+        try:
+            self._chk(self.lib.b2m_stage_front(self.ctx, d_in.ptr, _dims(d_in.shape), C.byref(o), d_c, d_m, C.byref(r)))
+            img = self.download(d_c, d_in.shape, np.float32)
+            mask = self.download(d_m, d_in.shape, np.uint8)
+        finally:
+            d_in.free()
+            self.lib.b2m_dev_free(d_c)
+            self.lib.b2m_dev_free(d_m)
+        return dict(img=img, mask=mask, iso=r.iso_used, lo=list(r.lo), hi=list(r.hi), mn=r.vmin, mx=r.vmax, res=r)
+
+    def mc(self, img, lo, hi, iso, original_mc=0, backend=BACKEND_LEWINER):
+        d_in = self.upload(img)
+        o = self._opts(iso, original_mc, 0, 0, 0, backend)
+        r = Result()
+        try:
+            self._chk(self.lib.b2m_stage_mc(self.ctx, d_in.ptr, _dims(d_in.shape), (C.c_int * 3)(*lo), (C.c_int * 3)(*hi),
+                                            C.byref(o), C.byref(r)))
+            v = np.empty((r.nverts, 3), np.float64)
+            t = np.empty((r.ntris, 3), np.int32)
+            self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
+        finally:
+            d_in.free()
+        return v, t, r
+
+    def weld(self, verts, tris):
+        v = np.ascontiguousarray(verts, dtype=np.float64).copy()
+        t = np.ascontiguousarray(tris, dtype=np.int32).copy()
+        nv, nt = C.c_int(len(v)), C.c_int(len(t))
+        self._chk(self.lib.b2m_stage_weld(self.ctx, v.ctypes.data, t.ctypes.data, C.byref(nv), C.byref(nt)))
+        return v[:nv.value].copy(), t[:nt.value].copy()
