@@ -1,0 +1,294 @@
+#!/usr/bin/env python3
+"""bench.py — Gvoxels/s of the meshify() hot path (smooth + CC + MC + weld) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 1024] [--impl reference]
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic G1024
+"gyroid + bumps" 1024^3 float32 volume, Lewiner MC33, -p 1 -l 1 -b 1, isolevel 0.  A step is one
+whole meshify() pass over the volume.
+
+  value : volume resident in HBM, mesh left in HBM; K steps between one CUDA-event pair on the
+          library's stream (b2m_timer_start/stop), barrier + synchronize on both sides, max over ranks.
+  e2e   : the same through the reference-facing C entry point meshify() (include/meshify.h) with a
+          pinned HOST volume in and malloc()'d HOST mesh out, copies inside the timed region.
+  roofline : the dominant kernel of the step, from per-launch CUDA-event pairs recorded live during
+          the timed steps (b2m_set_profile); algorithmic bytes per launch are in KERNEL_BYTES below
+          (DESIGN.md §Kernels), peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
+  cpu_baseline : the unmodified reference (oracle/_ref, built by oracle/build_ref.sh) on a bounded
+          sample (G384, same generator and flags), 1 core — the path has no threading.
+  --impl reference : only that CPU reference, each step one G256 volume of the same workload.
+N > 1: one process per GPU (torchrun), NCCL for the barrier and the max-over-ranks only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+FLAGS = dict(original_mc=0, pre_smooth=1, only_largest=1, fill_bubbles=1, backend=0)
+ISO = 0.0
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_bytes(name, n, nv, nt, nwords):
+    """ALGORITHMIC bytes one launch of kernel `name` must move: n voxels f32,
+    nwords 32-voxel bit words, nv/nt mesh vertices/triangles."""
+    table = {
+        "smooth3": 8 * n,                        # R V + W V
+        "minmax": 4 * n,
+        "threshold": 4 * n + nwords * 4,         # R V + W bits
+        "mc_classify": 4 * n,                    # R V (composed on the fly)
+        "mc_emit": 24 * nv + 12 * nt,            # surface term S
+        "tri_remap_degen": 12 * nt + 72 * nt + 4 * nt,
+        "cc_link": nwords * 4, "cc_flatten": nwords * 4, "cc_init": nwords * 4, "cc_best": nwords * 4,
+        "cc_select": nwords * 8, "dilate_bbox": nwords * 12,
+    }
+    return table.get(name)
+
+
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:  # noqa: BLE001
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def ref_meshify_time(n, steps, warmup):
+    """time the unmodified reference (oracle/_ref) on G<n>; falls back to the oracle port"""
+    from nii2mesh_b200 import synth
+    import oracle
+    vol = synth.gyroid(n)
+    if oracle.ref_available("lewiner"):
+        R, kind = oracle.Ref("lewiner"), "reference"
+        fn = lambda: R.meshify(vol, ISO, 0, 1, 1, 1)  # noqa: E731
+    else:
+        O, kind = oracle.Oracle(), "port"
+        fn = lambda: O.meshify(vol, ISO, 0, 1, 1, 1, 0)  # noqa: E731
+    for _ in range(warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = fn()
+    dt = (time.perf_counter() - t0) / steps
+    assert r["rc"] == 0
+    return dt, kind, len(r["verts"]), len(r["tris"])
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = 256
+    dt, kind, nv, nt = ref_meshify_time(n, args.steps, min(args.warmup, 1))
+    val = n ** 3 / dt / 1e9
+    out = {"impl": "reference", "metric": "Gvoxels/s meshify (smooth+CC+MC+weld)", "value": val, "unit": "Gvoxels/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "G1024 gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
+                                  f"each step = one G{n} volume of the same generator (bounded sample)"},
+           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": 1, "kind": kind,
+                            "sample": f"G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris; meshify() is single-threaded"},
+           "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--impl", default="b2m")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from nii2mesh_b200 import lib, synth
+    eng = lib.Engine(local)
+    n = args.size
+    N = n ** 3
+    tile = synth.gyroid_tile(128)
+    dvol = eng.tiled_volume(tile, (n, n, n))
+
+    # ---- device-resident throughput -------------------------------------------------------------
+    for _ in range(args.warmup):
+        _, _, r = eng.meshify_device(dvol, ISO, fetch=False, **FLAGS)
+    eng.set_profile(True)
+    ktot, kcnt = {}, {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    eng.timer_start()
+    launches = 0
+    stage = np.zeros(8)
+    per_step_k = []
+    for _ in range(args.steps):
+        _, _, r = eng.meshify_device(dvol, ISO, fetch=False, **FLAGS)
+        launches += r.launches
+        stage += np.array(list(r.ms))
+        per_step_k.append(eng.kernel_times())   # reads events already completed (the call synchronises)
+    ms_total = eng.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    eng.set_profile(False)
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * N / (ms_step * 1e-3) / 1e9
+    for ks in per_step_k:
+        for name, ms in ks:
+            ktot[name] = ktot.get(name, 0.0) + ms
+            kcnt[name] = kcnt.get(name, 0) + 1
+    nv, nt = r.nverts, r.ntris
+    nwords = n * n * ((n + 31) // 32)
+    peak, peak_src = peaks()
+    top = max(ktot, key=ktot.get)
+    top_ms = ktot[top] / kcnt[top]
+    kb = kernel_bytes(top, N, nv, nt, nwords)
+    achieved = kb / (top_ms * 1e-3) / 1e9 if kb else None
+    # whole-step algorithmic traffic (60 B/voxel for -p1 -l1 -b1, plus the surface term)
+    step_bytes = 60 * N + 24 * nv + 12 * nt
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": top_ms, "kernel_share_of_step": ktot[top] / (ms_step * args.steps),
+                "algorithmic_bytes_per_launch": kb,
+                "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
+                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                "kernels_ms_per_step": {k: round(v / args.steps, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1])}}
+
+    # ---- end to end through meshify() (include/meshify.h) with host buffers --------------------------
+    e2e = None
+    if not args.no_e2e:
+        L = eng.lib
+        hp = C.c_void_p()
+        eng._chk(L.b2m_host_alloc(C.byref(hp), N * 4))
+        hvol = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(n, n, n))
+        reps = n // 128
+        if reps * 128 == n:
+            hvol.reshape(reps, 128, reps, 128, reps, 128)[...] = tile[None, :, None, :, None, :]
+        else:
+            hvol[...] = synth.gyroid(n)
+        L.meshify.argtypes = [C.c_void_p, C.POINTER(C.c_short), C.c_int, C.c_float, C.POINTER(C.c_void_p),
+                              C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_bool, C.c_bool,
+                              C.c_bool, C.c_bool]
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        dim = (C.c_short * 3)(n, n, n)
+        os.environ["B2M_DEVICE"] = str(local)
+
+        def one():
+            pt, pp, cnt, cnv = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+            rc = L.meshify(hp, dim, 0, ISO, C.byref(pt), C.byref(pp), C.byref(cnt), C.byref(cnv), True, True, True, False)
+            assert rc == 0 and (cnv.value, cnt.value) == (nv, nt)
+            libc.free(pp)
+            libc.free(pt)
+        dvol.free()
+        ke = max(1, min(args.steps, 5))
+        for _ in range(2):
+            one()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            one()
+        barrier()
+        dt = max_over_ranks((time.perf_counter() - t0) / ke)
+        e2e = {"value": world * N / dt / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
+               "d2h_bytes_per_step": nv * 24 + nt * 12, "ms_per_step": dt * 1e3, "steps": ke,
+               "api": "meshify() (include/meshify.h), pinned host volume in, malloc'd host mesh out"}
+        L.b2m_host_free(hp)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sn = 384
+        dt, kind, cnv, cnt = ref_meshify_time(sn, 1, 0)
+        cpu = {"value": sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": kind,
+               "sample": f"G{sn} ({sn}^3 voxels, same generator and flags), 1 run of {dt:.1f} s, {cnv} verts {cnt} tris; "
+                         f"host has {os.cpu_count()} cores, meshify() is single-threaded"}
+    if rank == 0:
+        out = {"metric": "Gvoxels/s meshify (smooth+CC+MC+weld)", "value": value, "unit": "Gvoxels/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])",
+                          "voxels_per_gpu": N, "parallelism": "single GPU" if world == 1 else f"{world} independent volumes, one per GPU",
+                          "l2": "inputs (4 B/voxel volume) larger than the 126 MB L2; no flush needed",
+                          "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris}},
+               "stage_ms": {k: round(float(v) / args.steps, 4) for k, v in zip(lib.STAGES, stage)},
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

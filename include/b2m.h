@@ -82,6 +82,20 @@ int b2m_h2d(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
 int b2m_d2h(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
 int b2m_sync(b2m_ctx *ctx);
 int b2m_flush_l2(b2m_ctx *ctx); /* writes a 256 MiB scratch buffer (benchmark hygiene) */
+/* d_out[z][y][x] = d_tile[(z+z_offset) % tz][y % ty][x % tx]: periodic replication of a small device
+ * tile into a (slab of a) large volume without a host copy (synthetic G1024 / G2048 inputs). */
+int b2m_tile_volume(b2m_ctx *ctx, const float *d_tile, const int64_t tile_dims[3], float *d_out,
+                    const int64_t dims[3], int64_t z_offset);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+/* per-kernel device times of the LAST hot-path call on this ctx: when profiling is on, every kernel
+ * launch is bracketed by a CUDA-event pair on the ctx stream (the live launch list of bench.py). */
+int b2m_set_profile(b2m_ctx *ctx, int on);
+int b2m_profile_count(b2m_ctx *ctx);
+int b2m_profile_entry(b2m_ctx *ctx, int i, const char **name, float *ms);
+/* one CUDA-event pair on the ctx stream around an arbitrary region of calls */
+int b2m_timer_start(b2m_ctx *ctx);
+int b2m_timer_stop(b2m_ctx *ctx, float *ms);
 
 /* ---- the hot path -------------------------------------------------------------------------- */
 /* Whole meshify() on a volume already resident in device memory (x fastest, dims = NX,NY,NZ).

@@ -360,20 +360,16 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
   c.S = fo->S; c.fill = fo->fill; c.keep = fo->keep;
   c.nx = g.nx; c.ny = g.ny; c.nz = g.nz; c.w = g.w;
   c.iso = fo->iso; c.mn = fo->vmin; c.edge_max = fo->edge_max;
-  k_compose<<<b2m_cdiv(g.n, 256), 256, 0, ctx->stream>>>(c, d_composed, d_mask, want_min ? &d_sc->cmin_enc : nullptr);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "compose", k_compose<<<b2m_cdiv(g.n, 256), 256, 0, ctx->stream>>>(c, d_composed, d_mask, want_min ? &d_sc->cmin_enc : nullptr));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
 
 static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2 *nodes, int conn) {
   unsigned blocks = b2m_cdiv(cg.nwords, 256);
-  k_cc_init<<<blocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes);
-  B2M_LAUNCHED(ctx);
-  k_cc_link<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes, conn);
-  B2M_LAUNCHED(ctx);
-  k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "cc_init", k_cc_init<<<blocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes));
+  KT_LAUNCH(ctx, "cc_link", k_cc_link<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes, conn));
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -408,10 +404,8 @@ int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *
     B2M_TRY(b2m_reserve(ctx, BUF_FILL, wbytes));
     uint32_t *fill = b2m_ptr<uint32_t>(ctx, BUF_FILL);
     B2M_TRY(cc_label(ctx, bg, cg, nodes, 6));
-    k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, nullptr, &d_sc->nroots_bg);
-    B2M_LAUNCHED(ctx);
-    k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, 1, nullptr, &d_sc->nroots_bg, fg, fill);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, nullptr, &d_sc->nroots_bg));
+    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, 1, nullptr, &d_sc->nroots_bg, fg, fill));
     fo->fill = fill;
     bright = fill;
   }
@@ -422,14 +416,11 @@ int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *
     largest = b2m_ptr<uint32_t>(ctx, BUF_LARGEST);
     keep = b2m_ptr<uint32_t>(ctx, BUF_KEEP);
     B2M_TRY(cc_label(ctx, bright, cg, nodes, 18));
-    k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, &d_sc->best_fg, &d_sc->nroots_fg);
-    B2M_LAUNCHED(ctx);
-    k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, &d_sc->best_fg, &d_sc->nroots_fg));
+    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest));
     fo->keep = keep;
   }
-  k_dilate_bbox<<<blocks, 256, 0, ctx->stream>>>(largest, bright, cg, keep, d_sc->lo);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<blocks, 256, 0, ctx->stream>>>(largest, bright, cg, keep, d_sc->lo));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

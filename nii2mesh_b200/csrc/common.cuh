@@ -88,6 +88,13 @@ struct b2m_scalars {
   unsigned int pad[8];
 };
 
+// per-kernel device timing (opt-in, b2m_set_profile): one CUDA-event pair per launch on ctx->stream
+#define B2M_KT_MAX 256
+struct b2m_ktimer {
+  const char *name;
+  cudaEvent_t e0, e1;
+};
+
 struct b2m_ctx {
   int device;
   cudaStream_t stream;
@@ -98,7 +105,20 @@ struct b2m_ctx {
   int tables_ready;
   int sm_count;
   unsigned ev_mask;        // which stage event pairs were recorded in the current call
+  int profile;             // record an event pair around every kernel launch
+  int nkt, nkt_events;     // entries used in this call / event pairs created so far
+  b2m_ktimer kt[B2M_KT_MAX];
 };
+
+int b2m_kt_begin(b2m_ctx *ctx, const char *name);  // returns slot or -1
+void b2m_kt_end(b2m_ctx *ctx, int slot);
+#define KT_LAUNCH(ctx, name, ...)             \
+  do {                                        \
+    int kt_ = b2m_kt_begin((ctx), (name));    \
+    __VA_ARGS__;                              \
+    b2m_kt_end((ctx), kt_);                   \
+    (ctx)->launches++;                        \
+  } while (0)
 
 int b2m_reserve(b2m_ctx *ctx, int which, size_t bytes);
 template <typename T>

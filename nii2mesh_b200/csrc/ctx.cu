@@ -61,9 +61,54 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
   for (int i = 0; i < BUF_COUNT; i++)
     if (c->buf[i].p) cudaFree(c->buf[i].p);
   for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); i++) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < c->nkt_events; i++) { cudaEventDestroy(c->kt[i].e0); cudaEventDestroy(c->kt[i].e1); }
   cudaFreeHost(c->h_scalars);
   cudaStreamDestroy(c->stream);
   free(c);
+}
+
+int b2m_kt_begin(b2m_ctx *ctx, const char *name) {
+  if (!ctx->profile || ctx->nkt >= B2M_KT_MAX) return -1;
+  int i = ctx->nkt;
+  if (i >= ctx->nkt_events) {
+    if (cudaEventCreate(&ctx->kt[i].e0) != cudaSuccess || cudaEventCreate(&ctx->kt[i].e1) != cudaSuccess) return -1;
+    ctx->nkt_events = i + 1;
+  }
+  ctx->kt[i].name = name;
+  cudaEventRecord(ctx->kt[i].e0, ctx->stream);
+  ctx->nkt = i + 1;
+  return i;
+}
+void b2m_kt_end(b2m_ctx *ctx, int slot) {
+  if (slot >= 0) cudaEventRecord(ctx->kt[slot].e1, ctx->stream);
+}
+
+extern "C" int b2m_set_profile(b2m_ctx *ctx, int on) {
+  if (!ctx) return B2M_EARG;
+  ctx->profile = on != 0;
+  ctx->nkt = 0;
+  return B2M_OK;
+}
+extern "C" int b2m_profile_count(b2m_ctx *ctx) { return ctx ? ctx->nkt : 0; }
+extern "C" int b2m_profile_entry(b2m_ctx *ctx, int i, const char **name, float *ms) {
+  if (!ctx || i < 0 || i >= ctx->nkt || !name || !ms) return B2M_EARG;
+  CU_TRY(cudaEventSynchronize(ctx->kt[i].e1));
+  CU_TRY(cudaEventElapsedTime(ms, ctx->kt[i].e0, ctx->kt[i].e1));
+  *name = ctx->kt[i].name;
+  return B2M_OK;
+}
+// one event pair on the ctx stream for callers that time a whole region (bench.py)
+extern "C" int b2m_timer_start(b2m_ctx *ctx) {
+  if (!ctx) return B2M_EARG;
+  CU_TRY(cudaEventRecord(ctx->ev[2 * B2M_NSTAGE], ctx->stream));
+  return B2M_OK;
+}
+extern "C" int b2m_timer_stop(b2m_ctx *ctx, float *ms) {
+  if (!ctx || !ms) return B2M_EARG;
+  CU_TRY(cudaEventRecord(ctx->ev[2 * B2M_NSTAGE + 1], ctx->stream));
+  CU_TRY(cudaEventSynchronize(ctx->ev[2 * B2M_NSTAGE + 1]));
+  CU_TRY(cudaEventElapsedTime(ms, ctx->ev[2 * B2M_NSTAGE], ctx->ev[2 * B2M_NSTAGE + 1]));
+  return B2M_OK;
 }
 
 int b2m_reserve(b2m_ctx *ctx, int which, size_t bytes) {
@@ -155,5 +200,30 @@ extern "C" int b2m_flush_l2(b2m_ctx *ctx) {
   B2M_TRY(b2m_reserve(ctx, BUF_L2FLUSH, bytes));
   k_fill_u32<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(b2m_ptr<uint4>(ctx, BUF_L2FLUSH), bytes / 16, 0x5a5a5a5au);
   CU_TRY(cudaGetLastError());
+  return B2M_OK;
+}
+
+// periodic replication of a small tile into a large volume (synthetic inputs generated on device)
+__global__ void __launch_bounds__(256) k_tile_volume(const float *__restrict__ tile, int tx, int ty, int tz,
+                                                     float *__restrict__ out, int nx, int ny, int nz, long long zoff) {
+  const long long rows = (long long)ny * nz;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int z = (int)(row / ny), y = (int)(row - (long long)z * ny);
+    const float *src = tile + ((size_t)((z + zoff) % tz) * ty + (size_t)(y % ty)) * tx;
+    float *dst = out + (size_t)row * nx;
+    for (int x = threadIdx.x; x < nx; x += blockDim.x) dst[x] = __ldg(src + x % tx);
+  }
+}
+
+extern "C" int b2m_tile_volume(b2m_ctx *ctx, const float *d_tile, const int64_t td[3], float *d_out,
+                               const int64_t dims[3], int64_t z_offset) {
+  if (!ctx || !d_tile || !td || !d_out || !dims) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  long long rows = (long long)dims[1] * dims[2];
+  unsigned blocks = (unsigned)(rows < (long long)ctx->sm_count * 32 ? rows : (long long)ctx->sm_count * 32);
+  k_tile_volume<<<blocks, 256, 0, ctx->stream>>>(d_tile, (int)td[0], (int)td[1], (int)td[2], d_out, (int)dims[0],
+                                                 (int)dims[1], (int)dims[2], (long long)z_offset);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
   return B2M_OK;
 }

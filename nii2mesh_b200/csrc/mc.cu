@@ -573,8 +573,7 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
     dim3 grid(p.segs, b2m_cdiv(p.sy, MCA_ROWS), p.sz);
-    k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p));
     CU_TRY(cudaGetLastError());
     if (attempt == 0) {
       B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
@@ -592,8 +591,7 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
     p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segt, p.segt, nseg, &d_sc->tot_t));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segc, p.segc, nseg, &d_sc->tot_c));
@@ -625,8 +623,7 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
     e.nv_edge = tot_v;
     e.first_cube = ctx->h_scalars->first_cube;
     CU_TRY(cudaMemsetAsync(&d_sc->n_cand, 0, 4, ctx->stream));
-    k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "mc_emit", k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
     CU_TRY(cudaGetLastError());
     B2M_TRY(b2m_fetch_scalars(ctx));
     if (ctx->h_scalars->n_cand <= ccap) break;

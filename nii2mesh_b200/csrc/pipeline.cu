@@ -159,6 +159,7 @@ extern "C" int b2m_meshify_device(b2m_ctx *ctx, const float *d_img, const int64_
   memset(res, 0, sizeof(*res));
   ctx->launches = 0;
   ctx->ev_mask = 0;
+  ctx->nkt = 0;
   int rc = meshify_device_impl(ctx, d_img, dims, opts, res);
   if (rc != B2M_OK) cudaStreamSynchronize(ctx->stream);
   return rc;
@@ -223,6 +224,7 @@ extern "C" int b2m_stage_front(b2m_ctx *ctx, const float *d_img, const int64_t d
   memset(res, 0, sizeof(*res));
   ctx->launches = 0;
   ctx->ev_mask = 0;
+  ctx->nkt = 0;
   b2m_geom g = b2m_make_geom(dims);
   b2m_front_out fo;
   memset(&fo, 0, sizeof(fo));
@@ -241,6 +243,7 @@ extern "C" int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims
   memset(res, 0, sizeof(*res));
   ctx->launches = 0;
   ctx->ev_mask = 0;
+  ctx->nkt = 0;
   b2m_geom g = b2m_make_geom(dims);
   B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
   b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
@@ -282,6 +285,7 @@ extern "C" int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *n
   CU_TRY(cudaSetDevice(ctx->device));
   ctx->launches = 0;
   ctx->ev_mask = 0;
+  ctx->nkt = 0;
   B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
   CU_TRY(cudaMemsetAsync(ctx->buf[BUF_SCALARS].p, 0, sizeof(b2m_scalars), ctx->stream));
   B2M_TRY(b2m_reserve(ctx, BUF_VERTS, (size_t)*nv * 24));

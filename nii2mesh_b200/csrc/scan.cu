@@ -95,8 +95,7 @@ static int scan_rec(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t 
     return B2M_OK;
   }
   if (n <= 4096 && d_in == d_out) {
-    k_scan_single<<<1, 1024, 0, ctx->stream>>>(d_out, n, d_total);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "scan_single", k_scan_single<<<1, 1024, 0, ctx->stream>>>(d_out, n, d_total));
     CU_TRY(cudaGetLastError());
     return B2M_OK;
   }
@@ -108,16 +107,13 @@ static int scan_rec(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t 
   }
   B2M_TRY(b2m_reserve(ctx, which, nblk * 4));
   uint32_t *part = b2m_ptr<uint32_t>(ctx, which);
-  k_scan_reduce<<<(unsigned)nblk, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, part);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "scan_reduce", k_scan_reduce<<<(unsigned)nblk, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, part));
   if (nblk <= 65536) {
-    k_scan_single<<<1, 1024, 0, ctx->stream>>>(part, nblk, d_total);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "scan_single", k_scan_single<<<1, 1024, 0, ctx->stream>>>(part, nblk, d_total));
   } else {
     B2M_TRY(scan_rec(ctx, part, part, nblk, d_total, level + 1));
   }
-  k_scan_apply<<<(unsigned)nblk, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, n, part);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "scan_apply", k_scan_apply<<<(unsigned)nblk, SCAN_THREADS, 0, ctx->stream>>>(d_in, d_out, n, part));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -195,11 +191,9 @@ int b2m_sort_u64(b2m_ctx *ctx, uint64_t *d_keys, size_t n, int key_bits) {
   if (passes & 1) passes++;  // even number of passes: the result ends in d_keys
   for (int p = 0; p < passes; p++) {
     int shift = 8 * p;
-    k_rs_hist<<<nblk, RS_THREADS, 0, ctx->stream>>>(a, n, shift, hist, nblk);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "rs_hist", k_rs_hist<<<nblk, RS_THREADS, 0, ctx->stream>>>(a, n, shift, hist, nblk));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, hist, hist, (size_t)nblk * 256, nullptr));
-    k_rs_scatter<<<nblk, RS_THREADS, 0, ctx->stream>>>(a, b, n, shift, hist, nblk);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "rs_scatter", k_rs_scatter<<<nblk, RS_THREADS, 0, ctx->stream>>>(a, b, n, shift, hist, nblk));
     uint64_t *t = a; a = b; b = t;
   }
   CU_TRY(cudaGetLastError());

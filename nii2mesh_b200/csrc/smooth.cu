@@ -178,24 +178,21 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
 
 int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
   dim3 grid(b2m_cdiv(g.nx, SM_TX), b2m_cdiv(g.ny, SM_TY), b2m_cdiv(g.nz, SM_ZC));
-  k_smooth3<<<grid, SM_THREADS, 0, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, &d_sc->vmin_enc);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "smooth3", k_smooth3<<<grid, SM_THREADS, 0, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, &d_sc->vmin_enc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
 
 int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, b2m_scalars *d_sc) {
   unsigned blocks = (unsigned)min((long long)ctx->sm_count * 16, (g.n / 4 + 255) / 256 + 1);
-  k_minmax<<<blocks, 256, 0, ctx->stream>>>(d_in, (size_t)g.n, &d_sc->vmin_enc);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "minmax", k_minmax<<<blocks, 256, 0, ctx->stream>>>(d_in, (size_t)g.n, &d_sc->vmin_enc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
 
 int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg) {
   long long threads = g.nwords * 32;
-  k_threshold<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "threshold", k_threshold<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

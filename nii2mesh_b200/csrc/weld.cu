@@ -171,23 +171,18 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backe
     uint32_t *head = b2m_ptr<uint32_t>(ctx, BUF_TMP0), *rep = b2m_ptr<uint32_t>(ctx, BUF_TMP1);
     // key origin: the reference's pts[0].  Lewiner: vertex 0.  Classic: first soup vertex (mc.cu).
     const double *p0 = (backend == B2M_BACKEND_CLASSIC && !all_candidates) ? d_sc->pts0 : verts;
-    k_weld_keys<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(verts, all_candidates ? nullptr : b2m_ptr<uint32_t>(ctx, BUF_CAND),
-                                                                ncand, p0, keys);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "weld_keys", k_weld_keys<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(verts, all_candidates ? nullptr : b2m_ptr<uint32_t>(ctx, BUF_CAND),
+                                                                ncand, p0, keys));
     B2M_TRY(b2m_sort_u64(ctx, keys, ncand, 64));
-    k_weld_resolve<<<b2m_cdiv(ncand, 128), 128, 0, ctx->stream>>>(verts, keys, ncand, head);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "weld_resolve", k_weld_resolve<<<b2m_cdiv(ncand, 128), 128, 0, ctx->stream>>>(verts, keys, ncand, head));
     CU_TRY(cudaMemsetAsync(rep, 0, (size_t)ncand * 4, ctx->stream));
-    k_weld_rep<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(keys, ncand, head, rep);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "weld_rep", k_weld_rep<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(keys, ncand, head, rep));
     B2M_TRY(b2m_reserve(ctx, BUF_REMAP, (size_t)nv * 4));
     B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, (size_t)(nv > nt ? nv : nt) * 4 + 16));
     uint32_t *rm = b2m_ptr<uint32_t>(ctx, BUF_REMAP), *fl = b2m_ptr<uint32_t>(ctx, BUF_FLAGS);
-    k_iota_ones<<<b2m_cdiv(nv, 256), 256, 0, ctx->stream>>>(rm, fl, nv);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "iota_ones", k_iota_ones<<<b2m_cdiv(nv, 256), 256, 0, ctx->stream>>>(rm, fl, nv));
     CU_TRY(cudaMemsetAsync(&d_sc->n_removed, 0, 4, ctx->stream));
-    k_weld_mark<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(keys, ncand, head, rep, rm, fl, &d_sc->n_removed);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "weld_mark", k_weld_mark<<<b2m_cdiv(ncand, 256), 256, 0, ctx->stream>>>(keys, ncand, head, rep, rm, fl, &d_sc->n_removed));
     CU_TRY(cudaGetLastError());
     B2M_TRY(b2m_fetch_scalars(ctx));
     unsigned nrem = ctx->h_scalars->n_removed;
@@ -196,8 +191,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backe
       nv_out = nv - nrem;
       B2M_TRY(b2m_reserve(ctx, BUF_VERTS2, (size_t)nv_out * 24));
       double *v2 = b2m_ptr<double>(ctx, BUF_VERTS2);
-      k_compact_verts<<<b2m_cdiv(nv, 256), 256, 0, ctx->stream>>>(verts, v2, rm, fl, nv);
-      B2M_LAUNCHED(ctx);
+      KT_LAUNCH(ctx, "compact_verts", k_compact_verts<<<b2m_cdiv(nv, 256), 256, 0, ctx->stream>>>(verts, v2, rm, fl, nv));
       verts = v2;
       remap = rm;
       // newidx lives in BUF_FLAGS, which the triangle pass also needs for its keep flags: move it
@@ -211,8 +205,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backe
   // degenerate triangles
   B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, (size_t)(nv > nt ? nv : nt) * 4 + 16));
   uint32_t *tf = b2m_ptr<uint32_t>(ctx, BUF_FLAGS);
-  k_tri_remap_degen<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, nt, verts, remap, newidx, tf);
-  B2M_LAUNCHED(ctx);
+  KT_LAUNCH(ctx, "tri_remap_degen", k_tri_remap_degen<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, nt, verts, remap, newidx, tf));
   B2M_TRY(b2m_exclusive_scan_u32(ctx, tf, tf, nt, &d_sc->n_tri_kept));
   CU_TRY(cudaGetLastError());
   B2M_TRY(b2m_fetch_scalars(ctx));
@@ -220,8 +213,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backe
   if (nt_out != nt) {
     B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)nt_out * 12));
     int *t2 = b2m_ptr<int>(ctx, BUF_TRIS2);
-    k_compact_tris<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, t2, tf, &d_sc->n_tri_kept, nt);
-    B2M_LAUNCHED(ctx);
+    KT_LAUNCH(ctx, "compact_tris", k_compact_tris<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, t2, tf, &d_sc->n_tri_kept, nt));
     tris = t2;
   }
   CU_TRY(cudaEventRecord(e3, ctx->stream));

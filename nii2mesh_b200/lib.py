@@ -67,6 +67,12 @@ def load():
     L.b2m_d2h.argtypes = [vp, vp, vp, C.c_size_t]
     L.b2m_sync.argtypes = [vp]
     L.b2m_flush_l2.argtypes = [vp]
+    L.b2m_set_profile.argtypes = [vp, C.c_int]
+    L.b2m_profile_count.argtypes = [vp]
+    L.b2m_profile_entry.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
+    L.b2m_timer_start.argtypes = [vp]
+    L.b2m_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.b2m_tile_volume.argtypes = [vp, vp, i64p, vp, i64p, C.c_int64]
     L.b2m_meshify_device.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(Result)]
     L.b2m_meshify_host.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
     L.b2m_fetch_mesh.argtypes = [vp, C.POINTER(Result), vp, vp]
@@ -130,6 +136,33 @@ class Engine:
         if rc != 0:
             raise B2MError(f"libb2m error {rc}: {self.lib.b2m_last_error().decode()}")
 
+    # ---- measurement ----
+    def set_profile(self, on=True):
+        self._chk(self.lib.b2m_set_profile(self.ctx, int(on)))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the last hot-path call (profiling must be on), in launch order"""
+        out = []
+        for i in range(self.lib.b2m_profile_count(self.ctx)):
+            name, ms = C.c_char_p(), C.c_float()
+            self._chk(self.lib.b2m_profile_entry(self.ctx, i, C.byref(name), C.byref(ms)))
+            out.append((name.value.decode(), float(ms.value)))
+        return out
+
+    def timer_start(self):
+        self._chk(self.lib.b2m_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._chk(self.lib.b2m_timer_stop(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._chk(self.lib.b2m_sync(self.ctx))
+
+    def flush_l2(self):
+        self._chk(self.lib.b2m_flush_l2(self.ctx))
+
     # ---- memory ----
     def alloc(self, nbytes):
         p = C.c_void_p()
@@ -141,6 +174,17 @@ class Engine:
         p = self.alloc(vol.nbytes)
         self._chk(self.lib.b2m_h2d(self.ctx, p, vol.ctypes.data, vol.nbytes))
         return DeviceVolume(self, vol.shape, p)
+
+    def tiled_volume(self, tile, shape, z_offset=0):
+        """periodic replication of a small host tile into a device volume of `shape` (z,y,x), on the device"""
+        t = self.upload(tile)
+        n = int(np.prod(shape))
+        out = DeviceVolume(self, shape, self.alloc(n * 4))
+        try:
+            self._chk(self.lib.b2m_tile_volume(self.ctx, t.ptr, _dims(t.shape), out.ptr, _dims(shape), int(z_offset)))
+        finally:
+            t.free()
+        return out
 
     def download(self, ptr, shape, dtype):
         out = np.empty(shape, dtype)

@@ -1,0 +1,246 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+libb2m.so (include/b2m.h, include/meshify.h); results are compared with the CPU oracle on the same
+inputs and with the golden digests recorded from the unmodified reference.
+
+Bar: integer/index work (masks, bbox, triangle topology) bit-exact; vertex positions within 1e-5
+relative (north_star) — in fact the kernels reproduce the reference's f32/f64 operations in the
+same order, so positions are compared bit-for-bit wherever the emission order is the reference's.
+"""
+import ctypes as C
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+import cases
+import surfaces
+from conftest import GOLDEN, bits_differ
+from oracle.canon import assert_same_mesh, topology_digest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.loads((GOLDEN / "golden.json").read_text())
+VOLS = cases.volumes()
+POS_RTOL = 1e-5  # north_star: vertex positions within 1e-5 relative
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_smooth_bit_exact(eng, orc, name):
+    vol = VOLS[name][0]
+    a = eng.smooth(vol)
+    assert bits_differ(a, orc.smooth(vol)) == 0
+    assert sha(a) == GOLD["smooth"][name]
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_front_masks_bbox_bit_exact(eng, orc, name):
+    """smooth -> range -> isolevel sanity -> CC (largest / bubbles) -> dilate -> darken -> bbox"""
+    vol, iso = VOLS[name]
+    for ps, ol, fb in ((0, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 1, 1), (0, 1, 0)):
+        a = eng.front(vol, iso, ps, ol, fb)
+        b = orc.front(vol, iso, ps, ol, fb)
+        tag = f"{name} p{ps} l{ol} b{fb}"
+        assert (a["lo"], a["hi"]) == (b["lo"], b["hi"]), tag
+        assert (a["iso"], a["mn"], a["mx"]) == (b["iso"], b["mn"], b["mx"]), tag
+        if ol or fb:
+            assert np.array_equal(a["mask"] != 0, b["mask"] != 0), tag
+        assert bits_differ(a["img"], b["img"]) == 0, tag
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_front_golden(eng, name):
+    vol, iso = VOLS[name]
+    for backend, omc, ps, ol, fb in cases.flag_sets(name):
+        if backend:
+            continue
+        key = f"{name}/backend{backend}_o{omc}_p{ps}_l{ol}_b{fb}"
+        if key in GOLD["front"]:
+            assert sha(eng.front(vol, iso, ps, ol, fb)["img"]) == GOLD["front"][key], key
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_marching_cubes_arrays(eng, orc, name):
+    """Lewiner: vertex and triangle ARRAYS identical to the reference's emission order;
+    classic: edge-keyed mesh == the reference's soup after its own weld."""
+    vol, iso = VOLS[name]
+    for ps, ol in ((1, 1), (0, 0)):
+        f = orc.front(vol, iso, ps, ol, 0)
+        for omc in (0, 1):
+            ov, ot = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], omc, 0)
+            gv, gt, _ = eng.mc(f["img"], f["lo"], f["hi"], f["iso"], omc, 0)
+            assert np.array_equal(gt, ot), f"{name} p{ps} o{omc}"
+            assert np.array_equal(gv, ov), f"{name} p{ps} o{omc}"
+        sv, st = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], 0, 1)
+        wv, wt = orc.weld(sv, st)
+        gv, gt, _ = eng.mc(f["img"], f["lo"], f["hi"], f["iso"], 0, 1)
+        cv, ct = eng.weld(gv, gt)  # resolves the rare corner merges exactly like the reference
+        assert_same_mesh(cv, ct, wv, orc.degenerate(wv, wt), POS_RTOL)
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_selftest_surfaces(eng, k):
+    v, t, _ = eng.mc(surfaces.surface(k), [0, 0, 0], [59, 59, 59], 0.0, 0, 0)
+    assert (len(v), len(t)) == surfaces.KNOWN[k]
+    assert topology_digest(v, t)[2] == GOLD["surfaces"][str(k)]["digest"]
+    if k == 7:
+        v, t, _ = eng.mc(surfaces.surface(7), [0, 0, 0], [59, 59, 59], 0.0, 1, 0)
+        assert (len(v), len(t)) == surfaces.KNOWN_ORIGINAL[7]
+        assert topology_digest(v, t)[2] == GOLD["surfaces"]["7_original"]["digest"]
+
+
+@pytest.mark.parametrize("name", [n for n in VOLS if VOLS[n][0].size < 300000])
+def test_weld_hook(eng, orc, name):
+    vol, iso = VOLS[name]
+    f = orc.front(vol, iso, 0, 0, 0)
+    for backend in (0, 1):
+        ov, ot = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], 0, backend)
+        wv, wt = orc.weld(ov, ot)
+        wt = orc.degenerate(wv, wt)
+        gv, gt = eng.weld(ov, ot)
+        assert len(gv) == len(wv)
+        assert_same_mesh(gv, gt, wv, wt, POS_RTOL)
+
+
+def test_weld_adversarial(eng, orc):
+    rng = np.random.default_rng(11)
+    for trial in range(10):
+        base = rng.uniform(0, 40, (60, 3))
+        pts = [base]
+        for s in (2e-6, 6e-6, 9.9e-6, 1.2e-5):
+            pts.append(base[rng.integers(0, 60, 25)] + rng.normal(0, s, (25, 3)))
+        v = np.concatenate(pts)
+        v = v[rng.permutation(len(v))]
+        t = rng.integers(0, len(v), (300, 3)).astype(np.int32)
+        wv, wt = orc.weld(v, t)
+        wt = orc.degenerate(wv, wt)
+        gv, gt = eng.weld(v, t)
+        assert len(gv) == len(wv) and len(gt) == len(wt), trial
+        assert_same_mesh(gv, gt, wv, wt, POS_RTOL)
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_meshify_vs_oracle_and_golden(eng, orc, name):
+    """the whole path, host buffers in / host mesh out (b2m_meshify_host = what meshify() calls)"""
+    vol, iso = VOLS[name]
+    for backend, omc, ps, ol, fb in cases.flag_sets(name):
+        key = f"{name}/backend{backend}_o{omc}_p{ps}_l{ol}_b{fb}"
+        g = GOLD["meshify"][key]
+        gv, gt, r = eng.meshify(vol, iso, omc, ps, ol, fb, backend)
+        assert (len(gv), len(gt)) == (g["nverts"], g["ntris"]), key
+        nu, nt, faces = topology_digest(gv, gt, with_coords=False)
+        assert nu == g["nused"], key
+        # bit-exact positions + topology against the reference's recorded digest
+        assert topology_digest(gv, gt)[2] == g["digest"], key
+        if vol.size < 600000:
+            o = orc.meshify(vol, iso, omc, ps, ol, fb, backend)
+            assert (r.pre_nverts, r.pre_ntris) == (o["pre_nv"], o["pre_nt"]), key
+            assert_same_mesh(gv, gt, o["verts"], o["tris"], POS_RTOL)
+
+
+def _c_meshify(libb2m):
+    libb2m.meshify.argtypes = [C.c_void_p, C.POINTER(C.c_short), C.c_int, C.c_float, C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_bool, C.c_bool,
+                               C.c_bool, C.c_bool]
+    return libb2m.meshify
+
+
+def test_reference_signature_meshify(libb2m, orc, bet):
+    """meshify() exactly as nii2() calls it (src/nii2mesh.c:326): short dims, malloc'd outputs"""
+    vol, _ = bet
+    fn = _c_meshify(libb2m)
+    img = vol.copy()
+    nz, ny, nx = img.shape
+    dim = (C.c_short * 3)(nx, ny, nz)
+    pt, pp, nt, nv = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    rc = fn(img.ctypes.data, dim, 0, 67.729, C.byref(pt), C.byref(pp), C.byref(nt), C.byref(nv), True, True, False, False)
+    assert rc == 0
+    g = GOLD["meshify"]["bet/backend0_o0_p1_l1_b0"]
+    assert (nv.value, nt.value) == (g["nverts"], g["ntris"]) == (172304, 344400)
+    v = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_double)), shape=(nv.value, 3)).copy()
+    t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(nt.value, 3)).copy()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(pp)  # plain malloc() blocks owned by the caller (src/nii2mesh.c:353-354)
+    libc.free(pt)
+    assert topology_digest(v, t)[2] == g["digest"]
+    # classic back-end through the runtime switch that replaces -DUSE_CLASSIC_CUBES
+    libb2m.b2m_set_default_backend(1)
+    try:
+        rc = fn(img.ctypes.data, dim, 0, 67.729, C.byref(pt), C.byref(pp), C.byref(nt), C.byref(nv), True, True, False,
+                False)
+        assert rc == 0
+        g = GOLD["meshify"]["bet/backend1_o0_p1_l1_b0"]
+        assert (nv.value, nt.value) == (g["nverts"], g["ntris"])
+        libc.free(pp)
+        libc.free(pt)
+    finally:
+        libb2m.b2m_set_default_backend(0)
+
+
+def test_failure_semantics(eng, libb2m):
+    from nii2mesh_b200 import lib
+    with pytest.raises(lib.MeshifyFailure):  # "No variability in image intensity" -> EXIT_FAILURE
+        eng.meshify(cases.flat_volume(), 1.0)
+    fn = _c_meshify(libb2m)
+    img = cases.flat_volume()
+    dim = (C.c_short * 3)(10, 9, 8)
+    pt, pp, nt, nv = C.c_void_p(), C.c_void_p(), C.c_int(-7), C.c_int(-7)
+    rc = fn(img.ctypes.data, dim, 0, 1.0, C.byref(pt), C.byref(pp), C.byref(nt), C.byref(nv), True, True, False, False)
+    assert rc == 1 and not pt.value and not pp.value and nt.value == -7  # outputs untouched on failure
+    # isolevel outside the intensity range is reset to mid-range (src/meshify.c:316-319)
+    v, t, r = eng.meshify(VOLS["isoreset"][0], 1.0e6, 0, 1, 1, 0)
+    assert r.iso_reset == 1 and r.iso_used == np.float32(0.5 * (np.float64(np.float32(r.vmin + r.vmax))))
+
+
+def test_input_not_modified_and_deterministic(eng):
+    vol, iso = VOLS["blobs2"]
+    keep = vol.copy()
+    a = eng.meshify(vol, iso, 0, 1, 1, 1)
+    b = eng.meshify(vol, iso, 0, 1, 1, 1)
+    assert np.array_equal(vol, keep)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+# ---- full-size, size-independent properties -----------------------------------------------------
+def _gyroid_counts(n):  # pre-weld counts of the G family are cubic in tiles/axis
+    return 79416 * n ** 3 + 45456 * n ** 2 - 1410 * n, 158848 * n ** 3 + 90912 * n ** 2 - 2832 * n
+
+
+@pytest.mark.parametrize("n,post", [(256, (814168, 1628383)), (512, (5802752, 11606149)),
+                                    (1024, (43545074, 87096797))])
+def test_gyroid_full_size_known_counts(eng, n, post):
+    """BASELINE config 3 family (Lewiner -p1 -l1 -b1): the reference's recorded counts
+     before and after weld/cleanup, at 256^3, 512^3 and the full 1024^3."""
+    from nii2mesh_b200 import synth
+    d = eng.tiled_volume(synth.gyroid_tile(128), (n, n, n))
+    try:
+        _, _, r = eng.meshify_device(d, 0.0, 0, 1, 1, 1, 0, fetch=False)
+        assert (r.pre_nverts, r.pre_ntris) == _gyroid_counts(n // 128)
+        assert (r.nverts, r.ntris) == post
+        v, t, r2 = eng.meshify_device(d, 0.0, 0, 1, 1, 1, 0, fetch=(n <= 512))
+        assert (r2.nverts, r2.ntris) == post  # idempotent: the device volume is not modified
+        if v is not None:
+            # closed-surface bookkeeping that does not depend on size: every index in range and used
+            assert t.min() >= 0 and t.max() < len(v)
+            assert len(np.unique(t)) >= len(v) - r.ndegenerate
+    finally:
+        d.free()
+
+
+def test_sphere512_classic_known_counts(eng):
+    """BASELINE config 2: S512 noisy sphere, original marching cubes, -p 0 -l 0."""
+    from nii2mesh_b200 import synth
+    vol = synth.noisy_sphere(512)
+    d = eng.upload(vol)
+    try:
+        _, _, r = eng.meshify_device(d, 0.0, 1, 0, 0, 0, 1, fetch=False)   # classic build
+        assert (r.pre_nverts, r.pre_ntris, r.nverts, r.ntris) == (16032504, 5344168, 2791829, 5343010)
+        _, _, r = eng.meshify_device(d, 0.0, 1, 0, 0, 0, 0, fetch=False)   # Lewiner build, -o 1
+        assert (r.pre_nverts, r.pre_ntris, r.nverts, r.ntris) == (2791860, 5331520, 2791807, 5330338)
+    finally:
+        d.free()

@@ -1,0 +1,141 @@
+"""CPU tests of the oracle (oracle/oracle.c): pinned against (a) golden digests produced by the
+unmodified compiled reference (tests/golden/golden.json, tools/make_golden.py) and (b) the compiled
+reference itself, live, whenever oracle/_ref is present.  No GPU needed."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+
+import cases
+import surfaces
+from conftest import GOLDEN, bits_differ
+from oracle.canon import assert_same_mesh, topology_digest
+
+GOLD = json.loads((GOLDEN / "golden.json").read_text())
+VOLS = cases.volumes()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ---- golden vectors (reference outputs recorded in the build container) ---------------------------
+@pytest.mark.parametrize("name", list(VOLS))
+def test_smooth_golden(orc, name):
+    assert sha(orc.smooth(VOLS[name][0])) == GOLD["smooth"][name]
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_bwlabel_dilate_golden(orc, name):
+    vol, iso = VOLS[name]
+    mask = (vol >= np.float32(iso)).astype(np.float32)
+    for ol, fb in ((1, 0), (0, 1), (1, 1)):
+        assert sha(orc.bwlabel(mask, 18, ol, fb) != 0) == GOLD["bwlabel"][f"{name}/l{ol}b{fb}"], (ol, fb)
+    assert sha(orc.dilate25(mask) != 0) == GOLD["dilate"][name]
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_selftest_surfaces_known_answers(orc, k):
+    """the reference's own MC self test: 10 analytic 60^3 surfaces (src/MarchingCubes.c:1282-1362)"""
+    v, t = orc.mc(surfaces.surface(k), [0, 0, 0], [59, 59, 59], 0.0, 0, 0)
+    assert (len(v), len(t)) == surfaces.KNOWN[k]
+    assert topology_digest(v, t)[2] == GOLD["surfaces"][str(k)]["digest"]
+
+
+def test_selftest_surface_original_mc(orc):
+    v, t = orc.mc(surfaces.surface(7), [0, 0, 0], [59, 59, 59], 0.0, 1, 0)
+    assert (len(v), len(t)) == surfaces.KNOWN_ORIGINAL[7]
+    assert topology_digest(v, t)[2] == GOLD["surfaces"]["7_original"]["digest"]
+
+
+@pytest.mark.parametrize("name", list(VOLS))
+def test_meshify_golden(orc, name):
+    vol, iso = VOLS[name]
+    for backend, omc, ps, ol, fb in cases.flag_sets(name):
+        key = f"{name}/backend{backend}_o{omc}_p{ps}_l{ol}_b{fb}"
+        g = GOLD["meshify"][key]
+        o = orc.meshify(vol, iso, omc, ps, ol, fb, backend)
+        assert o["rc"] == g["rc"], key
+        if g["rc"]:
+            continue
+        assert (len(o["verts"]), len(o["tris"])) == (g["nverts"], g["ntris"]), key
+        assert topology_digest(o["verts"], o["tris"])[2] == g["digest"], key
+        f = orc.front(vol, iso, ps, ol, fb)
+        assert sha(f["img"]) == GOLD["front"][key], key
+
+
+def test_no_variability_fails(orc):
+    assert orc.meshify(cases.flat_volume(), 1.0)["rc"] != 0
+
+
+# ---- live against the compiled reference --------------------------------------------------------
+SMALL = [n for n in VOLS if VOLS[n][0].size < 400000]
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_stages_vs_reference(orc, ref_lewiner, ref_classic, name):
+    vol, iso = VOLS[name]
+    assert bits_differ(orc.smooth(vol), ref_lewiner.smooth(vol)) == 0
+    mask = (vol >= np.float32(iso)).astype(np.float32)
+    for ol, fb in ((1, 0), (0, 1), (1, 1), (0, 0)):
+        assert np.array_equal(orc.bwlabel(mask, 18, ol, fb), ref_lewiner.bwlabel(mask, 18, ol, fb)), (ol, fb)
+    assert np.array_equal(orc.dilate25(mask), ref_lewiner.dilate(mask))
+    f = orc.front(vol, iso, 0, 0, 0)
+    if f["rc"]:
+        return
+    for omc in (0, 1):
+        ov, ot = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], omc, 0)
+        rv, rt = ref_lewiner.mc(f["img"], f["lo"], f["hi"], f["iso"], omc)
+        assert np.array_equal(ot, rt) and np.array_equal(ov, rv), f"lewiner o{omc}"
+    ov, ot = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], 0, 1)
+    rv, rt = ref_classic.mc(f["img"], f["lo"], f["hi"], f["iso"], 0)
+    assert np.array_equal(ot, rt) and np.array_equal(ov, rv), "classic"
+    # weld + degenerate removal on the classic soup (most merges)
+    wv, wt = orc.weld(ov, ot)
+    xv, xt = ref_classic.weld(rv, rt)
+    assert np.array_equal(wv, xv) and np.array_equal(wt, xt)
+    assert np.array_equal(orc.degenerate(wv, wt), ref_classic.degenerate(xv, xt))
+
+
+@pytest.mark.parametrize("name", ["sphere40", "blobs", "thin4", "isoreset"])
+def test_meshify_vs_reference(orc, ref_lewiner, ref_classic, name):
+    vol, iso = VOLS[name]
+    for backend, omc, ps, ol, fb in cases.flag_sets(name):
+        R = ref_classic if backend else ref_lewiner
+        r = R.meshify(vol, iso, omc, ps, ol, fb)
+        o = orc.meshify(vol, iso, omc, ps, ol, fb, backend)
+        assert o["rc"] == r["rc"]
+        if r["rc"] == 0:
+            assert np.array_equal(o["verts"], r["verts"]) and np.array_equal(o["tris"], r["tris"])
+
+
+def test_weld_adversarial_vs_reference(orc, ref_lewiner):
+    """near-duplicate vertices around the 1e-5 tolerance, incl. chains (later heads steal)"""
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        base = rng.uniform(0, 40, (60, 3))
+        pts = [base]
+        for s in (2e-6, 6e-6, 9.9e-6, 1.2e-5):
+            pts.append(base[rng.integers(0, 60, 25)] + rng.normal(0, s, (25, 3)))
+        v = np.concatenate(pts)
+        v = v[rng.permutation(len(v))]
+        t = rng.integers(0, len(v), (300, 3)).astype(np.int32)
+        wv, wt = orc.weld(v, t)
+        xv, xt = ref_lewiner.weld(v, t)
+        assert np.array_equal(wv, xv) and np.array_equal(wt, xt), trial
+        assert np.array_equal(orc.degenerate(wv, wt), ref_lewiner.degenerate(xv, xt)), trial
+
+
+def test_canon_detects_differences(orc):
+    vol, iso = VOLS["sphere24"]
+    o = orc.meshify(vol, iso, 0, 1, 1, 0, 0)
+    v, t = o["verts"], o["tris"]
+    perm = np.random.default_rng(0).permutation(len(v))
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(len(v))
+    assert_same_mesh(v[perm], inv[t][::-1], v, t)  # relabelled + reordered: same mesh
+    bad = t.copy()
+    bad[0] = bad[0][[1, 0, 2]]  # flipped winding
+    with pytest.raises(AssertionError):
+        assert_same_mesh(v, bad, v, t)
