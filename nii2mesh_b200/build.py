@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libb2m build failed")
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
-                           "-lcudart_static", "-lm"])
+                           "-lcudart_static", "-lm", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
     return LIB
 
 

@@ -72,78 +72,187 @@ __device__ __forceinline__ uint32_t bits_range(int s, int e) {  // ones at s..e 
   return hi & ~((1u << s) - 1u);
 }
 
-__global__ void __launch_bounds__(256) k_cc_init(const uint32_t *__restrict__ bits, long long nwords,
-                                                 uint2 *__restrict__ nodes) {
-  long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (word >= nwords) return;
-  uint32_t w = bits[word];
-  uint32_t starts = w & ~(w << 1);
-  while (starts) {
-    int s = __ffs(starts) - 1;
-    starts &= starts - 1;
-    uint32_t slot = (uint32_t)word * 16u + (uint32_t)(s >> 1);
-    nodes[slot] = make_uint2(slot, 0u);
+// ---- tile-local labelling ----------------------------------------------------------------------
+// A CTA labels a tile of CT_W x CT_Y x CT_Z bit words (256 x 8 x 8 voxels) entirely in shared memory
+// (same run slots, same union-by-minimum rule, ~30-cycle shared-memory hops instead of L2 round
+// trips), then publishes one global node per run: parent = the tile-local root's GLOBAL slot, and on
+// the local roots the voxel count and face flag of the whole local component.  Only neighbour pairs
+// that straddle two tiles are left for the global union-find (k_cc_border), which therefore works
+// on a forest of a few tile-roots per tile instead of one node per run.
+#define CT_W 8
+#define CT_Y 8
+#define CT_Z 8
+#define CT_WORDS (CT_W * CT_Y * CT_Z)
+
+// shared-memory entry of a run slot: parent local slot << 16 | face flag << 15 | voxel count (<= 16384)
+__device__ __forceinline__ uint32_t lfind(volatile uint32_t *par, uint32_t a) {
+  uint32_t p = par[a] >> 16;
+  while (p != a) {
+    a = p;
+    p = par[a] >> 16;
+  }
+  return a;
+}
+__device__ __forceinline__ void lunion(uint32_t *par, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = lfind(par, a);
+    b = lfind(par, b);
+    if (a == b) return;
+    if (a < b) { uint32_t t = a; a = b; b = t; }
+    uint32_t old = atomicMin(&par[a], b << 16) >> 16;  // counts are still zero in this phase
+    if (old == a) return;
+    a = old;
   }
 }
 
-// union `me` with every run of the neighbour row word(s) that touches the run [s,e] of word xw.
-// wide: also x-1 / x+1 (edge neighbours); else only the same x (face neighbour).
-__device__ __forceinline__ void link_row(uint2 *nodes, uint32_t me, const uint32_t *__restrict__ nbrow,
-                                         long long nbword0, int xw, int w, uint32_t runmask, int s, int e, bool wide) {
-  uint32_t nw = __ldg(nbrow + xw);
-  uint32_t m = runmask;
-  if (wide) m |= (runmask << 1) | (runmask >> 1);
-  uint32_t t = nw & m;
-  while (t) {
-    int b = __ffs(t) - 1;
-    int st = run_start(nw, b);
-    int en = run_end(nw, st);
-    uf_union(nodes, me, (uint32_t)(nbword0 + xw) * 16u + (uint32_t)(st >> 1));
-    t &= ~bits_range(st, en);
-  }
-  if (wide) {
-    if (s == 0 && xw > 0) {
-      uint32_t pw = __ldg(nbrow + xw - 1);
-      if (pw >> 31) uf_union(nodes, me, (uint32_t)(nbword0 + xw - 1) * 16u + (uint32_t)(run_start(pw, 31) >> 1));
+// Enumerates the backward neighbour runs of run [s,e] (mask rm) of the word at tile-local (lx,ly,lz)
+// and calls link(neighbour word delta (dx,dy,dz), neighbour word bits, start bit of the neighbour run).
+// fetch(dx,dy,dz) returns the neighbour word's bits or 0 when that pair is not this phase's business.
+template <int CONN, class Fetch, class Link>
+__device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, Fetch fetch, Link link) {
+  auto row = [&](int dy, int dz, bool wide) {
+    const uint32_t nw = fetch(0, dy, dz);
+    uint32_t m = rm;
+    if (wide) m |= (rm << 1) | (rm >> 1);
+    uint32_t t = nw & m;
+    while (t) {
+      const int b = __ffs(t) - 1;
+      const int st = run_start(nw, b);
+      const int en = run_end(nw, st);
+      link(0, dy, dz, st);
+      t &= ~bits_range(st, en);
     }
-    if (e == 31 && xw < w - 1) {
-      uint32_t nx = __ldg(nbrow + xw + 1);
-      if (nx & 1u) uf_union(nodes, me, (uint32_t)(nbword0 + xw + 1) * 16u);
-    }
-  }
-}
-
-// conn = 6 or 18.  One thread per bit word; backward neighbours only (each pair linked once).
-__global__ void __launch_bounds__(256) k_cc_link(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes, int conn) {
-  long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (word >= g.nwords) return;
-  uint32_t wv = __ldg(bits + word);
-  if (!wv) return;
-  long long row = word / g.w;
-  int xw = (int)(word - row * g.w);
-  int z = (int)(row / g.ny);
-  int y = (int)(row - (long long)z * g.ny);
-  const bool wide = conn >= 18;
-  uint32_t rest = wv;
-  while (rest) {
-    int s = __ffs(rest) - 1;
-    int e = run_end(wv, s);
-    uint32_t rm = bits_range(s, e);
-    rest &= ~rm;
-    uint32_t me = (uint32_t)word * 16u + (uint32_t)(s >> 1);
-    if (s == 0 && xw > 0) {  // the run continues from the previous word of this row
-      uint32_t pw = __ldg(bits + word - 1);
-      if (pw >> 31) uf_union(nodes, me, (uint32_t)(word - 1) * 16u + (uint32_t)(run_start(pw, 31) >> 1));
-    }
-    if (y > 0) link_row(nodes, me, bits + (row - 1) * g.w, (row - 1) * g.w, xw, g.w, rm, s, e, wide);
-    if (z > 0) {
-      long long r2 = row - g.ny;
-      link_row(nodes, me, bits + r2 * g.w, r2 * g.w, xw, g.w, rm, s, e, wide);
-      if (wide) {
-        if (y > 0) link_row(nodes, me, bits + (r2 - 1) * g.w, (r2 - 1) * g.w, xw, g.w, rm, s, e, false);
-        if (y < g.ny - 1) link_row(nodes, me, bits + (r2 + 1) * g.w, (r2 + 1) * g.w, xw, g.w, rm, s, e, false);
+    if (wide) {
+      if (s == 0) {
+        const uint32_t pw = fetch(-1, dy, dz);
+        if (pw >> 31) link(-1, dy, dz, run_start(pw, 31));
+      }
+      if (e == 31) {
+        const uint32_t nx = fetch(1, dy, dz);
+        if (nx & 1u) link(1, dy, dz, 0);
       }
     }
+  };
+  if (s == 0) {  // the run continues from the previous word of this row
+    const uint32_t pw = fetch(-1, 0, 0);
+    if (pw >> 31) link(-1, 0, 0, run_start(pw, 31));
+  }
+  const bool wide = CONN >= 18;
+  row(-1, 0, wide);
+  row(0, -1, wide);
+  if (wide) {
+    row(-1, -1, false);
+    row(1, -1, false);
+  }
+}
+
+template <int CONN>
+__global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, uint2 *__restrict__ nodes) {
+  __shared__ uint32_t sb[CT_WORDS];
+  __shared__ uint32_t par[CT_WORDS * 16];
+  const int t = threadIdx.x;
+  const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
+  const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
+  const bool valid = xw < g.w && y < g.ny && z < g.nz;
+  const long long word = valid ? ((long long)z * g.ny + y) * g.w + xw : 0;
+  const uint32_t wv = valid ? __ldg(bits + word) : 0u;
+  sb[t] = wv;
+  {
+    uint32_t starts = wv & ~(wv << 1);
+    while (starts) {
+      const int s = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint32_t slot = (uint32_t)t * 16u + (uint32_t)(s >> 1);
+      par[slot] = slot << 16;
+    }
+  }
+  __syncthreads();
+  auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
+    const int ax = lx + dx, ay = ly + dy, az = lz + dz;
+    if ((unsigned)ax >= CT_W || (unsigned)ay >= CT_Y || (unsigned)az >= CT_Z) return 0u;  // other tile: k_cc_border
+    return sb[(az * CT_Y + ay) * CT_W + ax];
+  };
+  // phase A: unions inside the tile
+  for (uint32_t rest = wv; rest;) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    const uint32_t rm = bits_range(s, e);
+    rest &= ~rm;
+    const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
+    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st) {
+      const int nt = ((lz + dz) * CT_Y + (ly + dy)) * CT_W + (lx + dx);
+      lunion(par, me, (uint32_t)nt * 16u + (uint32_t)(st >> 1));
+    });
+  }
+  __syncthreads();
+  // phase B: local roots collect the voxel count and the face flag of their local component
+  const bool rowface = (y == 0) || (y == g.ny - 1) || (z == 0) || (z == g.nz - 1);
+  uint32_t myroot[16];  // local root per run of this word, in run order (<= 16 runs)
+  int nrun = 0;
+  for (uint32_t rest = wv; rest; nrun++) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    rest &= ~bits_range(s, e);
+    const uint32_t r = lfind(par, (uint32_t)t * 16u + (uint32_t)(s >> 1));
+    myroot[nrun] = r;
+    const int x0 = xw * 32 + s, x1 = xw * 32 + e;
+    atomicAdd(&par[r], (uint32_t)(e - s + 1));
+    if (rowface || x0 == 0 || x1 == g.nx - 1) atomicOr(&par[r], 0x8000u);
+  }
+  __syncthreads();
+  // phase C: publish the global nodes
+  const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_Y, tz0 = blockIdx.z * CT_Z;
+  nrun = 0;
+  for (uint32_t rest = wv; rest; nrun++) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    rest &= ~bits_range(s, e);
+    const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
+    const uint32_t r = myroot[nrun];
+    const int rt = (int)(r >> 4);
+    const int rx = rt % CT_W, ry = (rt / CT_W) % CT_Y, rz = rt / (CT_W * CT_Y);
+    const long long rword = ((long long)(tz0 + rz) * g.ny + (ty0 + ry)) * g.w + (tx0 + rx);
+    const uint32_t gparent = (uint32_t)rword * 16u + (r & 15u);
+    uint32_t stat = 0;
+    if (r == me) {
+      const uint32_t pe = par[me];
+      stat = (pe & 0x7fffu) | ((pe & 0x8000u) << 16);
+    }
+    nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)] = make_uint2(gparent, stat);
+  }
+}
+
+// neighbour pairs that straddle two tiles: global lock-free unions between (mostly) tile roots
+template <int CONN>
+__global__ void __launch_bounds__(256) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes) {
+  const long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (word >= g.nwords) return;
+  const long long rowi = word / g.w;
+  const int xw = (int)(word - rowi * g.w);
+  const int z = (int)(rowi / g.ny);
+  const int y = (int)(rowi - (long long)z * g.ny);
+  const int lx = xw % CT_W, ly = y % CT_Y, lz = z % CT_Z;
+  // only words on a tile face can have a backward neighbour in another tile
+  if (!(lx == 0 || lx == CT_W - 1 || ly == 0 || ly == CT_Y - 1 || lz == 0)) return;
+  const uint32_t wv = __ldg(bits + word);
+  if (!wv) return;
+  auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
+    const int ax = lx + dx, ay = ly + dy, az = lz + dz;
+    if ((unsigned)ax < CT_W && (unsigned)ay < CT_Y && (unsigned)az < CT_Z) return 0u;  // same tile: done locally
+    const int gx = xw + dx, gy = y + dy, gz = z + dz;
+    if (gx < 0 || gx >= g.w || gy < 0 || gy >= g.ny || gz < 0) return 0u;
+    return __ldg(bits + ((long long)gz * g.ny + gy) * g.w + gx);
+  };
+  for (uint32_t rest = wv; rest;) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    const uint32_t rm = bits_range(s, e);
+    rest &= ~rm;
+    const uint32_t me = (uint32_t)word * 16u + (uint32_t)(s >> 1);
+    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st) {
+      const long long nword = ((long long)(z + dz) * g.ny + (y + dy)) * g.w + (xw + dx);
+      uf_union(nodes, me, (uint32_t)nword * 16u + (uint32_t)(st >> 1));
+    });
   }
 }
 
@@ -158,45 +267,39 @@ __device__ __forceinline__ void flush_stats(uint2 *nodes, uint32_t root, uint32_
   }
 }
 
-// flatten every word run to its root; accumulate voxel counts (low 31 bits of node.y) and the
-// "touches a volume face" flag (bit 31) per root.
+// every tile root that lost its root status in k_cc_border hands the count / face flag of its local
+// component to its final root and is pointed straight at it (runs then reach the final root in two hops).
 __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes) {
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t wv = word < g.nwords ? __ldg(bits + word) : 0u;
-  long long row = word < g.nwords ? word / g.w : 0;
-  int xw = (int)(word - row * g.w);
-  int z = (int)(row / g.ny);
-  int y = (int)(row - (long long)z * g.ny);
-  const bool rowface = (y == 0) || (y == g.ny - 1) || (z == 0) || (z == g.nz - 1);
-  uint32_t curRoot = 0xffffffffu, curCnt = 0, curFlag = 0;
-  uint32_t rest = wv;
+  uint32_t starts = wv & ~(wv << 1);
   // all lanes iterate together until every lane is out of runs (keeps the match/reduce converged)
-  while (__any_sync(0xffffffffu, rest != 0)) {
+  while (__any_sync(0xffffffffu, starts != 0)) {
     uint32_t root = 0xffffffffu, cnt = 0, flag = 0;
-    if (rest) {
-      int s = __ffs(rest) - 1;
-      int e = run_end(wv, s);
-      uint32_t rm = bits_range(s, e);
-      rest &= ~rm;
-      uint32_t slot = (uint32_t)word * 16u + (uint32_t)(s >> 1);
-      root = uf_find(nodes, slot);
-      if (root != slot) atomicMin(&nodes[slot].x, root);
-      cnt = (uint32_t)(e - s + 1);
-      int x0 = xw * 32 + s, x1 = xw * 32 + e;
-      flag = (rowface || x0 == 0 || x1 == g.nx - 1) ? 1u : 0u;
+    if (starts) {
+      const int s = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint32_t slot = (uint32_t)word * 16u + (uint32_t)(s >> 1);
+      const uint2 nd = nodes[slot];
+      if ((nd.y & 0x7fffffffu) && nd.x != slot) {  // a tile root (it owns a count) that is no longer a root
+        root = uf_find(nodes, slot);
+        atomicMin(&nodes[slot].x, root);
+        cnt = nd.y & 0x7fffffffu;
+        flag = nd.y >> 31;
+      }
     }
-    if (root == curRoot) {
-      curCnt += cnt;
-      curFlag |= flag;
-      root = 0xffffffffu; cnt = 0; flag = 0;
-    }
-    // flush the previous accumulator of lanes whose root changed
-    bool changed = root != 0xffffffffu;
-    uint32_t fr = changed ? curRoot : 0xffffffffu, fc = changed ? curCnt : 0, ff = changed ? curFlag : 0;
-    if (__any_sync(0xffffffffu, fr != 0xffffffffu)) flush_stats(nodes, fr, fc, ff);
-    if (changed) { curRoot = root; curCnt = cnt; curFlag = flag; }
+    if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
   }
-  flush_stats(nodes, curRoot, curCnt, curFlag);
+}
+
+// final root of a run after k_cc_flatten: run -> tile root -> final root
+__device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ nodes, uint32_t slot) {
+  uint32_t p = nodes[slot].x;
+  while (p != slot) {
+    slot = p;
+    p = nodes[slot].x;
+  }
+  return slot;
 }
 
 // number of components and the largest one: key = (size << 32) | ~rootslot, so that among equal
@@ -253,7 +356,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
       int e = run_end(wv, s);
       uint32_t rm = bits_range(s, e);
       rest &= ~rm;
-      if (nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)].x == bestslot) res |= rm;
+      if (cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1)) == bestslot) res |= rm;
     }
   } else {
     res = __ldg(other + word);
@@ -264,7 +367,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
         int e = run_end(wv, s);
         uint32_t rm = bits_range(s, e);
         rest &= ~rm;
-        uint32_t root = nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)].x;
+        uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
         if (!(nodes[root].y >> 31)) res |= rm;
       }
     }
@@ -274,51 +377,75 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
 
 // keep = largest | dilate25(largest) (interior voxels only), and the bounding box of the bright
 // voxels  bright = fillOrFg & keep  (keep == all ones when largest == nullptr).
+// A thread owns one bit-word column (xw, y) and marches along z: per new plane it loads the three
+// rows y-1, y, y+1 once (x neighbours by funnel shifts with the adjacent words) and keeps
+//   PF(z) = OR over dy of full(y+dy, z),  full = c | c<<1 | c>>1 (with carries)    [all 9 in-plane taps]
+//   Q(z)  = full(y,z) | full(y+1,z) | nol(y-1,z),  nol = c | c>>1                  [plane z-1 taps: the
+//           reference's dilate() never tests offset (-1,-1,-1), src/meshify.c:252]
+// so that out(z) = Q(z-1) | PF(z) | PF(z+1): 3 word loads per output word instead of 27.
+#define DIL_ZC 16
 __global__ void __launch_bounds__(256) k_dilate_bbox(const uint32_t *__restrict__ largest,
                                                      const uint32_t *__restrict__ bright_src, cc_geom g,
                                                      uint32_t *__restrict__ keep, int *__restrict__ lohi) {
-  long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (y, xw) flattened
+  const long long ncol = (long long)g.ny * g.w;
   int lo0 = INT_MAX, lo1 = INT_MAX, lo2 = INT_MAX, hi0 = -1, hi1 = -1, hi2 = -1;
-  if (word < g.nwords) {
-    long long row = word / g.w;
-    int xw = (int)(word - row * g.w);
-    int z = (int)(row / g.ny);
-    int y = (int)(row - (long long)z * g.ny);
-    uint32_t k = 0xffffffffu;
-    if (largest) {
-      k = __ldg(largest + word);
-      if (y >= 1 && y <= g.ny - 2 && z >= 1 && z <= g.nz - 2) {
-        uint32_t acc = 0;
-#pragma unroll
-        for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-          for (int dy = -1; dy <= 1; dy++) {
-            const uint32_t *r = largest + (row + dy + (long long)dz * g.ny) * g.w;
-            uint32_t c = __ldg(r + xw);
-            uint32_t p = xw > 0 ? __ldg(r + xw - 1) : 0u;
-            uint32_t n = xw < g.w - 1 ? __ldg(r + xw + 1) : 0u;
-            uint32_t left = (c << 1) | (p >> 31);   // bit x = voxel x-1  (neighbour dx = -1)
-            uint32_t right = (c >> 1) | (n << 31);  // bit x = voxel x+1  (neighbour dx = +1)
-            acc |= c | right;
-            if (!(dz == -1 && dy == -1)) acc |= left;  // (-1,-1,-1) is never tested (meshify.c:252)
-          }
-        // interior x only: 1 .. nx-2
-        int xb = xw * 32;
-        uint32_t im = 0xffffffffu;
-        if (xb == 0) im &= ~1u;
-        int last = g.nx - 2 - xb;  // highest interior bit in this word
-        if (last < 0) im = 0;
-        else if (last < 31) im &= (2u << last) - 1u;
-        k |= acc & im;
-      }
-      keep[word] = k;
+  if (col < ncol) {
+    const int y = (int)(col / g.w), xw = (int)(col - (long long)y * g.w);
+    const int z0 = blockIdx.y * DIL_ZC, z1 = min(z0 + DIL_ZC, g.nz);
+    const long long plane = ncol;
+    // interior x mask of this word: voxels 1 .. nx-2
+    uint32_t im = 0xffffffffu;
+    {
+      const int xb = xw * 32;
+      if (xb == 0) im &= ~1u;
+      const int last = g.nx - 2 - xb;  // highest interior bit in this word
+      if (last < 0) im = 0;
+      else if (last < 31) im &= (2u << last) - 1u;
     }
-    uint32_t b = __ldg(bright_src + word) & k;
-    if (b) {
-      lo0 = xw * 32 + __ffs(b) - 1;
-      hi0 = xw * 32 + 31 - __clz(b);
-      lo1 = hi1 = y;
-      lo2 = hi2 = z;
+    const bool yin = y >= 1 && y <= g.ny - 2;
+    uint32_t Qm1 = 0, PF0 = 0, Q0 = 0, c0 = 0;  // Q(z-1), PF(z), Q(z), largest word at z
+    auto load_plane = [&](int z, uint32_t &PF, uint32_t &Q, uint32_t &cc) {
+      PF = Q = cc = 0;
+      if (z < 0 || z >= g.nz) return;
+      const uint32_t *base = largest + (long long)z * plane + col;
+#pragma unroll
+      for (int dy = -1; dy <= 1; dy++) {
+        if (y + dy < 0 || y + dy >= g.ny) continue;
+        const uint32_t *r = base + (long long)dy * g.w;
+        const uint32_t c = __ldg(r);
+        const uint32_t pw = xw > 0 ? __ldg(r - 1) : 0u;
+        const uint32_t nw = xw < g.w - 1 ? __ldg(r + 1) : 0u;
+        const uint32_t left = (c << 1) | (pw >> 31);   // bit x = voxel x-1
+        const uint32_t right = (c >> 1) | (nw << 31);  // bit x = voxel x+1
+        PF |= c | left | right;
+        Q |= (dy == -1) ? (c | right) : (c | left | right);
+        if (dy == 0) cc = c;
+      }
+    };
+    if (largest) {
+      uint32_t t0, t1;
+      load_plane(z0 - 1, t0, Qm1, t1);
+      load_plane(z0, PF0, Q0, c0);
+    }
+    for (int z = z0; z < z1; z++) {
+      const long long word = (long long)z * plane + col;
+      uint32_t k = 0xffffffffu;
+      if (largest) {
+        uint32_t PF1, Q1, c1;
+        load_plane(z + 1, PF1, Q1, c1);
+        k = c0;
+        if (yin && z >= 1 && z <= g.nz - 2) k |= (Qm1 | PF0 | PF1) & im;
+        keep[word] = k;
+        Qm1 = Q0; PF0 = PF1; Q0 = Q1; c0 = c1;
+      }
+      const uint32_t bb = __ldg(bright_src + word) & k;
+      if (bb) {
+        lo0 = min(lo0, xw * 32 + __ffs(bb) - 1);
+        hi0 = max(hi0, xw * 32 + 31 - __clz(bb));
+        lo1 = min(lo1, y); hi1 = max(hi1, y);
+        lo2 = min(lo2, z); hi2 = max(hi2, z);
+      }
     }
   }
   lo0 = __reduce_min_sync(0xffffffffu, lo0); lo1 = __reduce_min_sync(0xffffffffu, lo1); lo2 = __reduce_min_sync(0xffffffffu, lo2);
@@ -367,8 +494,14 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
 
 static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2 *nodes, int conn) {
   unsigned blocks = b2m_cdiv(cg.nwords, 256);
-  KT_LAUNCH(ctx, "cc_init", k_cc_init<<<blocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes));
-  KT_LAUNCH(ctx, "cc_link", k_cc_link<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes, conn));
+  dim3 tiles(b2m_cdiv(cg.w, CT_W), b2m_cdiv(cg.ny, CT_Y), b2m_cdiv(cg.nz, CT_Z));
+  if (conn >= 18) {
+    KT_LAUNCH(ctx, "cc_local", k_cc_local<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_border", k_cc_border<18><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
+  } else {
+    KT_LAUNCH(ctx, "cc_local", k_cc_local<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_border", k_cc_border<6><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
+  }
   KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
@@ -420,7 +553,10 @@ int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *
     KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest));
     fo->keep = keep;
   }
-  KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<blocks, 256, 0, ctx->stream>>>(largest, bright, cg, keep, d_sc->lo));
+  {
+    dim3 dgrid(b2m_cdiv((size_t)g.ny * g.w, 256), b2m_cdiv(g.nz, DIL_ZC));
+    KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<dgrid, 256, 0, ctx->stream>>>(largest, bright, cg, keep, d_sc->lo));
+  }
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

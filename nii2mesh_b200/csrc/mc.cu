@@ -37,8 +37,8 @@ struct mc_params {
   int classic;      // backend == CLASSIC
   int original_mc;
   const signed char *tab;
-  uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks
-  uint32_t *segv, *segt, *segc;  // per segment counts -> exclusive prefix (in place)
+  uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks, .w = packed counts -> vertex base (scan3)
+  uint32_t *segt, *segc;  // per segment exclusive triangle / centroid-vertex bases
   uint4 *active;
   unsigned int active_cap;
   b2m_scalars *sc;
@@ -208,109 +208,329 @@ __device__ void mc33_select(const signed char *__restrict__ tab, const float *c,
 }
 
 // ---- pass A: classify ------------------------------------------------------------------------
-// One warp per 32-voxel segment of a sub-volume row; a CTA covers 8 consecutive rows so that the
-// y+1 row of warp k is the y row of warp k+1 (L1 reuse); z+1 rows are re-read through L2.
-#define MCA_ROWS 8
-__global__ void __launch_bounds__(32 * MCA_ROWS) k_mc_classify(mc_params p) {
-  const unsigned lane = threadIdx.x & 31;
-  const int seg = blockIdx.x;
-  const int y = blockIdx.y * MCA_ROWS + (threadIdx.x >> 5);
-  const int z = blockIdx.z;
-  if (y >= p.sy) return;  // whole warp
+// Warps are independent (no barriers): a warp owns 32 x-columns x MCC_ROWS rows of the sub-volume
+// and marches along z.  Per plane every lane evaluates the inside/outside BIT of its column for
+// MCC_ROWS+1 rows (9 independent loads in flight), so classification works on four 9-bit masks
+// per lane (this plane / next plane, own column / x+1 column via one shuffle); corner VALUES are
+// only re-read for the rare ambiguous MC33 cubes.  Active voxels are appended to a warp-private
+// shared-memory buffer and flushed to the global list with one atomic per ~100 records (a
+// same-address atomic per warp-row serialises in L2 and dominated the first version).
+// Per 32-voxel segment the kernel leaves {xbits, ybits, zbits, packed counts}; packed counts =
+// nv | nt << 7 | nc << 16 (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.
+#define MCC_ROWS 8
+#define MCC_WARPS 4
+#define MCC_ZC 64
+#define MCC_BUF 160
+
+__device__ __forceinline__ bool mc_inside_at(const mc_params &p, int x, int y, int z) {
+  // inside/outside bit of sub-volume voxel (x,y,z): identical to mc_inside(mc_data()) with a short
+  // path for voxels inside the volume (no wrap, no pad)
+  const int gx = p.lo0 + x, gy = p.lo1 + y, gz = p.lo2 + z;
+  if (gx < p.c.nx && gy < p.c.ny && gz < p.c.nz) {
+    const float v = composed_value(p.c, gx, gy, gz);
+    return p.classic ? (v < p.c.iso) : (__fsub_rn(v, p.c.iso) > -FLT_EPSILON);
+  }
+  return mc_inside(p, mc_data(p, x, y, z));
+}
+
+// 9-bit inside masks of plane z for this lane's column (rows ybase..ybase+8) and for column x+1.
+// Generic version: every bounds / wrap / pad case (boundary warps only).
+__device__ __noinline__ unsigned mc_plane_masks_slow(const mc_params &p, int seg, int ybase, int z, unsigned lane,
+                                                     unsigned &mx) {
   const int x = seg * 32 + (int)lane;
-  const size_t row = (size_t)z * p.sy + y;
-  const bool vx = x < p.sx, vy1 = y + 1 < p.sy, vz1 = z + 1 < p.sz;
-  // this lane's column at the four rows (y,z) (y+1,z) (y,z+1) (y+1,z+1); lane 0 also fetches x+32
-  float d00 = 0.f, d10 = 0.f, d01 = 0.f, d11 = 0.f, e00 = 0.f, e10 = 0.f, e01 = 0.f, e11 = 0.f;
-  if (vx) {
-    d00 = mc_data(p, x, y, z);
-    if (vy1) d10 = mc_data(p, x, y + 1, z);
-    if (vz1) d01 = mc_data(p, x, y, z + 1);
-    if (vy1 && vz1) d11 = mc_data(p, x, y + 1, z + 1);
-  }
-  const int xe = seg * 32 + 32;
-  if (lane == 0 && xe < p.sx) {
-    e00 = mc_data(p, xe, y, z);
-    if (vy1) e10 = mc_data(p, xe, y + 1, z);
-    if (vz1) e01 = mc_data(p, xe, y, z + 1);
-    if (vy1 && vz1) e11 = mc_data(p, xe, y + 1, z + 1);
-  }
-  float c[8];
-  c[0] = d00; c[3] = d10; c[4] = d01; c[7] = d11;
-  {
-    float n00 = __shfl_down_sync(0xffffffffu, d00, 1), n10 = __shfl_down_sync(0xffffffffu, d10, 1);
-    float n01 = __shfl_down_sync(0xffffffffu, d01, 1), n11 = __shfl_down_sync(0xffffffffu, d11, 1);
-    float x00 = __shfl_sync(0xffffffffu, e00, 0), x10 = __shfl_sync(0xffffffffu, e10, 0);
-    float x01 = __shfl_sync(0xffffffffu, e01, 0), x11 = __shfl_sync(0xffffffffu, e11, 0);
-    c[1] = lane == 31 ? x00 : n00; c[2] = lane == 31 ? x10 : n10;
-    c[5] = lane == 31 ? x01 : n01; c[6] = lane == 31 ? x11 : n11;
-  }
-  const bool vx1 = x + 1 < p.sx;
-  const bool in0 = mc_inside(p, c[0]);
-  const bool ex = vx && vx1 && (in0 != mc_inside(p, c[1]));
-  const bool ey = vx && vy1 && (in0 != mc_inside(p, c[3]));
-  const bool ez = vx && vz1 && (in0 != mc_inside(p, c[4]));
-  int ntri = 0, hasc = 0, off = 0, lut = 0;
-  if (vx1 && vy1 && vz1) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) lut |= mc_inside(p, c[q]) ? (1 << q) : 0;
-    if (lut != 0 && lut != 255) {
-      if (p.classic) {
-        int o = MCT_casesClassic + 16 * lut, n = 0;
-        while (n < 5 && p.tab[o + 3 * n] != -1) n++;
-        off = o; ntri = n;
-      } else {
-        mc33_select(p.tab, c, lut, p.original_mc, off, ntri, hasc);
-      }
+  unsigned m = 0;
+  if (z < p.sz) {
+    if (x < p.sx) {
+      for (int r = 0; r <= MCC_ROWS; r++)
+        if (ybase + r < p.sy) m |= (mc_inside_at(p, x, ybase + r, z) ? 1u : 0u) << r;
     }
   }
-  const unsigned xb = __ballot_sync(0xffffffffu, ex), yb = __ballot_sync(0xffffffffu, ey), zb = __ballot_sync(0xffffffffu, ez);
-  const int nv = (int)ex + (int)ey + (int)ez;
-  // warp exclusive prefixes of (nv, ntri, hasc)
-  int pv = nv, pt = ntri, pc = hasc;
+  bool hin = false;
+  const int xe = seg * 32 + 32;
+  if (lane <= MCC_ROWS && z < p.sz && xe < p.sx && ybase + (int)lane < p.sy) hin = mc_inside_at(p, xe, ybase + (int)lane, z);
+  const unsigned hm = __ballot_sync(0xffffffffu, hin);
+  mx = __shfl_down_sync(0xffffffffu, m, 1);
+  if (lane == 31) mx = hm;
+  return m;
+}
+
+// inside bit of one in-volume voxel: S value, optional fill / keep bit-row words (offset `wo` from the
+// array base), face darkening.  FILL/KEEP are compile-time so that no null pointer is ever formed.
+template <bool FILL, bool KEEP>
+__device__ __forceinline__ bool mc_inside_fast(const mc_params &p, size_t so, size_t wo, unsigned bit, bool face) {
+  float v = __ldg(p.c.S + so);
+  if (FILL) { if ((__ldg(p.c.fill + wo) >> bit) & 1u) v = fmaxf(v, p.c.iso); }
+  if (KEEP) { if (!((__ldg(p.c.keep + wo) >> bit) & 1u)) v = p.c.mn; }
+  if (face) v = fminf(p.c.edge_max, v);
+  return p.classic ? (v < p.c.iso) : (__fsub_rn(v, p.c.iso) > -FLT_EPSILON);
+}
+
+// interior: all 33 columns, 9 rows and the plane lie inside the sub-volume AND the volume (warp-uniform
+// test), so there is no wrap/pad and the addresses advance by constant strides.
+template <bool FILL, bool KEEP>
+__device__ __forceinline__ unsigned mc_plane_masks_fast(const mc_params &p, int seg, int ybase, int z, unsigned lane,
+                                                        unsigned &mx) {
+  const int gz = p.lo2 + z;
+  const int gx = p.lo0 + seg * 32 + (int)lane, gy0 = p.lo1 + ybase;
+  const size_t row0 = (size_t)gz * p.c.ny + gy0;
+  const size_t so = row0 * p.c.nx + gx, wo = row0 * p.c.w + (gx >> 5);
+  const bool zxface = gz == 0 || gz == p.c.nz - 1 || gx == 0 || gx == p.c.nx - 1;
+  unsigned m = 0;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int a = __shfl_up_sync(0xffffffffu, pv, d), b = __shfl_up_sync(0xffffffffu, pt, d), cc = __shfl_up_sync(0xffffffffu, pc, d);
-    if (lane >= (unsigned)d) { pv += a; pt += b; pc += cc; }
+  for (int r = 0; r <= MCC_ROWS; r++) {
+    const bool face = zxface || gy0 + r == 0 || gy0 + r == p.c.ny - 1;
+    const bool in = mc_inside_fast<FILL, KEEP>(p, so + (size_t)(r * p.c.nx), wo + (size_t)(r * p.c.w), (unsigned)gx & 31u, face);
+    m |= (in ? 1u : 0u) << r;
   }
-  const int tv = __shfl_sync(0xffffffffu, pv, 31), tt = __shfl_sync(0xffffffffu, pt, 31), tc = __shfl_sync(0xffffffffu, pc, 31);
-  pv -= nv; pt -= ntri; pc -= hasc;
-  const size_t sidx = row * p.segs + seg;
-  if (lane == 0) {
-    p.segbits[sidx] = make_uint4(xb, yb, zb, 0u);
-    p.segv[sidx] = (uint32_t)tv;
-    p.segt[sidx] = (uint32_t)tt;
-    p.segc[sidx] = (uint32_t)tc;
+  // halo column x = seg*32 + 32: lane r evaluates row r
+  bool hin = false;
+  if (lane <= MCC_ROWS) {
+    const int hx = p.lo0 + seg * 32 + 32;
+    const size_t hrow = row0 + lane;
+    const bool face = gz == 0 || gz == p.c.nz - 1 || hx == 0 || hx == p.c.nx - 1 || gy0 + (int)lane == 0 ||
+                      gy0 + (int)lane == p.c.ny - 1;
+    hin = mc_inside_fast<FILL, KEEP>(p, hrow * p.c.nx + hx, hrow * p.c.w + (hx >> 5), (unsigned)hx & 31u, face);
+  }
+  const unsigned hm = __ballot_sync(0xffffffffu, hin);
+  mx = __shfl_down_sync(0xffffffffu, m, 1);
+  if (lane == 31) mx = hm;
+  return m;
+}
+
+__device__ __forceinline__ unsigned mc_plane_masks(const mc_params &p, int seg, int ybase, int z, unsigned lane,
+                                                   unsigned &mx, bool interior_xy) {
+  if (!(interior_xy && z < p.sz && p.lo2 + z < p.c.nz)) return mc_plane_masks_slow(p, seg, ybase, z, lane, mx);
+  if (p.c.fill) {
+    if (p.c.keep) return mc_plane_masks_fast<true, true>(p, seg, ybase, z, lane, mx);
+    return mc_plane_masks_fast<true, false>(p, seg, ybase, z, lane, mx);
+  }
+  if (p.c.keep) return mc_plane_masks_fast<false, true>(p, seg, ybase, z, lane, mx);
+  return mc_plane_masks_fast<false, false>(p, seg, ybase, z, lane, mx);
+}
+
+__global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_constant__ mc_params p) {
+  __shared__ uint4 rbuf[MCC_WARPS][MCC_BUF];
+  const unsigned lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5;
+  const int seg = blockIdx.x;
+  const int ybase = (blockIdx.y * MCC_WARPS + wrp) * MCC_ROWS;
+  if (ybase >= p.sy) return;  // whole warp; no block-level barriers in this kernel
+  const int z0 = blockIdx.z * MCC_ZC;
+  const int z1 = min(z0 + MCC_ZC, p.sz);
+  const int x = seg * 32 + (int)lane;
+  const bool vx = x < p.sx, vx1 = x + 1 < p.sx;
+  const int nyv = min(MCC_ROWS + 1, p.sy - ybase);             // valid rows among the 9
+  const unsigned rowsv = (1u << min(nyv, MCC_ROWS)) - 1u;      // rows r < 8 that exist
+  const unsigned vy1m = (1u << (nyv - 1)) - 1u;                // rows r whose r+1 exists
+  uint4 *mybuf = rbuf[wrp];
+  unsigned cnt = 0;  // records parked in mybuf (warp-uniform)
+  unsigned long long first = ~0ull;
+  unsigned a, b;     // plane z: own column, x+1 column
+  // warp-uniform: the 33 columns and 9 rows this warp touches exist in the sub-volume and in the volume
+  const bool interior_xy = seg * 32 + 32 < p.sx && p.lo0 + seg * 32 + 32 < p.c.nx && ybase + MCC_ROWS < p.sy &&
+                           p.lo1 + ybase + MCC_ROWS < p.c.ny;
+  a = mc_plane_masks(p, seg, ybase, z0, lane, b, interior_xy);
+  for (int z = z0; z < z1; z++) {
+    unsigned c, d;   // plane z+1
+    c = mc_plane_masks(p, seg, ybase, z + 1, lane, d, interior_xy);
+    const bool vz1 = z + 1 < p.sz;
+    const unsigned exm = (vx && vx1) ? ((a ^ b) & rowsv) : 0u;
+    const unsigned eym = vx ? ((a ^ (a >> 1)) & vy1m) : 0u;
+    const unsigned ezm = (vx && vz1) ? ((a ^ c) & rowsv) : 0u;
+    const unsigned orm = a | (a >> 1) | b | (b >> 1) | c | (c >> 1) | d | (d >> 1);
+    const unsigned andm = a & (a >> 1) & b & (b >> 1) & c & (c >> 1) & d & (d >> 1);
+    const unsigned trim = (vx1 && vz1) ? ((orm & ~andm) & vy1m) : 0u;
+    const unsigned rows_active = __reduce_or_sync(0xffffffffu, exm | eym | ezm | trim);
+    if (lane < MCC_ROWS && ((rowsv & ~rows_active) >> lane) & 1u)
+      p.segbits[((size_t)z * p.sy + ybase + lane) * p.segs + seg] = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned ra = rows_active; ra; ra &= ra - 1) {
+      const int r = __ffs(ra) - 1;
+      const size_t row = (size_t)z * p.sy + ybase + r;
+      const bool ex = (exm >> r) & 1u, ey = (eym >> r) & 1u, ez = (ezm >> r) & 1u, tri = (trim >> r) & 1u;
+      int ntri = 0, hasc = 0, off = 0, lut = 0;
+      if (tri) {
+        lut = (int)(((a >> r) & 1u) | (((b >> r) & 1u) << 1) | (((b >> (r + 1)) & 1u) << 2) | (((a >> (r + 1)) & 1u) << 3) |
+                    (((c >> r) & 1u) << 4) | (((d >> r) & 1u) << 5) | (((d >> (r + 1)) & 1u) << 6) | (((c >> (r + 1)) & 1u) << 7));
+        if (p.classic || p.original_mc) {
+          int o = MCT_casesClassic + 16 * lut, n = 0;
+          while (n < 5 && p.tab[o + 3 * n] != -1) n++;
+          off = o; ntri = n;
+        } else {
+          const int kase = p.tab[MCT_cases + 2 * lut];
+          float cv[8];
+          if (kase == 3 || kase == 4 || kase == 6 || kase == 7 || kase == 10 || kase == 12 || kase == 13) {
+            const int y = ybase + r;  // ambiguous: the face / interior tests need the corner values
+            cv[0] = mc_data(p, x, y, z); cv[1] = mc_data(p, x + 1, y, z); cv[2] = mc_data(p, x + 1, y + 1, z);
+            cv[3] = mc_data(p, x, y + 1, z); cv[4] = mc_data(p, x, y, z + 1); cv[5] = mc_data(p, x + 1, y, z + 1);
+            cv[6] = mc_data(p, x + 1, y + 1, z + 1); cv[7] = mc_data(p, x, y + 1, z + 1);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) cv[q] = 0.f;
+          }
+          mc33_select(p.tab, cv, lut, 0, off, ntri, hasc);
+        }
+      }
+      const unsigned xb = __ballot_sync(0xffffffffu, ex), yb = __ballot_sync(0xffffffffu, ey), zb = __ballot_sync(0xffffffffu, ez);
+      const int nv = (int)ex + (int)ey + (int)ez;
+      const int pk = nv | (ntri << 7) | (hasc << 16);
+      int incl = pk;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= (unsigned)dd) incl += t;
+      }
+      const int tot = __shfl_sync(0xffffffffu, incl, 31);
+      const int excl = incl - pk;
+      if (lane == 0) p.segbits[row * p.segs + seg] = make_uint4(xb, yb, zb, (uint32_t)tot);
+      if (p.classic && ntri > 0) {
+        unsigned long long key = ((unsigned long long)row << 16) | (unsigned long long)x;
+        first = key < first ? key : first;
+      }
+      const bool act = nv > 0 || ntri > 0;
+      const unsigned am = __ballot_sync(0xffffffffu, act);
+      const unsigned n = __popc(am);
+      if (cnt + n > MCC_BUF) {  // flush the warp-private buffer
+        __syncwarp();
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&p.sc->n_active, cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (unsigned i = lane; i < cnt; i += 32)
+          if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
+        __syncwarp();
+        cnt = 0;
+      }
+      if (act) {
+        const int pv = excl & 127, pt = (excl >> 7) & 511, pc = (excl >> 16) & 63;
+        uint4 rec;
+        rec.x = (uint32_t)row;
+        rec.y = (uint32_t)x | ((uint32_t)ex << 16) | ((uint32_t)ey << 17) | ((uint32_t)ez << 18) | ((uint32_t)ntri << 19) |
+                ((uint32_t)hasc << 23) | ((uint32_t)pc << 24);
+        rec.z = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)off << 16);
+        rec.w = (uint32_t)lut;
+        mybuf[cnt + __popc(am & ((1u << lane) - 1u))] = rec;
+      }
+      cnt += n;
+    }
+    a = c;
+    b = d;
+  }
+  __syncwarp();
+  if (cnt) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&p.sc->n_active, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned i = lane; i < cnt; i += 32)
+      if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
   }
   if (p.classic) {  // first active cube in raster order: its first soup vertex is the weld's pts[0]
-    unsigned long long key = ntri > 0 ? (((unsigned long long)row << 16) | (unsigned long long)x) : ~0ull;
 #pragma unroll
-    for (int d = 16; d; d >>= 1) {
-      unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
-      key = o < key ? o : key;
+    for (int dd = 16; dd; dd >>= 1) {
+      unsigned long long o = __shfl_xor_sync(0xffffffffu, first, dd);
+      first = o < first ? o : first;
     }
-    if (lane == 0 && key != ~0ull && key < *(volatile unsigned long long *)&p.sc->first_cube)
-      atomicMin(&p.sc->first_cube, key);
+    if (lane == 0 && first != ~0ull) atomicMin(&p.sc->first_cube, first);
   }
-  const bool act = nv > 0 || ntri > 0;
-  const unsigned am = __ballot_sync(0xffffffffu, act);
-  if (am) {
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&p.sc->n_active, (unsigned)__popc(am));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (act) {
-      unsigned pos = base + __popc(am & ((1u << lane) - 1u));
-      if (pos < p.active_cap) {
-        uint4 r;
-        r.x = (uint32_t)row;
-        r.y = (uint32_t)x | ((uint32_t)ex << 16) | ((uint32_t)ey << 17) | ((uint32_t)ez << 18) | ((uint32_t)ntri << 19) |
-              ((uint32_t)hasc << 23) | ((uint32_t)pc << 24);
-        r.z = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)off << 16);
-        r.w = (uint32_t)lut;
-        p.active[pos] = r;
-      }
-    }
+}
+
+// scan3: the packed per-segment counts (segbits[].w = nv | nt<<7 | nc<<16) -> exclusive bases
+// segbits[].w = vbase, segt[] = tbase, segc[] = cbase; totals -> sc->tot_v/tot_t/tot_c.
+#define S3_THREADS 256
+#define S3_ITEMS 8
+#define S3_TILE (S3_THREADS * S3_ITEMS)
+struct u3 { uint32_t v, t, c; };
+__device__ __forceinline__ u3 u3_add(u3 a, u3 b) { return {a.v + b.v, a.t + b.t, a.c + b.c}; }
+__device__ __forceinline__ u3 u3_unpack(uint32_t w) { return {w & 127u, (w >> 7) & 511u, w >> 16}; }
+__device__ __forceinline__ u3 warp_incl_scan3(u3 a) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t v = __shfl_up_sync(0xffffffffu, a.v, d), t = __shfl_up_sync(0xffffffffu, a.t, d), c = __shfl_up_sync(0xffffffffu, a.c, d);
+    if (lane >= (unsigned)d) { a.v += v; a.t += t; a.c += c; }
   }
+  return a;
+}
+// exclusive block scan of one u3 per thread; *total = block sum.  sm: 33 entries
+__device__ __forceinline__ u3 block_excl_scan3(u3 a, u3 *total, u3 *sm) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  u3 inc = warp_incl_scan3(a);
+  if (lane == 31) sm[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    u3 w = lane < nwarp ? sm[lane] : u3{0, 0, 0};
+    u3 winc = warp_incl_scan3(w);
+    sm[lane] = {winc.v - w.v, winc.t - w.t, winc.c - w.c};
+    if (lane == 31) sm[32] = winc;
+  }
+  __syncthreads();
+  u3 base = sm[warp];
+  u3 res = {inc.v - a.v + base.v, inc.t - a.t + base.t, inc.c - a.c + base.c};
+  *total = sm[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(S3_THREADS) k_scan3_reduce(const uint4 *__restrict__ seg, size_t n, uint32_t *__restrict__ part,
+                                                             size_t nblk) {
+  __shared__ u3 sm[33];
+  size_t base = (size_t)blockIdx.x * S3_TILE;
+  u3 s = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < S3_ITEMS; i++) {
+    size_t idx = base + (size_t)i * S3_THREADS + threadIdx.x;
+    if (idx < n) s = u3_add(s, u3_unpack(__ldg(&seg[idx].w)));
+  }
+  u3 tot;
+  block_excl_scan3(s, &tot, sm);
+  if (threadIdx.x == 0) { part[blockIdx.x] = tot.v; part[nblk + blockIdx.x] = tot.t; part[2 * nblk + blockIdx.x] = tot.c; }
+}
+
+// one block: exclusive scan of the three partial arrays in place; totals -> tot[0..2]
+__global__ void __launch_bounds__(1024) k_scan3_single(uint32_t *part, size_t nblk, unsigned int *tot) {
+  __shared__ u3 sm[33];
+  u3 carry = {0, 0, 0};
+  for (size_t base = 0; base < nblk; base += blockDim.x) {
+    size_t idx = base + threadIdx.x;
+    u3 v = idx < nblk ? u3{part[idx], part[nblk + idx], part[2 * nblk + idx]} : u3{0, 0, 0};
+    u3 t;
+    u3 ex = block_excl_scan3(v, &t, sm);
+    if (idx < nblk) { part[idx] = ex.v + carry.v; part[nblk + idx] = ex.t + carry.t; part[2 * nblk + idx] = ex.c + carry.c; }
+    carry = u3_add(carry, t);
+  }
+  if (threadIdx.x == 0) { tot[0] = carry.v; tot[1] = carry.t; tot[2] = carry.c; }
+}
+
+__global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ seg, size_t n, const uint32_t *__restrict__ part,
+                                                            size_t nblk, uint32_t *__restrict__ segt, uint32_t *__restrict__ segc) {
+  __shared__ u3 sm[33];
+  size_t base = (size_t)blockIdx.x * S3_TILE + (size_t)threadIdx.x * S3_ITEMS;
+  u3 v[S3_ITEMS];
+  u3 s = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < S3_ITEMS; i++) {
+    size_t idx = base + i;
+    v[i] = idx < n ? u3_unpack(seg[idx].w) : u3{0, 0, 0};
+    s = u3_add(s, v[i]);
+  }
+  u3 tot;
+  u3 ex = block_excl_scan3(s, &tot, sm);
+  ex = u3_add(ex, u3{part[blockIdx.x], part[nblk + blockIdx.x], part[2 * nblk + blockIdx.x]});
+#pragma unroll
+  for (int i = 0; i < S3_ITEMS; i++) {
+    size_t idx = base + i;
+    if (idx < n) { seg[idx].w = ex.v; segt[idx] = ex.t; segc[idx] = ex.c; }
+    ex = u3_add(ex, v[i]);
+  }
+}
+
+static int mc_scan3(b2m_ctx *ctx, mc_params &p, size_t nseg, b2m_scalars *d_sc) {
+  size_t nblk = (nseg + S3_TILE - 1) / S3_TILE;
+  B2M_TRY(b2m_reserve(ctx, BUF_SCAN1, nblk * 3 * 4));
+  uint32_t *part = b2m_ptr<uint32_t>(ctx, BUF_SCAN1);
+  KT_LAUNCH(ctx, "scan3_reduce", k_scan3_reduce<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk));
+  KT_LAUNCH(ctx, "scan3_single", k_scan3_single<<<1, 1024, 0, ctx->stream>>>(part, nblk, &d_sc->tot_v));
+  KT_LAUNCH(ctx, "scan3_apply", k_scan3_apply<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk, p.segt, p.segc));
+  CU_TRY(cudaGetLastError());
+  return B2M_OK;
 }
 
 // ---- pass B: emit ------------------------------------------------------------------------------
@@ -329,7 +549,7 @@ __device__ __forceinline__ uint32_t mc_vidx(const mc_params &p, size_t row, int 
   size_t s = row * p.segs + (x >> 5);
   uint4 b = __ldg(p.segbits + s);
   unsigned lane = x & 31, m = (1u << lane) - 1u;
-  uint32_t n = __ldg(p.segv + s) + __popc(b.x & m) + __popc(b.y & m) + __popc(b.z & m);
+  uint32_t n = b.w + __popc(b.x & m) + __popc(b.y & m) + __popc(b.z & m);
   if (axis >= 1) n += (b.x >> lane) & 1u;
   if (axis == 2) n += (b.y >> lane) & 1u;
   return n;
@@ -378,7 +598,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
   const float flo0 = (float)p.lo0, flo1 = (float)p.lo1, flo2 = (float)p.lo2;
   // ---- own edge vertices ----
   if (ex | ey | ez) {
-    uint32_t vid = __ldg(p.segv + sidx) + (uint32_t)pv;
+    uint32_t vid = __ldg(&p.segbits[sidx].w) + (uint32_t)pv;
     if (!p.classic) {
       const float fx = (float)x, fy = (float)y, fz = (float)z;
       if (ex) {
@@ -559,10 +779,9 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
   const size_t nseg = nrows * p.segs;
   const size_t nvox = nrows * p.sx;
   B2M_TRY(b2m_reserve(ctx, BUF_SEG, nseg * sizeof(uint4)));
-  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, nseg * 3 * sizeof(uint32_t)));
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, nseg * 2 * sizeof(uint32_t)));
   p.segbits = b2m_ptr<uint4>(ctx, BUF_SEG);
-  p.segv = b2m_ptr<uint32_t>(ctx, BUF_SEG2);
-  p.segt = p.segv + nseg;
+  p.segt = b2m_ptr<uint32_t>(ctx, BUF_SEG2);
   p.segc = p.segt + nseg;
   size_t cap = nvox / 8 + 65536;
   if (cap > nvox) cap = nvox;
@@ -572,13 +791,11 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
     p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    dim3 grid(p.segs, b2m_cdiv(p.sy, MCA_ROWS), p.sz);
-    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p));
+    dim3 grid(p.segs, b2m_cdiv(p.sy, MCC_ROWS * MCC_WARPS), b2m_cdiv(p.sz, MCC_ZC));
+    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
     CU_TRY(cudaGetLastError());
     if (attempt == 0) {
-      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
-      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segt, p.segt, nseg, &d_sc->tot_t));
-      B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segc, p.segc, nseg, &d_sc->tot_c));
+      B2M_TRY(mc_scan3(ctx, p, nseg, d_sc));
     }
     B2M_TRY(b2m_fetch_scalars(ctx));
     n_active = ctx->h_scalars->n_active;
@@ -591,10 +808,8 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
     p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCA_ROWS, 0, ctx->stream>>>(p));
-    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segv, p.segv, nseg, &d_sc->tot_v));
-    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segt, p.segt, nseg, &d_sc->tot_t));
-    B2M_TRY(b2m_exclusive_scan_u32(ctx, p.segc, p.segc, nseg, &d_sc->tot_c));
+    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
+    B2M_TRY(mc_scan3(ctx, p, nseg, d_sc));
     B2M_TRY(b2m_fetch_scalars(ctx));
     n_active = ctx->h_scalars->n_active;
     break;

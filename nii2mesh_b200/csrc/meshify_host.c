@@ -103,7 +103,9 @@ double clockMsec(void) {
 
 long timediff(double startTimeMsec, double endTimeMsec) { return (long)round(endTimeMsec - startTimeMsec); }
 
-/* ---- minimal writers: enough to keep the CLI usable (mesh writers are outside the hot path) ---- */
+/* ---- minimal writers: enough to keep the CLI usable (mesh writers are outside the hot path).
+ * Build with -DB2M_NO_SAVE_MESH to leave save_mesh to the reference's own writers. ---- */
+#ifndef B2M_NO_SAVE_MESH
 static int has_ext(const char *fnm, const char *ext) {
   size_t n = strlen(fnm), m = strlen(ext);
   return n >= m && strcmp(fnm + n - m, ext) == 0;
@@ -166,3 +168,4 @@ int save_mesh(const char *fnm, vec3i *tris, vec3d *pts, int ntri, int npt, bool 
   fprintf(stderr, "save_mesh: this build writes .mz3, .ply and .obj only (got %s)\n", fnm);
   return EXIT_FAILURE;
 }
+#endif /* B2M_NO_SAVE_MESH */

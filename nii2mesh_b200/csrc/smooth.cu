@@ -6,92 +6,201 @@
 //   right in FP64 (no FMA: __dmul_rn/__dadd_rn), ONE rounding to f32 per pass; voxels whose index
 //   on the pass axis is < 2 or >= n-2 keep the previous pass's value; nothing happens when a
 //   dim < 5 (the reference ignores quick_smooth's EXIT_FAILURE, meshify.c:301).
-//
-// Layout: a CTA owns a 64x16 xy tile and marches along z.  Per plane it stages the raw tile
-// (+2 halo) in shared memory as doubles, runs the x pass and the y pass out of shared memory and
-// keeps a 5-deep ring of y-smoothed planes per thread in registers for the z pass, so every voxel
-// is read from HBM once (halo re-reads hit L2) and written once: 8 B/voxel algorithmic.
 #include "common.cuh"
 
-#define SM_TX 64
-#define SM_TY 16
-#define SM_THREADS 256
-#define SM_ZC 64
-#define SM_COLS (SM_TX * SM_TY / SM_THREADS) /* 4 outputs per thread per plane */
+// ---- tile geometry ----
+#define SX_TX 128                 /* tile width: 32 lanes x 4 voxels */
+#define SX_TY 28                  /* output rows per tile */
+#define SX_ROWS (SX_TY + 4)       /* rows staged per plane (2 + 2 halo) */
+#define SX_WARPS 16
+#define SX_THREADS (32 * SX_WARPS)
+#define SX_YZ_WARPS (SX_TY / 2)   /* warps that own output columns: 2 rows x 4 voxels per lane */
+#define SX_SMEM (2 * SX_ROWS * SX_TX * 8)
+
+#define K0 0.45
+#define K1 0.225
+#define K2 0.05
 
 __device__ __forceinline__ double fir5(double a, double b, double c, double d, double e) {
-  const double k0 = 0.45, k1 = 0.225, k2 = 0.05;
-  double s = __dmul_rn(a, k2);
-  s = __dadd_rn(s, __dmul_rn(b, k1));
-  s = __dadd_rn(s, __dmul_rn(c, k0));
-  s = __dadd_rn(s, __dmul_rn(d, k1));
-  s = __dadd_rn(s, __dmul_rn(e, k2));
+  double s = __dmul_rn(a, K2);
+  s = __dadd_rn(s, __dmul_rn(b, K1));
+  s = __dadd_rn(s, __dmul_rn(c, K0));
+  s = __dadd_rn(s, __dmul_rn(d, K1));
+  s = __dadd_rn(s, __dmul_rn(e, K2));
   return s;
 }
 
-__global__ void __launch_bounds__(SM_THREADS) k_smooth3(const float *__restrict__ in, float *__restrict__ out, int nx,
-                                                        int ny, int nz, unsigned int *__restrict__ mm_enc) {
-  __shared__ double raw[SM_TY + 4][SM_TX + 4];
-  __shared__ double xs[SM_TY + 4][SM_TX];
-  __shared__ float red[2][SM_THREADS / 32];
-  const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * SM_TX, y0 = blockIdx.y * SM_TY;
-  const int z0 = blockIdx.z * SM_ZC;
-  const int z1 = min(z0 + SM_ZC, nz);
-  const int zs = max(z0 - 2, 0);
+// (double)(float)d without the two 1/16-rate F2F conversions (measured on B200: DADD/DMUL issue at
+// 64/clk/SM, F2F.F64<->F32 at 16/clk/SM): adding 1.5*2^(e+29) makes the FP64 adder round d to the
+// f32 grid of its binade (round-to-nearest-even, one rounding); subtracting it back is exact.
+// Exact for every d whose float image is a normal number below 2^127; zeros pass through;
+// anything else (f32 denormal / overflow range, inf, nan) takes the real conversions.
+__device__ __forceinline__ double round_to_f32(double d) {
+  const int hi = __double2hiint(d);
+  const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
+  if (e - 897u < 253u) {  // 2^-126 <= |d| < 2^127
+    const double m = __hiloint2double((int)(((e + 29u) << 20) | 0x00080000u), 0);
+    return __dsub_rn(__dadd_rn(d, m), m);
+  }
+  if (d == 0.0) return d;
+  return (double)(float)d;
+}
+
+template <bool VEC>
+__device__ __forceinline__ void load_row4(const float *__restrict__ row, int gx, int nx, float f[4]) {
+  if (VEC) {
+    if (gx < nx) {
+      float4 t = __ldg(reinterpret_cast<const float4 *>(row + gx));
+      f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+    } else {
+      f[0] = f[1] = f[2] = f[3] = 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; k++) f[k] = (gx + k < nx) ? __ldg(row + gx + k) : 0.f;
+  }
+}
+
+// One CTA: a 128 x 28 xy tile, marching along z over [z0, z1) (+2 halo planes each side).
+//   x pass: warp w filters staged rows 2w, 2w+1 in registers (float4 per lane, neighbours by
+//           shuffle), rounds to the f32 grid and parks the row in shared memory as doubles;
+//   y pass: warps 0..13 own 2 rows x 4 voxels per lane and read 6 rows from shared memory;
+//   z pass: streaming accumulators - the reference's left-to-right sum
+//           ((((a*k2)+b*k1)+c*k0)+d*k1)+e*k2 is advanced by one term per arriving plane, so a
+//           column keeps 4 partial sums instead of a 5-plane ring.
+// Every voxel is read once (plus tile halos that hit L2) and written once: 8 B/voxel.
+template <bool VEC>
+__global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restrict__ in, float *__restrict__ out, int nx,
+                                                           int ny, int nz, int zc, unsigned int *__restrict__ mm_enc) {
+  extern __shared__ double2 xs2[];  // [2][SX_ROWS][2][32]
+  __shared__ float red[2][SX_WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
+  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
+  const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
+  const int gx = x0 + lane * 4;
   const size_t nxy = (size_t)nx * ny;
-  const int lx = tid % SM_TX, lyb = tid / SM_TX;  // lyb in 0..3
-  double ring[SM_COLS][5];
+  const bool yz = warp < SX_YZ_WARPS;
+  const int ly = warp * 2;
+  double S[2][4][4];
 #pragma unroll
-  for (int c = 0; c < SM_COLS; c++)
+  for (int r = 0; r < 2; r++)
 #pragma unroll
-    for (int k = 0; k < 5; k++) ring[c][k] = 0.0;
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) S[r][k][q] = 0.0;
   float vmin = INFINITY, vmax = -INFINITY;
 
-  for (int zp = zs; zp < z1 + 2; zp++) {
-    if (zp < nz) {
-      const float *plane = in + (size_t)zp * nxy;
-      for (int i = tid; i < (SM_TY + 4) * (SM_TX + 4); i += SM_THREADS) {
-        int ly = i / (SM_TX + 4), lxx = i % (SM_TX + 4);
-        int gx = x0 - 2 + lxx, gy = y0 - 2 + ly;
-        double v = 0.0;
-        if (gx >= 0 && gx < nx && gy >= 0 && gy < ny) v = (double)__ldg(plane + (size_t)gy * nx + gx);
-        raw[ly][lxx] = v;
-      }
-      __syncthreads();
-      for (int i = tid; i < (SM_TY + 4) * SM_TX; i += SM_THREADS) {
-        int ly = i / SM_TX, lxx = i % SM_TX;
-        int gx = x0 + lxx;
-        double v;
-        if (gx < 2 || gx >= nx - 2) v = raw[ly][lxx + 2];
-        else v = (double)(float)fir5(raw[ly][lxx], raw[ly][lxx + 1], raw[ly][lxx + 2], raw[ly][lxx + 3], raw[ly][lxx + 4]);
-        xs[ly][lxx] = v;
-      }
-      __syncthreads();
-    }
+  // raw rows of the plane being staged: rows 2*warp, 2*warp+1 (gy = y0 - 2 + r), prefetched one plane ahead
+  float raw[2][4], hal[2][2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
+  auto fetch = [&](int zp) {
 #pragma unroll
-    for (int c = 0; c < SM_COLS; c++) {
-      int ly = lyb + (SM_THREADS / SM_TX) * c;
-      int gy = y0 + ly;
-      double v = 0.0;
-      if (zp < nz) {
-        if (gy < 2 || gy >= ny - 2) v = xs[ly + 2][lx];
-        else v = (double)(float)fir5(xs[ly][lx], xs[ly + 1][lx], xs[ly + 2][lx], xs[ly + 3][lx], xs[ly + 4][lx]);
-      }
-      ring[c][0] = ring[c][1]; ring[c][1] = ring[c][2]; ring[c][2] = ring[c][3]; ring[c][3] = ring[c][4];
-      ring[c][4] = v;
-      int zo = zp - 2;
-      int gx = x0 + lx;
-      if (zo >= z0 && zo < z1 && gx < nx && gy < ny) {
-        float o;
-        if (zo < 2 || zo >= nz - 2) o = (float)ring[c][2];
-        else o = (float)fir5(ring[c][0], ring[c][1], ring[c][2], ring[c][3], ring[c][4]);
-        out[(size_t)zo * nxy + (size_t)gy * nx + gx] = o;
-        vmin = fminf(vmin, o);
-        vmax = fmaxf(vmax, o);
+    for (int rr = 0; rr < 2; rr++) {
+      const int gy = y0 - 2 + warp * 2 + rr;
+      raw[rr][0] = raw[rr][1] = raw[rr][2] = raw[rr][3] = 0.f;
+      hal[rr][0] = hal[rr][1] = 0.f;
+      if (gy >= 0 && gy < ny && zp < ze) {
+        const float *row = in + (size_t)zp * nxy + (size_t)gy * nx;
+        load_row4<VEC>(row, gx, nx, raw[rr]);
+        if (lane == 0 && x0 > 0) { hal[rr][0] = __ldg(row + x0 - 2); hal[rr][1] = __ldg(row + x0 - 1); }
+        if (lane == 31) {
+          if (gx + 4 < nx) hal[rr][0] = __ldg(row + gx + 4);
+          if (gx + 5 < nx) hal[rr][1] = __ldg(row + gx + 5);
+        }
       }
     }
-    // raw/xs are rewritten next iteration only after the two barriers above
+  };
+  fetch(zs);
+  for (int zp = zs; zp < ze; zp++) {
+    double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
+    // ---- x pass ----
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+      const int r = warp * 2 + rr;
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[2 + k] = (double)raw[rr][k];
+      v[0] = __shfl_up_sync(0xffffffffu, v[4], 1);
+      v[1] = __shfl_up_sync(0xffffffffu, v[5], 1);
+      v[6] = __shfl_down_sync(0xffffffffu, v[2], 1);
+      v[7] = __shfl_down_sync(0xffffffffu, v[3], 1);
+      if (lane == 0) { v[0] = (double)hal[rr][0]; v[1] = (double)hal[rr][1]; }
+      if (lane == 31) { v[6] = (double)hal[rr][0]; v[7] = (double)hal[rr][1]; }
+      double o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int x = gx + k;
+        const double f = round_to_f32(fir5(v[k], v[k + 1], v[k + 2], v[k + 3], v[k + 4]));
+        o[k] = (x < 2 || x >= nx - 2) ? v[k + 2] : f;
+      }
+      buf[r * 64 + lane] = make_double2(o[0], o[1]);
+      buf[r * 64 + 32 + lane] = make_double2(o[2], o[3]);
+    }
+    __syncthreads();
+    fetch(zp + 1);  // next plane's loads fly while this plane's y/z passes run
+    // ---- y pass + z pass ----
+    if (yz) {
+      const bool zborder = zp < 2 || zp >= nz - 2;
+      const int zo = zp - 2;
+      const bool emit_border = zborder && zp >= z0 && zp < z1;
+      const bool emit_inner = zo >= z0 && zo < z1 && zo >= 2 && zo < nz - 2;
+      float ob[2][4], oi[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {  // two voxels of the strip at a time keeps the live set under 128 registers
+        double c[6][2];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+          const double2 pj = buf[(ly + j) * 64 + h * 32 + lane];
+          c[j][0] = pj.x; c[j][1] = pj.y;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; rr++) {
+          const int gy = y0 + ly + rr;
+          const bool yborder = gy < 2 || gy >= ny - 2;
+#pragma unroll
+          for (int kk = 0; kk < 2; kk++) {
+            const int k = 2 * h + kk;
+            const double f = round_to_f32(fir5(c[rr][kk], c[rr + 1][kk], c[rr + 2][kk], c[rr + 3][kk], c[rr + 4][kk]));
+            const double ys = yborder ? c[rr + 2][kk] : f;
+            const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
+            const double fin = __dadd_rn(S[rr][k][3], q2);
+            S[rr][k][3] = __dadd_rn(S[rr][k][2], q1);
+            S[rr][k][2] = __dadd_rn(S[rr][k][1], q0);
+            S[rr][k][1] = __dadd_rn(S[rr][k][0], q1);
+            S[rr][k][0] = q2;
+            ob[rr][k] = (float)ys;
+            oi[rr][k] = (float)fin;
+          }
+        }
+      }
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int gy = y0 + ly + rr;
+        if (gy < ny && gx < nx) {
+          if (emit_border) {
+            float *dst = out + (size_t)zp * nxy + (size_t)gy * nx + gx;
+            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(ob[rr][0], ob[rr][1], ob[rr][2], ob[rr][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (gx + k < nx) {
+                if (!VEC) dst[k] = ob[rr][k];
+                vmin = fminf(vmin, ob[rr][k]); vmax = fmaxf(vmax, ob[rr][k]);
+              }
+          }
+          if (emit_inner) {
+            float *dst = out + (size_t)zo * nxy + (size_t)gy * nx + gx;
+            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[rr][0], oi[rr][1], oi[rr][2], oi[rr][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (gx + k < nx) {
+                if (!VEC) dst[k] = oi[rr][k];
+                vmin = fminf(vmin, oi[rr][k]); vmax = fmaxf(vmax, oi[rr][k]);
+              }
+          }
+        }
+      }
+    }
+    // the other half of the double buffer is rewritten only after the next barrier
   }
   // block reduction of the range
 #pragma unroll
@@ -99,11 +208,11 @@ __global__ void __launch_bounds__(SM_THREADS) k_smooth3(const float *__restrict_
     vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
     vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
   }
-  if ((tid & 31) == 0) { red[0][tid >> 5] = vmin; red[1][tid >> 5] = vmax; }
+  if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
   __syncthreads();
   if (tid < 32) {
-    vmin = tid < SM_THREADS / 32 ? red[0][tid] : INFINITY;
-    vmax = tid < SM_THREADS / 32 ? red[1][tid] : -INFINITY;
+    vmin = tid < SX_WARPS ? red[0][tid] : INFINITY;
+    vmax = tid < SX_WARPS ? red[1][tid] : -INFINITY;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
       vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
@@ -156,29 +265,63 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
   }
 }
 
-// mask = img >= iso (src/meshify.c:325-330) as bit rows: one warp per 32-voxel word, ballot.
-// fg word bit b <=> voxel x = 32*xw + b is foreground; bg = complement restricted to x < nx.
+// mask = img >= iso (src/meshify.c:325-330) as bit rows.  fg word bit b <=> voxel x = 32*xw + b is
+// foreground; bg = complement restricted to x < nx.  A warp turns THR_WPW consecutive bit words
+// (32 voxels each) per trip: THR_WPW independent 128-byte loads in flight, one ballot each, then
+// lanes 0..THR_WPW-1 store the words (the one-word-per-warp first version ran at 1.2 TB/s: too few
+// bytes in flight).
+#define THR_WPW 8
 __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
                                                    float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg) {
-  long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned lane = threadIdx.x & 31;
-  if (word >= nwords) return;
-  long long row = word / w;
-  int xw = (int)(word - row * w);
-  int x = xw * 32 + (int)lane;
-  bool valid = x < nx;
-  bool b = valid && (__ldg(in + row * nx + x) >= iso);
-  unsigned m = __ballot_sync(0xffffffffu, b);
-  unsigned vm = __ballot_sync(0xffffffffu, valid);
-  if (lane == 0) {
-    fg[word] = m;
-    if (bg) bg[word] = ~m & vm;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long w0 = warp * THR_WPW; w0 < nwords; w0 += nwarps * THR_WPW) {
+    float v[THR_WPW];
+    bool ok[THR_WPW];
+#pragma unroll
+    for (int j = 0; j < THR_WPW; j++) {
+      const long long word = w0 + j;
+      const long long row = word / w;
+      const int x = (int)(word - row * w) * 32 + (int)lane;
+      ok[j] = word < nwords && x < nx;
+      v[j] = ok[j] ? __ldg(in + row * nx + x) : 0.f;
+    }
+    uint32_t mine_fg = 0, mine_bg = 0;
+#pragma unroll
+    for (int j = 0; j < THR_WPW; j++) {
+      const unsigned m = __ballot_sync(0xffffffffu, ok[j] && v[j] >= iso);
+      const unsigned vm = __ballot_sync(0xffffffffu, ok[j]);
+      if (lane == (unsigned)j) { mine_fg = m; mine_bg = ~m & vm; }
+    }
+    if (lane < THR_WPW && w0 + lane < nwords) {
+      fg[w0 + lane] = mine_fg;
+      if (bg) bg[w0 + lane] = mine_bg;
+    }
   }
 }
 
 int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
-  dim3 grid(b2m_cdiv(g.nx, SM_TX), b2m_cdiv(g.ny, SM_TY), b2m_cdiv(g.nz, SM_ZC));
-  KT_LAUNCH(ctx, "smooth3", k_smooth3<<<grid, SM_THREADS, 0, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, &d_sc->vmin_enc));
+  const unsigned tx = b2m_cdiv(g.nx, SX_TX), ty = b2m_cdiv(g.ny, SX_TY);
+  // z chunk: enough CTAs to fill the machine a few times over, but >= 16 planes so that the 4 halo
+  // planes of a chunk stay a small overhead
+  int want = (int)((4 * (size_t)ctx->sm_count + (size_t)tx * ty - 1) / ((size_t)tx * ty));
+  if (want < 1) want = 1;
+  int zc = (g.nz + want - 1) / want;
+  if (zc < 16) zc = 16;
+  if (zc > 128) zc = 128;
+  dim3 grid(tx, ty, b2m_cdiv(g.nz, zc));
+  const bool vec = (g.nx % 4 == 0) && (((uintptr_t)d_in | (uintptr_t)d_out) % 16 == 0);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_smooth3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+    attr_done = true;
+  }
+  if (vec)
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, zc, &d_sc->vmin_enc));
+  else
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, zc, &d_sc->vmin_enc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -191,8 +334,11 @@ int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, b2m_scala
 }
 
 int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg) {
-  long long threads = g.nwords * 32;
-  KT_LAUNCH(ctx, "threshold", k_threshold<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg));
+  long long warps = (g.nwords + THR_WPW - 1) / THR_WPW;
+  long long blocks = (warps + 7) / 8;
+  const long long cap = (long long)ctx->sm_count * 64;  // grid-stride beyond a few waves
+  if (blocks > cap) blocks = cap;
+  KT_LAUNCH(ctx, "threshold", k_threshold<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
