@@ -93,10 +93,21 @@ __device__ __forceinline__ uint32_t lfind(volatile uint32_t *par, uint32_t a) {
   }
   return a;
 }
+// find with path halving; only valid while the count bits are still zero (phase A)
+__device__ __forceinline__ uint32_t lfind_compress(uint32_t *par, uint32_t a) {
+  uint32_t p = ((volatile uint32_t *)par)[a] >> 16;
+  while (p != a) {
+    const uint32_t gp = ((volatile uint32_t *)par)[p] >> 16;
+    if (gp != p) atomicMin(&par[a], gp << 16);
+    a = p;
+    p = gp;
+  }
+  return a;
+}
 __device__ __forceinline__ void lunion(uint32_t *par, uint32_t a, uint32_t b) {
   for (;;) {
-    a = lfind(par, a);
-    b = lfind(par, b);
+    a = lfind_compress(par, a);
+    b = lfind_compress(par, b);
     if (a == b) return;
     if (a < b) { uint32_t t = a; a = b; b = t; }
     uint32_t old = atomicMin(&par[a], b << 16) >> 16;  // counts are still zero in this phase
@@ -185,19 +196,34 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     });
   }
   __syncthreads();
-  // phase B: local roots collect the voxel count and the face flag of their local component
+  // phase B: local roots collect the voxel count and the face flag of their local component.
+  // Lanes that reach the same root combine first (one shared-memory atomic per warp and root: 512
+  // same-address atomics per tile were the bottleneck of the first version).
   const bool rowface = (y == 0) || (y == g.ny - 1) || (z == 0) || (z == g.nz - 1);
   uint32_t myroot[16];  // local root per run of this word, in run order (<= 16 runs)
   int nrun = 0;
-  for (uint32_t rest = wv; rest; nrun++) {
-    const int s = __ffs(rest) - 1;
-    const int e = run_end(wv, s);
-    rest &= ~bits_range(s, e);
-    const uint32_t r = lfind(par, (uint32_t)t * 16u + (uint32_t)(s >> 1));
-    myroot[nrun] = r;
-    const int x0 = xw * 32 + s, x1 = xw * 32 + e;
-    atomicAdd(&par[r], (uint32_t)(e - s + 1));
-    if (rowface || x0 == 0 || x1 == g.nx - 1) atomicOr(&par[r], 0x8000u);
+  {
+    uint32_t rest = wv;
+    while (__any_sync(0xffffffffu, rest != 0)) {
+      uint32_t r = 0xffffffffu, cnt = 0, flag = 0;
+      if (rest) {
+        const int s = __ffs(rest) - 1;
+        const int e = run_end(wv, s);
+        rest &= ~bits_range(s, e);
+        r = lfind(par, (uint32_t)t * 16u + (uint32_t)(s >> 1));
+        myroot[nrun++] = r;
+        const int x0 = xw * 32 + s, x1 = xw * 32 + e;
+        cnt = (uint32_t)(e - s + 1);
+        flag = (rowface || x0 == 0 || x1 == g.nx - 1) ? 0x8000u : 0u;
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, r);
+      const uint32_t tot = __reduce_add_sync(peers, cnt);
+      const uint32_t fl = __reduce_or_sync(peers, flag);
+      if (r != 0xffffffffu && (unsigned)(__ffs(peers) - 1) == (unsigned)(t & 31)) {
+        atomicAdd(&par[r], tot);
+        if (fl) atomicOr(&par[r], fl);
+      }
+    }
   }
   __syncthreads();
   // phase C: publish the global nodes

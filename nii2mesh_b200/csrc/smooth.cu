@@ -282,10 +282,15 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
 #pragma unroll
     for (int j = 0; j < THR_WPW; j++) {
       const long long word = w0 + j;
-      const long long row = word / w;
-      const int x = (int)(word - row * w) * 32 + (int)lane;
-      ok[j] = word < nwords && x < nx;
-      v[j] = ok[j] ? __ldg(in + row * nx + x) : 0.f;
+      if (nx == w * 32) {  // rows are whole words: voxel index = word * 32 + lane, no division
+        ok[j] = word < nwords;
+        v[j] = ok[j] ? __ldg(in + word * 32 + lane) : 0.f;
+      } else {
+        const long long row = word / w;
+        const int x = (int)(word - row * w) * 32 + (int)lane;
+        ok[j] = word < nwords && x < nx;
+        v[j] = ok[j] ? __ldg(in + row * nx + x) : 0.f;
+      }
     }
     uint32_t mine_fg = 0, mine_bg = 0;
 #pragma unroll
