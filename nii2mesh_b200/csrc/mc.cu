@@ -37,6 +37,7 @@ struct mc_params {
   int classic;      // backend == CLASSIC
   int original_mc;
   const signed char *tab;
+  const uint32_t *lutinfo;  // 256 entries: Lewiner MC33, or the classic table when classic / originalMC
   uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks, .w = packed counts -> vertex base (scan3)
   uint32_t *segt, *segc;  // per segment exclusive triangle / centroid-vertex bases
   uint4 *active;
@@ -119,7 +120,7 @@ __device__ bool t_interior(const float *c, int kase, int refedge, int s) {  // :
 #define PICK(off_, n_, c_) do { off = (off_); ntri = (n_); hasc = (c_); return; } while (0)
 
 // src/MarchingCubes.c:458-795.  c = clamped corner values; lut bit p = c[p] > 0.
-__device__ void mc33_select(const signed char *__restrict__ tab, const float *c, int lut, int original_mc, int &off,
+__device__ __noinline__ void mc33_select(const signed char *__restrict__ tab, const float *c, int lut, int original_mc, int &off,
                             int &ntri, int &hasc) {
   if (original_mc) {
     int o = MCT_casesClassic + 16 * lut, n = 0;
@@ -257,30 +258,39 @@ __device__ __noinline__ unsigned mc_plane_masks_slow(const mc_params &p, int seg
 // inside bit of one in-volume voxel: S value, optional fill / keep bit-row words (offset `wo` from the
 // array base), face darkening.  FILL/KEEP are compile-time so that no null pointer is ever formed.
 template <bool FILL, bool KEEP>
-__device__ __forceinline__ bool mc_inside_fast(const mc_params &p, size_t so, size_t wo, unsigned bit, bool face) {
-  float v = __ldg(p.c.S + so);
-  if (FILL) { if ((__ldg(p.c.fill + wo) >> bit) & 1u) v = fmaxf(v, p.c.iso); }
-  if (KEEP) { if (!((__ldg(p.c.keep + wo) >> bit) & 1u)) v = p.c.mn; }
+__device__ __forceinline__ bool mc_inside_fast(const mc_params &p, const float *__restrict__ sp,
+                                               const uint32_t *__restrict__ fp, const uint32_t *__restrict__ kp,
+                                               unsigned bit, bool face) {
+  float v = __ldg(sp);
+  if (FILL) { if ((__ldg(fp) >> bit) & 1u) v = fmaxf(v, p.c.iso); }
+  if (KEEP) { if (!((__ldg(kp) >> bit) & 1u)) v = p.c.mn; }
   if (face) v = fminf(p.c.edge_max, v);
   return p.classic ? (v < p.c.iso) : (__fsub_rn(v, p.c.iso) > -FLT_EPSILON);
 }
 
 // interior: all 33 columns, 9 rows and the plane lie inside the sub-volume AND the volume (warp-uniform
-// test), so there is no wrap/pad and the addresses advance by constant strides.
+// test), so there is no wrap/pad and the addresses advance by constant strides.  FILL/KEEP are
+// compile-time so that no pointer is formed from an absent (null) bit-row array.
 template <bool FILL, bool KEEP>
 __device__ __forceinline__ unsigned mc_plane_masks_fast(const mc_params &p, int seg, int ybase, int z, unsigned lane,
                                                         unsigned &mx) {
   const int gz = p.lo2 + z;
   const int gx = p.lo0 + seg * 32 + (int)lane, gy0 = p.lo1 + ybase;
   const size_t row0 = (size_t)gz * p.c.ny + gy0;
-  const size_t so = row0 * p.c.nx + gx, wo = row0 * p.c.w + (gx >> 5);
+  const float *sp = p.c.S + row0 * p.c.nx + gx;
+  const uint32_t *fp = FILL ? p.c.fill + row0 * p.c.w + (gx >> 5) : p.c.fill;
+  const uint32_t *kp = KEEP ? p.c.keep + row0 * p.c.w + (gx >> 5) : p.c.keep;
   const bool zxface = gz == 0 || gz == p.c.nz - 1 || gx == 0 || gx == p.c.nx - 1;
+  const int ylast = p.c.ny - 1 - gy0;  // row r is the y = ny-1 face when r == ylast
   unsigned m = 0;
 #pragma unroll
   for (int r = 0; r <= MCC_ROWS; r++) {
-    const bool face = zxface || gy0 + r == 0 || gy0 + r == p.c.ny - 1;
-    const bool in = mc_inside_fast<FILL, KEEP>(p, so + (size_t)(r * p.c.nx), wo + (size_t)(r * p.c.w), (unsigned)gx & 31u, face);
+    const bool face = zxface || (r == 0 && gy0 == 0) || r == ylast;
+    const bool in = mc_inside_fast<FILL, KEEP>(p, sp, fp, kp, (unsigned)gx & 31u, face);
     m |= (in ? 1u : 0u) << r;
+    sp += p.c.nx;
+    if (FILL) fp += p.c.w;
+    if (KEEP) kp += p.c.w;
   }
   // halo column x = seg*32 + 32: lane r evaluates row r
   bool hin = false;
@@ -289,7 +299,8 @@ __device__ __forceinline__ unsigned mc_plane_masks_fast(const mc_params &p, int 
     const size_t hrow = row0 + lane;
     const bool face = gz == 0 || gz == p.c.nz - 1 || hx == 0 || hx == p.c.nx - 1 || gy0 + (int)lane == 0 ||
                       gy0 + (int)lane == p.c.ny - 1;
-    hin = mc_inside_fast<FILL, KEEP>(p, hrow * p.c.nx + hx, hrow * p.c.w + (hx >> 5), (unsigned)hx & 31u, face);
+    hin = mc_inside_fast<FILL, KEEP>(p, p.c.S + hrow * p.c.nx + hx, FILL ? p.c.fill + hrow * p.c.w + (hx >> 5) : p.c.fill,
+                                     KEEP ? p.c.keep + hrow * p.c.w + (hx >> 5) : p.c.keep, (unsigned)hx & 31u, face);
   }
   const unsigned hm = __ballot_sync(0xffffffffu, hin);
   mx = __shfl_down_sync(0xffffffffu, m, 1);
@@ -341,33 +352,28 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
     const unsigned andm = a & (a >> 1) & b & (b >> 1) & c & (c >> 1) & d & (d >> 1);
     const unsigned trim = (vx1 && vz1) ? ((orm & ~andm) & vy1m) : 0u;
     const unsigned rows_active = __reduce_or_sync(0xffffffffu, exm | eym | ezm | trim);
-    if (lane < MCC_ROWS && ((rowsv & ~rows_active) >> lane) & 1u)
-      p.segbits[((size_t)z * p.sy + ybase + lane) * p.segs + seg] = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *segrow = p.segbits + ((size_t)z * p.sy + ybase) * p.segs + seg;  // + r * p.segs per row
+    if (lane < MCC_ROWS && ((rowsv & ~rows_active) >> lane) & 1u) segrow[(size_t)lane * p.segs] = make_uint4(0u, 0u, 0u, 0u);
     for (unsigned ra = rows_active; ra; ra &= ra - 1) {
       const int r = __ffs(ra) - 1;
       const size_t row = (size_t)z * p.sy + ybase + r;
       const bool ex = (exm >> r) & 1u, ey = (eym >> r) & 1u, ez = (ezm >> r) & 1u, tri = (trim >> r) & 1u;
       int ntri = 0, hasc = 0, off = 0, lut = 0;
       if (tri) {
-        lut = (int)(((a >> r) & 1u) | (((b >> r) & 1u) << 1) | (((b >> (r + 1)) & 1u) << 2) | (((a >> (r + 1)) & 1u) << 3) |
-                    (((c >> r) & 1u) << 4) | (((d >> r) & 1u) << 5) | (((d >> (r + 1)) & 1u) << 6) | (((c >> (r + 1)) & 1u) << 7));
-        if (p.classic || p.original_mc) {
-          int o = MCT_casesClassic + 16 * lut, n = 0;
-          while (n < 5 && p.tab[o + 3 * n] != -1) n++;
-          off = o; ntri = n;
-        } else {
-          const int kase = p.tab[MCT_cases + 2 * lut];
+        // corner bits: p0=a_r p1=b_r p2=b_{r+1} p3=a_{r+1} p4=c_r p5=d_r p6=d_{r+1} p7=c_{r+1}
+        const unsigned pa = (a >> r) & 3u, pb = (b >> r) & 3u, pc2 = (c >> r) & 3u, pd = (d >> r) & 3u;
+        lut = (int)(((pa & 1u) | ((pa & 2u) << 2) | (pb << 1)) | (((pc2 & 1u) | ((pc2 & 2u) << 2) | (pd << 1)) << 4));
+        const uint32_t info = __ldg(p.lutinfo + lut);
+        if (info >> 31) {  // ambiguous MC33 case: the face / interior tests need the corner values
+          const int y = ybase + r;
           float cv[8];
-          if (kase == 3 || kase == 4 || kase == 6 || kase == 7 || kase == 10 || kase == 12 || kase == 13) {
-            const int y = ybase + r;  // ambiguous: the face / interior tests need the corner values
-            cv[0] = mc_data(p, x, y, z); cv[1] = mc_data(p, x + 1, y, z); cv[2] = mc_data(p, x + 1, y + 1, z);
-            cv[3] = mc_data(p, x, y + 1, z); cv[4] = mc_data(p, x, y, z + 1); cv[5] = mc_data(p, x + 1, y, z + 1);
-            cv[6] = mc_data(p, x + 1, y + 1, z + 1); cv[7] = mc_data(p, x, y + 1, z + 1);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) cv[q] = 0.f;
-          }
+          cv[0] = mc_data(p, x, y, z); cv[1] = mc_data(p, x + 1, y, z); cv[2] = mc_data(p, x + 1, y + 1, z);
+          cv[3] = mc_data(p, x, y + 1, z); cv[4] = mc_data(p, x, y, z + 1); cv[5] = mc_data(p, x + 1, y, z + 1);
+          cv[6] = mc_data(p, x + 1, y + 1, z + 1); cv[7] = mc_data(p, x, y + 1, z + 1);
           mc33_select(p.tab, cv, lut, 0, off, ntri, hasc);
+        } else {
+          off = (int)(info & 0xffffu);
+          ntri = (int)(info >> 16);
         }
       }
       const unsigned xb = __ballot_sync(0xffffffffu, ex), yb = __ballot_sync(0xffffffffu, ey), zb = __ballot_sync(0xffffffffu, ez);
@@ -381,7 +387,7 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
       }
       const int tot = __shfl_sync(0xffffffffu, incl, 31);
       const int excl = incl - pk;
-      if (lane == 0) p.segbits[row * p.segs + seg] = make_uint4(xb, yb, zb, (uint32_t)tot);
+      if (lane == 0) segrow[(size_t)r * p.segs] = make_uint4(xb, yb, zb, (uint32_t)tot);
       if (p.classic && ntri > 0) {
         unsigned long long key = ((unsigned long long)row << 16) | (unsigned long long)x;
         first = key < first ? key : first;
@@ -729,11 +735,39 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
   }
 }
 
+// Per-cube-index summary tables derived from the case tables, uploaded after the blob:
+//   info = table offset | ntri << 16 | (needs the MC33 face/interior tests) << 31
+// [0..255] Lewiner MC33 (src/MarchingCubes.c:479-794, unambiguous cases resolved here), [256..511]
+// the classic table (oldcubes.c / Lewiner originalMC, src/MarchingCubes.c:471-477).
+#define MCT_INFO_OFF ((MCT_TOTAL + 15) & ~15)
 static int upload_tables(b2m_ctx *ctx) {
   if (ctx->tables_ready) return B2M_OK;
   extern const signed char *b2m_mc_table_blob(void);
-  B2M_TRY(b2m_reserve(ctx, BUF_TABLES, MCT_TOTAL));
-  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_TABLES].p, b2m_mc_table_blob(), MCT_TOTAL, cudaMemcpyHostToDevice, ctx->stream));
+  const signed char *blob = b2m_mc_table_blob();
+  static uint32_t info[512];
+  for (int lut = 0; lut < 256; lut++) {
+    const int kase = blob[MCT_cases + 2 * lut], cfg = blob[MCT_cases + 2 * lut + 1];
+    uint32_t v = 0;
+    switch (kase) {
+      case 0: v = 0; break;
+      case 1: v = (uint32_t)(MCT_tiling1 + cfg * MCT_tiling1_ROW) | (1u << 16); break;
+      case 2: v = (uint32_t)(MCT_tiling2 + cfg * MCT_tiling2_ROW) | (2u << 16); break;
+      case 5: v = (uint32_t)(MCT_tiling5 + cfg * MCT_tiling5_ROW) | (3u << 16); break;
+      case 8: v = (uint32_t)(MCT_tiling8 + cfg * MCT_tiling8_ROW) | (2u << 16); break;
+      case 9: v = (uint32_t)(MCT_tiling9 + cfg * MCT_tiling9_ROW) | (4u << 16); break;
+      case 11: v = (uint32_t)(MCT_tiling11 + cfg * MCT_tiling11_ROW) | (4u << 16); break;
+      case 14: v = (uint32_t)(MCT_tiling14 + cfg * MCT_tiling14_ROW) | (4u << 16); break;
+      default: v = 0x80000000u; break;  // 3,4,6,7,10,12,13: decided per cube by mc33_select
+    }
+    info[lut] = v;
+    int o = MCT_casesClassic + 16 * lut, n = 0;
+    while (n < 5 && blob[o + 3 * n] != -1) n++;
+    info[256 + lut] = (uint32_t)o | ((uint32_t)n << 16);
+  }
+  B2M_TRY(b2m_reserve(ctx, BUF_TABLES, MCT_INFO_OFF + sizeof(info)));
+  char *d = b2m_ptr<char>(ctx, BUF_TABLES);
+  CU_TRY(cudaMemcpyAsync(d, blob, MCT_TOTAL, cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(d + MCT_INFO_OFF, info, sizeof(info), cudaMemcpyHostToDevice, ctx->stream));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->tables_ready = 1;
   return B2M_OK;
@@ -759,6 +793,8 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
   if (p.sx < 2 || p.sy < 2 || p.sz < 2) return B2M_FAIL;
   p.segs = (p.sx + 31) / 32;
   p.tab = b2m_ptr<signed char>(ctx, BUF_TABLES);
+  p.lutinfo = reinterpret_cast<const uint32_t *>(b2m_ptr<char>(ctx, BUF_TABLES) + MCT_INFO_OFF) +
+              ((p.classic || p.original_mc) ? 256 : 0);
   p.sc = d_sc;
   // pad value: (min of the composed volume) - iso (src/MarchingCubes.c:1097-1102).  It is only ever
   // read when hi == dim on some axis, and it only matters when a face voxel can be bright, i.e.

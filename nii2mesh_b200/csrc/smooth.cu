@@ -10,11 +10,10 @@
 
 // ---- tile geometry ----
 #define SX_TX 128                 /* tile width: 32 lanes x 4 voxels */
-#define SX_TY 28                  /* output rows per tile */
+#define SX_TY 20                  /* output rows per tile */
 #define SX_ROWS (SX_TY + 4)       /* rows staged per plane (2 + 2 halo) */
-#define SX_WARPS 16
+#define SX_WARPS SX_ROWS          /* one staged row per warp; warps 0..SX_TY-1 also own one output row */
 #define SX_THREADS (32 * SX_WARPS)
-#define SX_YZ_WARPS (SX_TY / 2)   /* warps that own output columns: 2 rows x 4 voxels per lane */
 #define SX_SMEM (2 * SX_ROWS * SX_TX * 8)
 
 #define K0 0.45
@@ -33,17 +32,23 @@ __device__ __forceinline__ double fir5(double a, double b, double c, double d, d
 // (double)(float)d without the two 1/16-rate F2F conversions (measured on B200: DADD/DMUL issue at
 // 64/clk/SM, F2F.F64<->F32 at 16/clk/SM): adding 1.5*2^(e+29) makes the FP64 adder round d to the
 // f32 grid of its binade (round-to-nearest-even, one rounding); subtracting it back is exact.
-// Exact for every d whose float image is a normal number below 2^127; zeros pass through;
-// anything else (f32 denormal / overflow range, inf, nan) takes the real conversions.
+// FAST is exact when d is +0 or 2^-126 <= |d| < 2^127, which holds for every intermediate of the
+// filter when all its inputs are +0 or have 2^-100 <= |v| < 2^100 (sums of products with the
+// positive taps cannot fall below 2^-53 of their largest term unless they cancel to +0 exactly).
+// Inputs are screened when they are loaded (input_unsafe); a tile that sees anything else
+// (denormals, -0, huge values, inf, nan) takes the real conversions for that plane.
+template <bool FAST>
 __device__ __forceinline__ double round_to_f32(double d) {
-  const int hi = __double2hiint(d);
-  const unsigned e = ((unsigned)hi >> 20) & 0x7ffu;
-  if (e - 897u < 253u) {  // 2^-126 <= |d| < 2^127
-    const double m = __hiloint2double((int)(((e + 29u) << 20) | 0x00080000u), 0);
+  if (FAST) {
+    const int eh = __double2hiint(d) & 0x7ff00000;
+    const double m = __hiloint2double(eh + 0x01d80000, 0);
     return __dsub_rn(__dadd_rn(d, m), m);
   }
-  if (d == 0.0) return d;
   return (double)(float)d;
+}
+__device__ __forceinline__ bool input_unsafe(float f) {
+  const unsigned u = __float_as_uint(f);
+  return u != 0u && ((u & 0x7fffffffu) - 0x0d800000u) >= 0x64000000u;  // not +0 and outside [2^-100, 2^100)
 }
 
 template <bool VEC>
@@ -61,10 +66,67 @@ __device__ __forceinline__ void load_row4(const float *__restrict__ row, int gx,
   }
 }
 
-// One CTA: a 128 x 28 xy tile, marching along z over [z0, z1) (+2 halo planes each side).
-//   x pass: warp w filters staged rows 2w, 2w+1 in registers (float4 per lane, neighbours by
+// x pass of one staged row: 4 outputs per lane from the lane's float4 and its neighbours' (shuffled as
+// floats), rounded to the f32 grid, parked in shared memory as doubles
+template <bool FAST>
+__device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2], int lane, int gx, int nx,
+                                           double2 *__restrict__ dst) {
+  float f[8];
+#pragma unroll
+  for (int k = 0; k < 4; k++) f[2 + k] = raw[k];
+  f[0] = __shfl_up_sync(0xffffffffu, raw[2], 1);
+  f[1] = __shfl_up_sync(0xffffffffu, raw[3], 1);
+  f[6] = __shfl_down_sync(0xffffffffu, raw[0], 1);
+  f[7] = __shfl_down_sync(0xffffffffu, raw[1], 1);
+  if (lane == 0) { f[0] = hal[0]; f[1] = hal[1]; }
+  if (lane == 31) { f[6] = hal[0]; f[7] = hal[1]; }
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = (double)f[k];
+  double o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = gx + k;
+    const double r = round_to_f32<FAST>(fir5(v[k], v[k + 1], v[k + 2], v[k + 3], v[k + 4]));
+    o[k] = (x < 2 || x >= nx - 2) ? v[k + 2] : r;
+  }
+  dst[lane] = make_double2(o[0], o[1]);
+  dst[32 + lane] = make_double2(o[2], o[3]);
+}
+
+// y pass (1 row x 4 voxels per lane out of 5 staged rows) + z streaming accumulators
+template <bool FAST>
+__device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly, int lane, bool yborder,
+                                        double S[4][4], float ob[4], float oi[4]) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    double c[5][2];
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      const double2 pj = buf[(ly + j) * 64 + h * 32 + lane];
+      c[j][0] = pj.x; c[j][1] = pj.y;
+    }
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int k = 2 * h + kk;
+      const double f = round_to_f32<FAST>(fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]));
+      const double ys = yborder ? c[2][kk] : f;
+      const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
+      const double fin = __dadd_rn(S[k][3], q2);
+      S[k][3] = __dadd_rn(S[k][2], q1);
+      S[k][2] = __dadd_rn(S[k][1], q0);
+      S[k][1] = __dadd_rn(S[k][0], q1);
+      S[k][0] = q2;
+      ob[k] = (float)ys;
+      oi[k] = (float)fin;
+    }
+  }
+}
+
+// One CTA (32 warps): a 128 x 28 xy tile, marching along z over [z0, z1) (+2 halo planes each side).
+//   x pass: warp w filters staged row w (gy = y0-2+w) in registers (float4 per lane, neighbours by
 //           shuffle), rounds to the f32 grid and parks the row in shared memory as doubles;
-//   y pass: warps 0..13 own 2 rows x 4 voxels per lane and read 6 rows from shared memory;
+//   y pass: warps 0..27 own output row y0+w: 4 voxels per lane from 5 staged rows in shared memory;
 //   z pass: streaming accumulators - the reference's left-to-right sum
 //           ((((a*k2)+b*k1)+c*k0)+d*k1)+e*k2 is advanced by one term per arriving plane, so a
 //           column keeps 4 partial sums instead of a 5-plane ring.
@@ -74,129 +136,93 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restri
                                                            int ny, int nz, int zc, unsigned int *__restrict__ mm_enc) {
   extern __shared__ double2 xs2[];  // [2][SX_ROWS][2][32]
   __shared__ float red[2][SX_WARPS];
+  __shared__ int s_bad[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 3) s_bad[tid] = 0;
+  __syncthreads();
   const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
   const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
   const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
   const int gx = x0 + lane * 4;
   const size_t nxy = (size_t)nx * ny;
-  const bool yz = warp < SX_YZ_WARPS;
-  const int ly = warp * 2;
-  double S[2][4][4];
+  const bool yz = warp < SX_TY;
+  double S[4][4];
 #pragma unroll
-  for (int r = 0; r < 2; r++)
+  for (int k = 0; k < 4; k++)
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-#pragma unroll
-      for (int q = 0; q < 4; q++) S[r][k][q] = 0.0;
+    for (int q = 0; q < 4; q++) S[k][q] = 0.0;
   float vmin = INFINITY, vmax = -INFINITY;
 
-  // raw rows of the plane being staged: rows 2*warp, 2*warp+1 (gy = y0 - 2 + r), prefetched one plane ahead
-  float raw[2][4], hal[2][2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
+  // loop-invariant addressing: the row this warp stages (gy = y0 - 2 + warp) and the output row it owns (y0 + warp)
+  const int sy = y0 - 2 + warp;
+  const bool rowok = sy >= 0 && sy < ny;
+  const float *rowp = in + (size_t)zs * nxy + (size_t)(rowok ? sy : 0) * nx;
+  const bool haloL = lane == 0 && x0 > 0, haloR0 = lane == 31 && gx + 4 < nx, haloR1 = lane == 31 && gx + 5 < nx;
+  const int oy = y0 + warp;
+  const bool yborder = oy < 2 || oy >= ny - 2;
+  const bool ook = yz && oy < ny && gx < nx;
+  float *outp = out + (size_t)oy * nx + gx;  // + z * nxy
+
+  // raw row of the plane being staged, prefetched one plane ahead
+  float raw[4], hal[2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
   auto fetch = [&](int zp) {
-#pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-      const int gy = y0 - 2 + warp * 2 + rr;
-      raw[rr][0] = raw[rr][1] = raw[rr][2] = raw[rr][3] = 0.f;
-      hal[rr][0] = hal[rr][1] = 0.f;
-      if (gy >= 0 && gy < ny && zp < ze) {
-        const float *row = in + (size_t)zp * nxy + (size_t)gy * nx;
-        load_row4<VEC>(row, gx, nx, raw[rr]);
-        if (lane == 0 && x0 > 0) { hal[rr][0] = __ldg(row + x0 - 2); hal[rr][1] = __ldg(row + x0 - 1); }
-        if (lane == 31) {
-          if (gx + 4 < nx) hal[rr][0] = __ldg(row + gx + 4);
-          if (gx + 5 < nx) hal[rr][1] = __ldg(row + gx + 5);
-        }
-      }
+    raw[0] = raw[1] = raw[2] = raw[3] = 0.f;
+    hal[0] = hal[1] = 0.f;
+    if (rowok && zp < ze) {
+      load_row4<VEC>(rowp, gx, nx, raw);
+      if (haloL) { hal[0] = __ldg(rowp + x0 - 2); hal[1] = __ldg(rowp + x0 - 1); }
+      if (haloR0) hal[0] = __ldg(rowp + gx + 4);
+      if (haloR1) hal[1] = __ldg(rowp + gx + 5);
     }
+    rowp += nxy;
   };
   fetch(zs);
-  for (int zp = zs; zp < ze; zp++) {
+  size_t zoff = (size_t)zs * nxy;
+  for (int zp = zs; zp < ze; zp++, zoff += nxy) {
     double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
-    // ---- x pass ----
-#pragma unroll
-    for (int rr = 0; rr < 2; rr++) {
-      const int r = warp * 2 + rr;
-      double v[8];
-#pragma unroll
-      for (int k = 0; k < 4; k++) v[2 + k] = (double)raw[rr][k];
-      v[0] = __shfl_up_sync(0xffffffffu, v[4], 1);
-      v[1] = __shfl_up_sync(0xffffffffu, v[5], 1);
-      v[6] = __shfl_down_sync(0xffffffffu, v[2], 1);
-      v[7] = __shfl_down_sync(0xffffffffu, v[3], 1);
-      if (lane == 0) { v[0] = (double)hal[rr][0]; v[1] = (double)hal[rr][1]; }
-      if (lane == 31) { v[6] = (double)hal[rr][0]; v[7] = (double)hal[rr][1]; }
-      double o[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const int x = gx + k;
-        const double f = round_to_f32(fir5(v[k], v[k + 1], v[k + 2], v[k + 3], v[k + 4]));
-        o[k] = (x < 2 || x >= nx - 2) ? v[k + 2] : f;
-      }
-      buf[r * 64 + lane] = make_double2(o[0], o[1]);
-      buf[r * 64 + 32 + lane] = make_double2(o[2], o[3]);
-    }
+    // ---- x pass ---- (inputs are screened only now, not at fetch time: touching the prefetched
+    // registers earlier would stall on loads that are meant to fly across the y/z passes)
+    const bool raw_bad = input_unsafe(raw[0]) | input_unsafe(raw[1]) | input_unsafe(raw[2]) | input_unsafe(raw[3]) |
+                         input_unsafe(hal[0]) | input_unsafe(hal[1]);
+    const bool warp_bad = __any_sync(0xffffffffu, raw_bad);
+    if (!warp_bad) x_pass_row<true>(raw, hal, lane, gx, nx, buf + warp * 64);
+    else x_pass_row<false>(raw, hal, lane, gx, nx, buf + warp * 64);
+    // tile-wide "unsafe input" flag for this plane through shared memory (three slots: the slot of
+    // plane zp+2 is cleared after this barrier, one full barrier before its writers can run)
+    if (warp_bad && lane == 0) s_bad[zp % 3] = 1;
     __syncthreads();
+    const bool cta_bad = s_bad[zp % 3] != 0;
+    if (tid == 0) s_bad[(zp + 2) % 3] = 0;
     fetch(zp + 1);  // next plane's loads fly while this plane's y/z passes run
     // ---- y pass + z pass ----
     if (yz) {
+      float ob[4], oi[4];
+      if (!cta_bad) yz_pass<true>(buf, warp, lane, yborder, S, ob, oi);
+      else yz_pass<false>(buf, warp, lane, yborder, S, ob, oi);
       const bool zborder = zp < 2 || zp >= nz - 2;
       const int zo = zp - 2;
       const bool emit_border = zborder && zp >= z0 && zp < z1;
       const bool emit_inner = zo >= z0 && zo < z1 && zo >= 2 && zo < nz - 2;
-      float ob[2][4], oi[2][4];
+      if (ook) {
+        if (emit_border) {
+          float *dst = outp + zoff;
+          if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(ob[0], ob[1], ob[2], ob[3]);
 #pragma unroll
-      for (int h = 0; h < 2; h++) {  // two voxels of the strip at a time keeps the live set under 128 registers
-        double c[6][2];
-#pragma unroll
-        for (int j = 0; j < 6; j++) {
-          const double2 pj = buf[(ly + j) * 64 + h * 32 + lane];
-          c[j][0] = pj.x; c[j][1] = pj.y;
+          for (int k = 0; k < 4; k++)
+            if (VEC || gx + k < nx) {
+              if (!VEC) dst[k] = ob[k];
+              vmin = fminf(vmin, ob[k]); vmax = fmaxf(vmax, ob[k]);
+            }
         }
+        if (emit_inner) {
+          float *dst = outp + (zoff - 2 * nxy);
+          if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[0], oi[1], oi[2], oi[3]);
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++) {
-          const int gy = y0 + ly + rr;
-          const bool yborder = gy < 2 || gy >= ny - 2;
-#pragma unroll
-          for (int kk = 0; kk < 2; kk++) {
-            const int k = 2 * h + kk;
-            const double f = round_to_f32(fir5(c[rr][kk], c[rr + 1][kk], c[rr + 2][kk], c[rr + 3][kk], c[rr + 4][kk]));
-            const double ys = yborder ? c[rr + 2][kk] : f;
-            const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
-            const double fin = __dadd_rn(S[rr][k][3], q2);
-            S[rr][k][3] = __dadd_rn(S[rr][k][2], q1);
-            S[rr][k][2] = __dadd_rn(S[rr][k][1], q0);
-            S[rr][k][1] = __dadd_rn(S[rr][k][0], q1);
-            S[rr][k][0] = q2;
-            ob[rr][k] = (float)ys;
-            oi[rr][k] = (float)fin;
-          }
-        }
-      }
-#pragma unroll
-      for (int rr = 0; rr < 2; rr++) {
-        const int gy = y0 + ly + rr;
-        if (gy < ny && gx < nx) {
-          if (emit_border) {
-            float *dst = out + (size_t)zp * nxy + (size_t)gy * nx + gx;
-            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(ob[rr][0], ob[rr][1], ob[rr][2], ob[rr][3]);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              if (gx + k < nx) {
-                if (!VEC) dst[k] = ob[rr][k];
-                vmin = fminf(vmin, ob[rr][k]); vmax = fmaxf(vmax, ob[rr][k]);
-              }
-          }
-          if (emit_inner) {
-            float *dst = out + (size_t)zo * nxy + (size_t)gy * nx + gx;
-            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[rr][0], oi[rr][1], oi[rr][2], oi[rr][3]);
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-              if (gx + k < nx) {
-                if (!VEC) dst[k] = oi[rr][k];
-                vmin = fminf(vmin, oi[rr][k]); vmax = fmaxf(vmax, oi[rr][k]);
-              }
-          }
+          for (int k = 0; k < 4; k++)
+            if (VEC || gx + k < nx) {
+              if (!VEC) dst[k] = oi[k];
+              vmin = fminf(vmin, oi[k]); vmax = fmaxf(vmax, oi[k]);
+            }
         }
       }
     }

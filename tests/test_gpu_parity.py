@@ -37,6 +37,23 @@ def test_smooth_bit_exact(eng, orc, name):
     assert sha(a) == GOLD["smooth"][name]
 
 
+def test_smooth_unsafe_inputs_bit_exact(eng, orc):
+    """denormals, -0, huge values: the kernel's FP64-adder rounding shortcut must hand these planes to
+    the real f64->f32 conversions (and still match the reference bit for bit)"""
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((20, 33, 40)).astype(np.float32)
+    v[3:6, 4:9, 5:30] = 1e-42
+    v[7, 7, 7] = -0.0
+    v[10:12, 10:20, 3:9] = 3e38
+    v[15, 5, 5] = 1e-39
+    v[2, 2, 2:12] = 0.0
+    assert bits_differ(eng.smooth(v), orc.smooth(v)) == 0
+    z = np.zeros((9, 12, 64), np.float32)
+    z[4, 6, 30] = 1.0
+    assert bits_differ(eng.smooth(z), orc.smooth(z)) == 0
+    assert bits_differ(eng.smooth(-z), orc.smooth(-z)) == 0
+
+
 @pytest.mark.parametrize("name", list(VOLS))
 def test_front_masks_bbox_bit_exact(eng, orc, name):
     """smooth -> range -> isolevel sanity -> CC (largest / bubbles) -> dilate -> darken -> bbox"""
