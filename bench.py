@@ -263,7 +263,15 @@ def main():
             one()
         barrier()
         dt = max_over_ranks((time.perf_counter() - t0) / ke)
-        e2e = {"value": world * N / dt / 1e9, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
+        # one untimed call through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
+        r2 = lib.Result()
+        pv, pt = C.c_void_p(), C.c_void_p()
+        o2 = lib.Opts(ISO, 0, 1, 1, 1, 0, 0)
+        eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o2), C.byref(pv), C.byref(pt), C.byref(r2)))
+        libc.free(pv)
+        libc.free(pt)
+        breakdown = {"h2d_ms": round(r2.h2d_ms, 2), "device_ms": round(r2.ms[7], 2), "d2h_ms": round(r2.d2h_ms, 2)}
+        e2e = {"value": world * N / dt / 1e9, "breakdown": breakdown, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
                "d2h_bytes_per_step": nv * 24 + nt * 12, "ms_per_step": dt * 1e3, "steps": ke,
                "api": "meshify() (include/meshify.h), pinned host volume in, malloc'd host mesh out"}
         L.b2m_host_free(hp)

@@ -63,6 +63,7 @@ typedef struct {
   int iso_reset;             /* 1 if the isolevel was out of range and reset */
   float ms[B2M_NSTAGE];      /* CUDA-event device time per stage, ms; ms[B2M_T_TOTAL] = whole call */
   uint64_t launches;         /* kernels launched by this call */
+  float h2d_ms, d2h_ms;      /* b2m_meshify_host only: wall-clock time of the host->device / device->host copies */
 } b2m_result;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -105,6 +105,9 @@ struct b2m_ctx {
   int tables_ready;
   int sm_count;
   unsigned ev_mask;        // which stage event pairs were recorded in the current call
+  // host<->device staging for pageable host memory (b2m_copy_h2d / b2m_copy_d2h)
+  void *stage[3];          // pinned ring buffers (B2M_STAGE_BYTES each), allocated on first use
+  cudaEvent_t stage_ev[3];
   int profile;             // record an event pair around every kernel launch
   int nkt, nkt_events;     // entries used in this call / event pairs created so far
   b2m_ktimer kt[B2M_KT_MAX];
@@ -126,6 +129,11 @@ static inline T *b2m_ptr(b2m_ctx *ctx, int which) {
   return reinterpret_cast<T *>(ctx->buf[which].p);
 }
 int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
+// bulk copies between device memory and ANY host memory (pinned: one DMA; pageable: pipelined through
+// pinned ring buffers with a multi-threaded host memcpy); synchronous on return
+#define B2M_STAGE_BYTES ((size_t)32 << 20)
+int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 
 #define B2M_LAUNCHED(ctx) ((ctx)->launches++)
 

@@ -1,5 +1,6 @@
 // ctx.cu — context, workspace arena, memory helpers of libb2m.
 #include <stdarg.h>
+#include <unistd.h>
 
 #include "common.cuh"
 
@@ -62,6 +63,8 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
     if (c->buf[i].p) cudaFree(c->buf[i].p);
   for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); i++) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < c->nkt_events; i++) { cudaEventDestroy(c->kt[i].e0); cudaEventDestroy(c->kt[i].e1); }
+  for (int i = 0; i < 3; i++)
+    if (c->stage[i]) { cudaFreeHost(c->stage[i]); cudaEventDestroy(c->stage_ev[i]); }
   cudaFreeHost(c->h_scalars);
   cudaStreamDestroy(c->stream);
   free(c);
@@ -133,6 +136,87 @@ int b2m_reserve(b2m_ctx *ctx, int which, size_t bytes) {
   return B2M_OK;
 }
 
+// ---- bulk host <-> device copies ---------------------------------------------------------------------
+static bool host_is_pinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+static int stage_init(b2m_ctx *ctx) {
+  for (int i = 0; i < 3; i++)
+    if (!ctx->stage[i]) {
+      CU_TRY(cudaMallocHost(&ctx->stage[i], B2M_STAGE_BYTES));
+      CU_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+  return B2M_OK;
+}
+// multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded
+// copy); runs serially when called from inside a caller's own OpenMP region
+static int par_threads(void) {
+  static int n = 0;
+  if (!n) {
+    long c = sysconf(_SC_NPROCESSORS_ONLN);
+    const char *e = getenv("B2M_COPY_THREADS");
+    n = e ? atoi(e) : (int)(c > 16 ? 16 : c);
+    if (n < 1) n = 1;
+  }
+  return n;
+}
+static void par_memcpy(void *dst, const void *src, size_t n) {
+  const size_t slice = (size_t)4 << 20;
+  const long long ns = (long long)((n + slice - 1) / slice);
+#pragma omp parallel for schedule(static) num_threads(par_threads()) if (ns > 1)
+  for (long long i = 0; i < ns; i++) {
+    const size_t o = (size_t)i * slice;
+    memcpy((char *)dst + o, (const char *)src + o, n - o < slice ? n - o : slice);
+  }
+}
+
+int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+  if (!bytes) return B2M_OK;
+  if (bytes < ((size_t)1 << 20) || host_is_pinned(h_dst)) {
+    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2M_OK;
+  }
+  B2M_TRY(stage_init(ctx));
+  const size_t nchunk = (bytes + B2M_STAGE_BYTES - 1) / B2M_STAGE_BYTES;
+  auto issue = [&](size_t c) -> cudaError_t {
+    const size_t o = c * B2M_STAGE_BYTES, n = bytes - o < B2M_STAGE_BYTES ? bytes - o : B2M_STAGE_BYTES;
+    cudaError_t e = cudaMemcpyAsync(ctx->stage[c % 3], (const char *)d_src + o, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(ctx->stage_ev[c % 3], ctx->stream);
+  };
+  for (size_t c = 0; c < nchunk && c < 3; c++) CU_TRY(issue(c));
+  for (size_t c = 0; c < nchunk; c++) {
+    const size_t o = c * B2M_STAGE_BYTES, n = bytes - o < B2M_STAGE_BYTES ? bytes - o : B2M_STAGE_BYTES;
+    CU_TRY(cudaEventSynchronize(ctx->stage_ev[c % 3]));
+    par_memcpy((char *)h_dst + o, ctx->stage[c % 3], n);
+    if (c + 3 < nchunk) CU_TRY(issue(c + 3));
+  }
+  return B2M_OK;
+}
+
+int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
+  if (!bytes) return B2M_OK;
+  if (bytes < ((size_t)1 << 20) || host_is_pinned(h_src)) {
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    return B2M_OK;
+  }
+  B2M_TRY(stage_init(ctx));
+  const size_t nchunk = (bytes + B2M_STAGE_BYTES - 1) / B2M_STAGE_BYTES;
+  for (size_t c = 0; c < nchunk; c++) {
+    const size_t o = c * B2M_STAGE_BYTES, n = bytes - o < B2M_STAGE_BYTES ? bytes - o : B2M_STAGE_BYTES;
+    if (c >= 3) CU_TRY(cudaEventSynchronize(ctx->stage_ev[c % 3]));  // the DMA that last read this buffer is done
+    par_memcpy(ctx->stage[c % 3], (const char *)h_src + o, n);
+    CU_TRY(cudaMemcpyAsync((char *)d_dst + o, ctx->stage[c % 3], n, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(cudaEventRecord(ctx->stage_ev[c % 3], ctx->stream));
+  }
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
 int b2m_fetch_scalars(b2m_ctx *ctx) {
   CU_TRY(cudaMemcpyAsync(ctx->h_scalars, ctx->buf[BUF_SCALARS].p, sizeof(b2m_scalars), cudaMemcpyDeviceToHost,
                          ctx->stream));
@@ -171,16 +255,12 @@ extern "C" int b2m_host_free(void *hptr) {
 extern "C" int b2m_h2d(b2m_ctx *ctx, void *dst, const void *src, size_t bytes) {
   if (!ctx) return B2M_EARG;
   CU_TRY(cudaSetDevice(ctx->device));
-  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  return B2M_OK;
+  return b2m_copy_h2d(ctx, dst, src, bytes);
 }
 extern "C" int b2m_d2h(b2m_ctx *ctx, void *dst, const void *src, size_t bytes) {
   if (!ctx) return B2M_EARG;
   CU_TRY(cudaSetDevice(ctx->device));
-  CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_TRY(cudaStreamSynchronize(ctx->stream));
-  return B2M_OK;
+  return b2m_copy_d2h(ctx, dst, src, bytes);
 }
 extern "C" int b2m_sync(b2m_ctx *ctx) {
   if (!ctx) return B2M_EARG;
