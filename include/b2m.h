@@ -110,6 +110,35 @@ int b2m_meshify_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], 
 int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t dims[3], const b2m_opts *opts,
                      void **verts, void **tris, b2m_result *res);
 
+/* ---- z-slabs across GPUs (replaces nothing in the reference, which is single-threaded) ----
+ * The volume is cut into contiguous z-slabs, one rank (GPU) per slab, raster order = rank order.  Every rank
+ * calls b2m_meshify_slab() with its own planes; the ranks exchange halo planes for the smooth and for marching
+ * cubes, merge connected components across the slab faces, number the vertices globally in the reference's
+ * emission order and weld the seam vertices.  The assembled mesh equals b2m_meshify_device() on the whole
+ * volume bit for bit.  Transport: NCCL (one process per GPU, libnccl.so.2 loaded at run time) or a
+ * single-process group of host threads (peer copies). */
+typedef struct b2m_comm b2m_comm;
+int b2m_comm_nccl_id(void *id128);  /* rank 0: 128-byte ncclUniqueId to hand to the other ranks */
+int b2m_comm_create_nccl(b2m_comm **comm, b2m_ctx *ctx, const void *id128, int rank, int world);
+int b2m_comm_create_local(b2m_comm **comms /* [world] */, int world);  /* one handle per host thread */
+void b2m_comm_destroy(b2m_comm *comm);
+int b2m_comm_reset(b2m_comm *comm);
+
+typedef struct {
+  b2m_result r;          /* GLOBAL counts (nverts, ntris, pre_*), range, isolevel, bbox, this rank's stage times;
+                            r.d_verts / r.d_tris = this rank's blocks */
+  const void *d_verts;   /* this rank's welded vertices: [edge block | centroid block | extra block], 3 f64 each */
+  const void *d_tris;    /* this rank's triangles, 3 i32 each, indices into the ASSEMBLED vertex array */
+  int nv_edge, nv_cent, nv_extra, ntris_local;
+  int64_t v_edge_off, v_cent_off, v_extra_off;  /* where the three blocks sit in the assembled vertex array */
+  int64_t tri_off;                              /* where the triangles sit in the assembled triangle array */
+} b2m_slab_result;
+
+/* d_slab: planes [z0, z0+nzl) of a volume of gdims (x fastest), resident on ctx's device; comm may be NULL for a
+ * single slab covering the whole volume.  Collective: every rank of comm must call it. */
+int b2m_meshify_slab(b2m_ctx *ctx, b2m_comm *comm, const float *d_slab, const int64_t gdims[3], int64_t z0, int64_t nzl,
+                     const b2m_opts *opts, b2m_slab_result *out);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

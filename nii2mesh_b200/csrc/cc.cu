@@ -26,7 +26,9 @@
 struct cc_geom {
   int nx, ny, nz, w;
   long long nwords;
+  int zface_lo, zface_hi;  // plane 0 / plane nz-1 of the labelled region is a face of the whole volume (slabs)
 };
+#define CC_SENT 0xffffffffu /* slabs: parent of a seam root that belongs to the selected (largest) component */
 
 __device__ __forceinline__ uint32_t ld_parent(const uint2 *nodes, uint32_t a) {
   return __ldcg(reinterpret_cast<const unsigned int *>(&nodes[a].x));
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
   // phase B: local roots collect the voxel count and the face flag of their local component.
   // Lanes that reach the same root combine first (one shared-memory atomic per warp and root: 512
   // same-address atomics per tile were the bottleneck of the first version).
-  const bool rowface = (y == 0) || (y == g.ny - 1) || (z == 0) || (z == g.nz - 1);
+  const bool rowface = (y == 0) || (y == g.ny - 1) || (z == 0 && g.zface_lo) || (z == g.nz - 1 && g.zface_hi);
   uint32_t myroot[16];  // local root per run of this word, in run order (<= 16 runs)
   int nrun = 0;
   {
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
 __device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ nodes, uint32_t slot) {
   uint32_t p = nodes[slot].x;
   while (p != slot) {
+    if (p == CC_SENT) return CC_SENT;
     slot = p;
     p = nodes[slot].x;
   }
@@ -364,29 +367,36 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
 // mode 0: out = runs of `bits` whose root is the largest component
 // mode 1: out = other | runs of `bits` (the background) whose root does not touch a face, only if
 //         there are >= 2 background components (src/bwlabel.c:488-491); else out = other
+// Slabs: the decision is global and made on the host: sel >= 0 is the winning root slot of THIS rank,
+// sel == -1 no local winner (runs of seam roots marked CC_SENT are still selected); sel == -2 reads
+// *best (single volume).  nroots_ovr >= 0 replaces *nroots by the global component count.
 __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ bits, long long nwords,
                                                    const uint2 *__restrict__ nodes, int mode,
                                                    const unsigned long long *__restrict__ best,
                                                    const unsigned int *__restrict__ nroots,
-                                                   const uint32_t *__restrict__ other, uint32_t *__restrict__ out) {
+                                                   const uint32_t *__restrict__ other, uint32_t *__restrict__ out,
+                                                   long long sel, long long nroots_ovr) {
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (word >= nwords) return;
   uint32_t wv = __ldg(bits + word);
   uint32_t res = 0;
   if (mode == 0) {
-    uint32_t bestslot = 0xffffffffu - (uint32_t)(*best & 0xffffffffull);
-    bool have = *best != 0ull;
+    uint32_t bestslot;
+    bool have;
+    if (sel == -2) { bestslot = 0xffffffffu - (uint32_t)(*best & 0xffffffffull); have = *best != 0ull; }
+    else { bestslot = sel >= 0 ? (uint32_t)sel : 0xfffffffeu; have = true; }
     uint32_t rest = wv;
     while (rest && have) {
       int s = __ffs(rest) - 1;
       int e = run_end(wv, s);
       uint32_t rm = bits_range(s, e);
       rest &= ~rm;
-      if (cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1)) == bestslot) res |= rm;
+      const uint32_t r = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+      if (r == bestslot || r == CC_SENT) res |= rm;
     }
   } else {
     res = __ldg(other + word);
-    if (*nroots > 1u) {
+    if ((nroots_ovr >= 0 ? (unsigned long long)nroots_ovr : (unsigned long long)*nroots) > 1ull) {
       uint32_t rest = wv;
       while (rest) {
         int s = __ffs(rest) - 1;
@@ -410,15 +420,17 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
 //           reference's dilate() never tests offset (-1,-1,-1), src/meshify.c:252]
 // so that out(z) = Q(z-1) | PF(z) | PF(z+1): 3 word loads per output word instead of 27.
 #define DIL_ZC 16
+// Slabs: the arrays are indexed with GLOBAL z (pre-offset EXT buffers), g.nz is the global NZ and the
+// kernel writes the own planes [zbeg, zend) only.
 __global__ void __launch_bounds__(256) k_dilate_bbox(const uint32_t *__restrict__ largest,
-                                                     const uint32_t *__restrict__ bright_src, cc_geom g,
+                                                     const uint32_t *__restrict__ bright_src, cc_geom g, int zbeg, int zend,
                                                      uint32_t *__restrict__ keep, int *__restrict__ lohi) {
   const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (y, xw) flattened
   const long long ncol = (long long)g.ny * g.w;
   int lo0 = INT_MAX, lo1 = INT_MAX, lo2 = INT_MAX, hi0 = -1, hi1 = -1, hi2 = -1;
   if (col < ncol) {
     const int y = (int)(col / g.w), xw = (int)(col - (long long)y * g.w);
-    const int z0 = blockIdx.y * DIL_ZC, z1 = min(z0 + DIL_ZC, g.nz);
+    const int z0 = zbeg + blockIdx.y * DIL_ZC, z1 = min(z0 + DIL_ZC, zend);
     const long long plane = ncol;
     // interior x mask of this word: voxels 1 .. nx-2
     uint32_t im = 0xffffffffu;
@@ -533,12 +545,340 @@ static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2
   return B2M_OK;
 }
 
+// ================================================================================================
+// Slabs: merging the components of neighbouring z-slabs.
+// Every rank labels its own planes with local run slots.  The local roots that reach a seam plane
+// ("seam roots") get compact ids (rank offset + index in the rank's sorted unique list); the upper
+// rank of every seam lists the adjacent (lower root, upper root) pairs, the de-duplicated pair lists
+// and the per-root (slot, count|face flag) entries of all ranks are all-gathered, and every rank
+// resolves the same small union-find (union by minimum id = earliest first voxel in raster order,
+// because ids are ordered by (rank, slot)).  Global sizes / face flags come back into the local
+// forest through the seam roots only; everything else stays slab-local.
+// ================================================================================================
+__global__ void __launch_bounds__(256) k_seam_collect(const uint32_t *__restrict__ bits, cc_geom g, const uint2 *__restrict__ nodes,
+                                                      int do_first, int do_last, uint64_t *__restrict__ list, unsigned cap,
+                                                      unsigned int *__restrict__ count, unsigned int *__restrict__ overflow) {
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const int which = blockIdx.y;
+  if (which == 0 ? !do_first : (!do_last || (g.nz == 1 && do_first))) return;
+  const long long word = (which == 0 ? 0 : (long long)(g.nz - 1) * pw) + t;
+  const uint32_t wv = __ldg(bits + word);
+  uint32_t starts = wv & ~(wv << 1);
+  while (starts) {
+    const int s = __ffs(starts) - 1;
+    starts &= starts - 1;
+    const uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+    const unsigned pos = atomicAdd(count, 1u);
+    if (pos < cap) list[pos] = root; else atomicOr(overflow, 4u);
+  }
+}
+__global__ void __launch_bounds__(256) k_seam_unique_flags(const uint64_t *__restrict__ keys, unsigned n, uint32_t *__restrict__ flag) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_seam_unique_scatter(const uint64_t *__restrict__ keys, unsigned n, const uint32_t *__restrict__ scan,
+                                                             const unsigned int *__restrict__ total, T *__restrict__ out) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t me = scan[i], next = i + 1 < n ? scan[i + 1] : *total;
+  if (next != me) out[me] = (T)keys[i];
+}
+__device__ __forceinline__ unsigned seam_lower_bound(const uint32_t *__restrict__ a, unsigned n, uint32_t v) {
+  unsigned lo = 0, hi = n;
+  while (lo < hi) {
+    const unsigned mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+// dense[word in plane * 16 + run slot] = index of the run's root in U, for the LAST own plane (sent up)
+__global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__ bits, cc_geom g, const uint2 *__restrict__ nodes,
+                                                    const uint32_t *__restrict__ U, unsigned m, uint32_t *__restrict__ dense) {
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const long long word = (long long)(g.nz - 1) * pw + t;
+  const uint32_t wv = __ldg(bits + word);
+  uint32_t starts = wv & ~(wv << 1);
+  while (starts) {
+    const int s = __ffs(starts) - 1;
+    starts &= starts - 1;
+    const uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+    dense[(size_t)t * 16 + (s >> 1)] = seam_lower_bound(U, m, root);
+  }
+}
+// upper rank of a seam: every run of the first own plane against the runs of the plane below
+// (18-connectivity: face + the four edge neighbours in that plane; 6-connectivity: face only)
+template <int CONN>
+__global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ below, cc_geom g,
+                                                    const uint2 *__restrict__ nodes, const uint32_t *__restrict__ U, unsigned m,
+                                                    unsigned off_me, unsigned off_below, const uint32_t *__restrict__ dense_below,
+                                                    int mb, uint64_t *__restrict__ pairs, unsigned cap,
+                                                    unsigned int *__restrict__ count, unsigned int *__restrict__ overflow) {
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const int y = (int)(t / g.w), xw = (int)(t - (long long)y * g.w);
+  const uint32_t wv = __ldg(bits + t);
+  uint64_t last = ~0ull;
+  for (uint32_t rest = wv; rest;) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    const uint32_t rm = bits_range(s, e);
+    rest &= ~rm;
+    const uint32_t root = cc_final_root(nodes, (uint32_t)t * 16u + (uint32_t)(s >> 1));
+    const uint64_t me = (uint64_t)(off_me + seam_lower_bound(U, m, root));
+    auto emit = [&](int nxw, int ny_, int st) {
+      const uint64_t nb = (uint64_t)(off_below + __ldg(dense_below + ((size_t)ny_ * g.w + nxw) * 16 + (st >> 1)));
+      const uint64_t key = (nb << mb) | me;
+      if (key == last) return;
+      last = key;
+      const unsigned pos = atomicAdd(count, 1u);
+      if (pos < cap) pairs[pos] = key; else atomicOr(overflow, 8u);
+    };
+    auto row = [&](int dy, bool wide) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= g.ny) return;
+      const uint32_t *r = below + (size_t)yy * g.w;
+      const uint32_t nw = __ldg(r + xw);
+      uint32_t msk = rm;
+      if (wide) msk |= (rm << 1) | (rm >> 1);
+      uint32_t tt = nw & msk;
+      while (tt) {
+        const int b = __ffs(tt) - 1;
+        const int st = run_start(nw, b);
+        const int en = run_end(nw, st);
+        emit(xw, yy, st);
+        tt &= ~bits_range(st, en);
+      }
+      if (wide) {
+        if (s == 0 && xw > 0) {
+          const uint32_t pv = __ldg(r + xw - 1);
+          if (pv >> 31) emit(xw - 1, yy, run_start(pv, 31));
+        }
+        if (e == 31 && xw + 1 < g.w) {
+          const uint32_t nv = __ldg(r + xw + 1);
+          if (nv & 1u) emit(xw + 1, yy, 0);
+        }
+      }
+    };
+    row(0, CONN >= 18);
+    if (CONN >= 18) { row(-1, false); row(1, false); }
+  }
+}
+// per own seam root: (local slot, count | face flag)
+__global__ void __launch_bounds__(256) k_seam_entries(const uint32_t *__restrict__ U, unsigned m, const uint2 *__restrict__ nodes,
+                                                      uint2 *__restrict__ ent) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) ent[i] = make_uint2(U[i], nodes[U[i]].y);
+}
+__global__ void __launch_bounds__(256) k_seam_iota(uint32_t *__restrict__ par, unsigned n) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) par[i] = i;
+}
+__device__ __forceinline__ uint32_t uf32_find(uint32_t *par, uint32_t a) {
+  uint32_t p = __ldcg(par + a);
+  while (p != a) {
+    const uint32_t gp = __ldcg(par + p);
+    if (gp != p) atomicMin(par + a, gp);
+    a = p;
+    p = gp;
+  }
+  return a;
+}
+__global__ void __launch_bounds__(256) k_seam_union(const uint64_t *__restrict__ pairs, unsigned n, int mb, uint32_t *par) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a = (uint32_t)(pairs[i] >> mb), b = (uint32_t)(pairs[i] & ((1ull << mb) - 1ull));
+  for (;;) {
+    a = uf32_find(par, a);
+    b = uf32_find(par, b);
+    if (a == b) return;
+    if (a < b) { const uint32_t t = a; a = b; b = t; }
+    const uint32_t old = atomicMin(par + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+__global__ void __launch_bounds__(256) k_seam_flatten(uint32_t *par, unsigned n) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = uf32_find(par, i);
+  if (r != i) atomicMin(par + i, r);
+}
+__global__ void __launch_bounds__(256) k_seam_stats(unsigned n, const uint32_t *__restrict__ par, const uint2 *__restrict__ ent,
+                                                    unsigned long long *__restrict__ gcnt, uint32_t *__restrict__ gflag) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t r = par[i];
+  const uint32_t st = ent[i].y;
+  atomicAdd(gcnt + r, (unsigned long long)(st & 0x7fffffffu));
+  if (st >> 31) atomicOr(gflag + r, 1u);
+}
+__global__ void __launch_bounds__(256) k_seam_best(unsigned n, const uint32_t *__restrict__ par, const unsigned long long *__restrict__ gcnt,
+                                                   unsigned long long *__restrict__ best, unsigned int *__restrict__ nroots) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || par[i] != i) return;
+  atomicAdd(nroots, 1u);
+  atomicMax(best, (gcnt[i] << 30) | (unsigned long long)(0x3fffffffu - i));
+}
+// mode 1: global face flags into the own seam roots; mode 0: mark the own seam roots of component gstar
+__global__ void __launch_bounds__(256) k_seam_apply(unsigned m, unsigned off, const uint32_t *__restrict__ U, const uint32_t *__restrict__ par,
+                                                    const uint32_t *__restrict__ gflag, uint2 *nodes, int mode, long long gstar) {
+  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const uint32_t r = par[off + i];
+  if (mode == 1) { if (gflag[r]) atomicOr(&nodes[U[i]].y, 0x80000000u); }
+  else if ((long long)r == gstar) nodes[U[i]].x = CC_SENT;
+}
+
+struct seam_result {
+  unsigned M, K;                 // seam roots over all ranks, components among them
+  unsigned long long best;      // (size << 30) | (2^30-1 - id) of the largest seam component (0: none)
+  int best_rank; unsigned best_slot;  // first voxel of that component: (rank, local slot)
+  unsigned m, off;              // own seam roots and their id offset
+  const uint32_t *U, *par, *gflag;
+};
+
+static int seam_bits(unsigned long long n) {
+  int b = 1;
+  while ((1ull << b) < n) b++;
+  return b;
+}
+
+// labelled `bits_own` (own planes, geometry cg) -> seam resolution.  `below` = the neighbour's last plane
+// (EXT plane 0) when this rank has a lower neighbour.
+static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
+                    const cc_geom &cg, uint2 *nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
+  const int W = sl.world, me = sl.rank;
+  const size_t pw = (size_t)cg.ny * cg.w;
+  const unsigned pblocks = b2m_cdiv(pw, 256);
+  memset(sr, 0, sizeof(*sr));
+  // 1. roots of the runs on the own boundary planes -> sorted unique list U
+  const unsigned cap_runs = (unsigned)(2 * pw * 16);
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM0, (size_t)cap_runs * 8 + (size_t)cap_runs * 4 + 256));
+  uint64_t *list = b2m_ptr<uint64_t>(ctx, BUF_SEAM0);
+  uint32_t *flag = reinterpret_cast<uint32_t *>(list + cap_runs);
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM1, (size_t)cap_runs * 4 + 2 * pw * 64 + 256));
+  uint32_t *U = b2m_ptr<uint32_t>(ctx, BUF_SEAM1);
+  uint32_t *dense_send = U + cap_runs, *dense_recv = dense_send + pw * 16;
+  CU_TRY(cudaMemsetAsync(&d_sc->seam_n, 0, 4, ctx->stream));
+  KT_LAUNCH(ctx, "seam_collect", k_seam_collect<<<dim3(pblocks, 2), 256, 0, ctx->stream>>>(bits_own, cg, nodes, sl.hl, sl.hh, list, cap_runs, &d_sc->seam_n, &d_sc->overflow));
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  const unsigned nL = ctx->h_scalars->seam_n;
+  if (nL > cap_runs) { b2m_set_error("seam: run list overflow"); return B2M_ECUDA; }
+  if (nL > 0) {
+    B2M_TRY(b2m_sort_u64(ctx, list, nL, 32));
+    KT_LAUNCH(ctx, "seam_unique", k_seam_unique_flags<<<b2m_cdiv(nL, 256), 256, 0, ctx->stream>>>(list, nL, flag));
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, flag, flag, nL, &d_sc->seam_n));
+    KT_LAUNCH(ctx, "seam_unique", k_seam_unique_scatter<uint32_t><<<b2m_cdiv(nL, 256), 256, 0, ctx->stream>>>(list, nL, flag, &d_sc->seam_n, U));
+  }
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_sync_scalars(ctx, comm));
+  unsigned offs[65], M = 0;
+  for (int r = 0; r < W; r++) { offs[r] = M; M += b2m_sc(ctx, comm, r)->seam_n; }
+  offs[W] = M;
+  const unsigned m = offs[me + 1] - offs[me];
+  sr->M = M; sr->m = m; sr->off = offs[me]; sr->U = U;
+  if (M == 0) return B2M_OK;
+  if (M >= (1u << 30)) { b2m_set_error("seam: too many seam components"); return B2M_EARG; }
+  const int mb = seam_bits(M);
+  // 2. compact ids of the last own plane go up; pairs are listed by the upper rank of each seam
+  if (sl.hh) KT_LAUNCH(ctx, "seam_dense", k_seam_dense<<<pblocks, 256, 0, ctx->stream>>>(bits_own, cg, nodes, U, m, dense_send));
+  B2M_TRY(b2m_comm_exchange(ctx, comm, dense_send, sl.hh ? pw * 64 : 0, dense_recv, sl.hl ? pw * 64 : 0, nullptr, 0, nullptr, 0));
+  const unsigned cap_pairs = (unsigned)(pw * 96);
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM2, (size_t)cap_pairs * 8 + (size_t)cap_pairs * 4 + 256));
+  uint64_t *pairs = b2m_ptr<uint64_t>(ctx, BUF_SEAM2);
+  uint32_t *pflag = reinterpret_cast<uint32_t *>(pairs + cap_pairs);
+  CU_TRY(cudaMemsetAsync(&d_sc->seam_n, 0, 4, ctx->stream));
+  if (sl.hl) {
+    if (conn >= 18)
+      KT_LAUNCH(ctx, "seam_pairs", k_seam_pairs<18><<<pblocks, 256, 0, ctx->stream>>>(bits_own, below, cg, nodes, U, m, offs[me], offs[me - 1], dense_recv, mb, pairs, cap_pairs, &d_sc->seam_n, &d_sc->overflow));
+    else
+      KT_LAUNCH(ctx, "seam_pairs", k_seam_pairs<6><<<pblocks, 256, 0, ctx->stream>>>(bits_own, below, cg, nodes, U, m, offs[me], offs[me - 1], dense_recv, mb, pairs, cap_pairs, &d_sc->seam_n, &d_sc->overflow));
+  }
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  const unsigned np_raw = ctx->h_scalars->seam_n;
+  if (np_raw > cap_pairs) { b2m_set_error("seam: pair list overflow"); return B2M_ECUDA; }
+  // the unique pairs and the own entries go to BUF_SEAM0 (the root list is no longer needed)
+  const size_t up_bytes = ((size_t)np_raw * 8 + 255) & ~(size_t)255;
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM0, up_bytes + (size_t)m * 8 + 256));
+  uint64_t *upairs = b2m_ptr<uint64_t>(ctx, BUF_SEAM0);
+  uint2 *ent_own = reinterpret_cast<uint2 *>(b2m_ptr<char>(ctx, BUF_SEAM0) + up_bytes);
+  if (np_raw > 0) {
+    B2M_TRY(b2m_sort_u64(ctx, pairs, np_raw, 2 * mb));
+    KT_LAUNCH(ctx, "seam_unique", k_seam_unique_flags<<<b2m_cdiv(np_raw, 256), 256, 0, ctx->stream>>>(pairs, np_raw, pflag));
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, pflag, pflag, np_raw, &d_sc->seam_n));
+    KT_LAUNCH(ctx, "seam_unique", k_seam_unique_scatter<uint64_t><<<b2m_cdiv(np_raw, 256), 256, 0, ctx->stream>>>(pairs, np_raw, pflag, &d_sc->seam_n, upairs));
+  }
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_sync_scalars(ctx, comm));
+  size_t pbytes[64], ebytes[64];
+  unsigned Ptot = 0;
+  for (int r = 0; r < W; r++) {
+    const unsigned npr = b2m_sc(ctx, comm, r)->seam_n;
+    pbytes[r] = (size_t)npr * 8;
+    ebytes[r] = (size_t)(offs[r + 1] - offs[r]) * 8;
+    Ptot += npr;
+  }
+  // 3. replicated resolution.  BUF_SEAM2 is re-carved: all pairs | all entries | parent | gcnt | gflag
+  size_t need = (size_t)Ptot * 8 + (size_t)M * (8 + 4 + 8 + 4) + 2048;
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM2, need));
+  char *base = b2m_ptr<char>(ctx, BUF_SEAM2);
+  size_t o = 0;
+  auto take = [&](size_t bytes) { char *q = base + o; o = (o + bytes + 255) & ~(size_t)255; return q; };
+  uint64_t *all_pairs = reinterpret_cast<uint64_t *>(take((size_t)Ptot * 8));
+  uint2 *all_ent = reinterpret_cast<uint2 *>(take((size_t)M * 8));
+  uint32_t *par = reinterpret_cast<uint32_t *>(take((size_t)M * 4));
+  unsigned long long *gcnt = reinterpret_cast<unsigned long long *>(take((size_t)M * 8));
+  uint32_t *gflag = reinterpret_cast<uint32_t *>(take((size_t)M * 4));
+  if (m) KT_LAUNCH(ctx, "seam_entries", k_seam_entries<<<b2m_cdiv(m, 256), 256, 0, ctx->stream>>>(U, m, nodes, ent_own));
+  B2M_TRY(b2m_comm_allgatherv(ctx, comm, upairs, all_pairs, pbytes));
+  B2M_TRY(b2m_comm_allgatherv(ctx, comm, ent_own, all_ent, ebytes));
+  const unsigned mblocks = b2m_cdiv(M, 256);
+  KT_LAUNCH(ctx, "seam_uf", k_seam_iota<<<mblocks, 256, 0, ctx->stream>>>(par, M));
+  if (Ptot) KT_LAUNCH(ctx, "seam_uf", k_seam_union<<<b2m_cdiv(Ptot, 256), 256, 0, ctx->stream>>>(all_pairs, Ptot, mb, par));
+  KT_LAUNCH(ctx, "seam_uf", k_seam_flatten<<<mblocks, 256, 0, ctx->stream>>>(par, M));
+  CU_TRY(cudaMemsetAsync(gcnt, 0, (size_t)M * 8, ctx->stream));
+  CU_TRY(cudaMemsetAsync(gflag, 0, (size_t)M * 4, ctx->stream));
+  KT_LAUNCH(ctx, "seam_stats", k_seam_stats<<<mblocks, 256, 0, ctx->stream>>>(M, par, all_ent, gcnt, gflag));
+  CU_TRY(cudaMemsetAsync(&d_sc->best_seam, 0, 8, ctx->stream));
+  CU_TRY(cudaMemsetAsync(&d_sc->seam_roots, 0, 4, ctx->stream));
+  KT_LAUNCH(ctx, "seam_stats", k_seam_best<<<mblocks, 256, 0, ctx->stream>>>(M, par, gcnt, &d_sc->best_seam, &d_sc->seam_roots));
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  sr->K = ctx->h_scalars->seam_roots;
+  sr->best = ctx->h_scalars->best_seam;
+  sr->par = par; sr->gflag = gflag;
+  if (sr->best) {
+    const unsigned id = 0x3fffffffu - (unsigned)(sr->best & 0x3fffffffull);
+    uint2 e;
+    CU_TRY(cudaMemcpyAsync(&e, all_ent + id, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(cudaStreamSynchronize(ctx->stream));
+    int r = 0;
+    while (r + 1 < W && offs[r + 1] <= id) r++;
+    sr->best_rank = r;
+    sr->best_slot = e.x;
+  }
+  return B2M_OK;
+}
+
 // CC part of the front: fills fo->fill / fo->keep and the raw bright bbox in d_sc->lo/hi.
-int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc, b2m_front_out *fo) {
-  cc_geom cg = {g.nx, g.ny, g.nz, g.w, g.nwords};
+// g = geometry of the EXT planes of this rank; bit rows are EXT buffers.
+int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc,
+               b2m_front_out *fo) {
+  const size_t pw = (size_t)g.ny * g.w;                       // words per plane
+  const long long own_words = (long long)pw * sl.nzl;
+  cc_geom cg = {g.nx, g.ny, sl.nzl, g.w, own_words, sl.z0 == 0, sl.z0 + sl.nzl == sl.gnz};
   size_t wbytes = (size_t)g.nwords * 4;
-  unsigned blocks = b2m_cdiv(g.nwords, 256);
+  unsigned blocks = b2m_cdiv(own_words, 256);
   const bool cc = o->only_largest || o->fill_bubbles;
+  const bool slabs = sl.world > 1;
   B2M_TRY(b2m_reserve(ctx, BUF_FG, wbytes));
   uint32_t *fg = b2m_ptr<uint32_t>(ctx, BUF_FG);
   uint32_t *bg = nullptr;
@@ -546,25 +886,42 @@ int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *
     B2M_TRY(b2m_reserve(ctx, BUF_BG, wbytes));
     bg = b2m_ptr<uint32_t>(ctx, BUF_BG);
   }
-  B2M_TRY(b2m_threshold_run(ctx, fo->S, g, fo->iso, fg, bg));
+  B2M_TRY(b2m_threshold_run(ctx, fo->S, g, fo->iso, fg, bg));  // all EXT planes: the halo bits equal the neighbour's
   fo->fill = nullptr;
   fo->keep = nullptr;
   const uint32_t *bright = fg;
   uint2 *nodes = nullptr;
+  const size_t own_off = (size_t)sl.hl * pw;                   // first own word in an EXT bit buffer
   if (cc) {
-    if ((unsigned long long)g.nwords * 16ull > 0xffffffffull) {
-      b2m_set_error("volume too large for 32-bit run slots (%lld words)", g.nwords);
+    if ((unsigned long long)own_words * 16ull > 0xffffffffull || (unsigned long long)own_words * 32ull > 0x7fffffffull) {
+      b2m_set_error("slab too large for 32-bit run slots / 31-bit component sizes (%lld words)", own_words);
       return B2M_EARG;
     }
-    B2M_TRY(b2m_reserve(ctx, BUF_NODES, (size_t)g.nwords * 16 * sizeof(uint2)));
+    B2M_TRY(b2m_reserve(ctx, BUF_NODES, (size_t)own_words * 16 * sizeof(uint2)));
     nodes = b2m_ptr<uint2>(ctx, BUF_NODES);
   }
+  // one halo plane of an EXT bit buffer from each neighbour (own boundary planes go the other way)
+  auto halo_bits = [&](uint32_t *ext) -> int {
+    if (!slabs) return B2M_OK;
+    return b2m_comm_exchange(ctx, comm, ext + own_off + (size_t)(sl.nzl - 1) * pw, sl.hh ? pw * 4 : 0, ext, sl.hl ? pw * 4 : 0,
+                             ext + own_off, sl.hl ? pw * 4 : 0, ext + own_off + (size_t)sl.nzl * pw, sl.hh ? pw * 4 : 0);
+  };
   if (o->fill_bubbles) {
     B2M_TRY(b2m_reserve(ctx, BUF_FILL, wbytes));
     uint32_t *fill = b2m_ptr<uint32_t>(ctx, BUF_FILL);
-    B2M_TRY(cc_label(ctx, bg, cg, nodes, 6));
-    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, nullptr, &d_sc->nroots_bg));
-    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bg, g.nwords, nodes, 1, nullptr, &d_sc->nroots_bg, fg, fill));
+    B2M_TRY(cc_label(ctx, bg + own_off, cg, nodes, 6));
+    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bg + own_off, own_words, nodes, nullptr, &d_sc->nroots_bg));
+    long long nroots_ovr = -1;
+    if (slabs) {
+      seam_result sr;
+      B2M_TRY(cc_seams(ctx, comm, sl, bg + own_off, bg, cg, nodes, 6, d_sc, &sr));
+      unsigned long long tot = 0;
+      for (int r = 0; r < sl.world; r++) tot += b2m_sc(ctx, comm, r)->nroots_bg;
+      nroots_ovr = (long long)(tot - (sr.M - sr.K));
+      if (sr.m) KT_LAUNCH(ctx, "seam_apply", k_seam_apply<<<b2m_cdiv(sr.m, 256), 256, 0, ctx->stream>>>(sr.m, sr.off, sr.U, sr.par, sr.gflag, nodes, 1, -1));
+    }
+    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bg + own_off, own_words, nodes, 1, nullptr, &d_sc->nroots_bg, fg + own_off, fill + own_off, -2, nroots_ovr));
+    B2M_TRY(halo_bits(fill));
     fo->fill = fill;
     bright = fill;
   }
@@ -574,14 +931,45 @@ int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *
     B2M_TRY(b2m_reserve(ctx, BUF_KEEP, wbytes));
     largest = b2m_ptr<uint32_t>(ctx, BUF_LARGEST);
     keep = b2m_ptr<uint32_t>(ctx, BUF_KEEP);
-    B2M_TRY(cc_label(ctx, bright, cg, nodes, 18));
-    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, &d_sc->best_fg, &d_sc->nroots_fg));
-    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright, g.nwords, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest));
+    B2M_TRY(cc_label(ctx, bright + own_off, cg, nodes, 18));
+    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bright + own_off, own_words, nodes, &d_sc->best_fg, &d_sc->nroots_fg));
+    long long sel = -2;
+    if (slabs) {
+      seam_result sr;
+      B2M_TRY(cc_seams(ctx, comm, sl, bright + own_off, bright, cg, nodes, 18, d_sc, &sr));
+      // global winner: most voxels, ties to the earliest first voxel = lowest (rank, slot) (src/bwlabel.c:462-466)
+      unsigned long long bsize = 0; int brank = -1; unsigned bslot = 0;
+      for (int r = 0; r < sl.world; r++) {
+        const unsigned long long k = b2m_sc(ctx, comm, r)->best_fg;
+        if (!k) continue;
+        const unsigned long long sz = k >> 32;
+        const unsigned slot = 0xffffffffu - (unsigned)(k & 0xffffffffull);
+        if (sz > bsize) { bsize = sz; brank = r; bslot = slot; }
+      }
+      long long gstar = -1;
+      if (sr.best) {
+        const unsigned long long sz = sr.best >> 30;
+        if (sz > bsize || (sz == bsize && (sr.best_rank < brank || (sr.best_rank == brank && sr.best_slot <= bslot)))) {
+          gstar = (long long)(0x3fffffffu - (unsigned)(sr.best & 0x3fffffffull));
+          brank = -1;
+        }
+      }
+      sel = (brank == sl.rank) ? (long long)bslot : -1;
+      if (gstar >= 0 && sr.m)
+        KT_LAUNCH(ctx, "seam_apply", k_seam_apply<<<b2m_cdiv(sr.m, 256), 256, 0, ctx->stream>>>(sr.m, sr.off, sr.U, sr.par, sr.gflag, nodes, 0, gstar));
+    }
+    KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright + own_off, own_words, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest + own_off, sel, -1));
+    B2M_TRY(halo_bits(largest));
     fo->keep = keep;
   }
   {
-    dim3 dgrid(b2m_cdiv((size_t)g.ny * g.w, 256), b2m_cdiv(g.nz, DIL_ZC));
-    KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<dgrid, 256, 0, ctx->stream>>>(largest, bright, cg, keep, d_sc->lo));
+    // global-z indexing: EXT buffers shifted down by ez0 planes
+    const long long shift = (long long)sl.ez0 * (long long)pw;
+    cc_geom dg = {g.nx, g.ny, sl.gnz, g.w, 0, 1, 1};
+    dim3 dgrid(b2m_cdiv((size_t)g.ny * g.w, 256), b2m_cdiv(sl.nzl, DIL_ZC));
+    KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<dgrid, 256, 0, ctx->stream>>>(largest ? largest - shift : nullptr, bright - shift, dg, sl.z0, sl.z0 + sl.nzl,
+                                                                              keep ? keep - shift : nullptr, d_sc->lo));
+    if (keep) B2M_TRY(halo_bits(keep));
   }
   CU_TRY(cudaGetLastError());
   return B2M_OK;

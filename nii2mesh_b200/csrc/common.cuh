@@ -61,6 +61,14 @@ enum {
   BUF_TMP0,
   BUF_TMP1,
   BUF_INPUT,       // device copy of a host volume (b2m_meshify_host)
+  BUF_WELD,        // weld: all the small per-item arrays and block tables (carved)
+  BUF_ITEMS_ALL,   // slabs: weld items of all ranks
+  BUF_HALO_LO,     // slabs: raw planes received from the rank below (smooth halo)
+  BUF_HALO_HI,     // slabs: raw planes received from the rank above
+  BUF_HALO_V,      // slabs: the next rank's first-plane vertices (triangle pass)
+  BUF_SEAM0,       // slabs: CC seam lists (roots, dense ids, pairs, tables) carved per use
+  BUF_SEAM1,
+  BUF_SEAM2,
   BUF_COUNT
 };
 
@@ -69,24 +77,61 @@ struct b2m_buf {
   size_t cap;
 };
 
-// device-side scalars of one meshify call (one 256-byte block, zeroed per call)
+// device-side scalars of one meshify call (one 256-byte block, zeroed per call).  In slab mode the
+// blocks of all ranks are all-gathered at every host decision point (b2m_sync_scalars).
 struct b2m_scalars {
   unsigned int vmin_enc, vmax_enc;       // order-preserving encodings of f32 min/max
   unsigned int cmin_enc;                 // min of the composed volume (lazy)
-  int lo[3], hi[3];                      // bright bbox (raw, before the +-1/+2 widening)
-  unsigned long long best_fg;            // (size << 32) | ~rootslot  of the largest fg cluster
-  unsigned int nroots_fg, nroots_bg;     // number of components
+  int lo[3], hi[3];                      // bright bbox (raw, before the +-1/+2 widening), global coordinates
+  unsigned long long best_fg;            // (size << 32) | ~rootslot  of the largest fg cluster (of this rank)
+  unsigned int nroots_fg, nroots_bg;     // number of components (of this rank)
   unsigned int n_active;                 // MC active records appended
-  unsigned int n_cand;                   // weld candidates appended
-  unsigned int n_removed;                // vertices merged away
+  unsigned int n_cand;                   // weld items appended
+  unsigned int n_first;                  // slabs: edge vertices owned by the first own sub-volume plane
   unsigned int tot_v, tot_t, tot_c;      // MC totals (edge vertices, triangles, centroid vertices)
   unsigned int n_tri_kept;               // triangles surviving the degenerate test
-  unsigned int overflow;                 // any capacity overflow flag
-  unsigned int n_clusters;               // weld: clusters formed among the candidates
+  unsigned int overflow;                 // capacity overflow / consistency flags
+  unsigned int seam_n;                   // slabs: seam list length (roots, then unique roots, then pairs)
+  unsigned int seam_roots;               // slabs: components of the replicated seam union-find
   unsigned long long first_cube;         // min (row << 16 | x) over active cubes (classic pts[0])
   double pts0[3];                        // classic: first soup vertex (the weld's key origin)
-  unsigned int pad[8];
+  double v0[3];                          // slabs: this rank's first vertex (Lewiner key origin = global vertex 0)
+  unsigned long long best_seam;          // slabs: (size << 30) | (2^30-1 - seam id) of the largest seam component
+  unsigned int pad[24];
 };
+static_assert(sizeof(b2m_scalars) == 256, "b2m_scalars is exchanged as one 256-byte block");
+
+// one weld item: a vertex (Lewiner) or a soup copy (classic) close enough to a grid corner to merge
+struct b2m_item {
+  double pos[3];
+  uint32_t id;   // original index in the reference's vertex array (vertex id / soup index 3*t+c)
+  uint32_t vid;  // edge-keyed vertex id it belongs to
+};
+
+// ---------------------------------------------------------------------------------------------
+// z-slab of a volume owned by one rank.  EXT buffers (S, bit rows) hold the own planes plus one halo
+// plane per existing neighbour: ext plane e <-> global plane e + ez0.
+struct b2m_slab {
+  int rank, world;
+  int gnz;       // global NZ
+  int z0, nzl;   // own planes: global [z0, z0 + nzl)
+  int hl, hh;    // halo planes below / above (0 or 1)
+  int ez0, nze;  // ext origin (z0 - hl) and ext plane count (hl + nzl + hh)
+};
+struct b2m_comm;
+int b2m_comm_rank(const b2m_comm *c);
+int b2m_comm_world(const b2m_comm *c);
+void b2m_comm_abort(b2m_comm *c);
+// all-gather the scalar blocks of all ranks (device -> pinned host) and synchronise the stream
+int b2m_sync_scalars(b2m_ctx *ctx, b2m_comm *c);
+b2m_scalars *b2m_sc(b2m_ctx *ctx, b2m_comm *c, int rank);  // host copy of rank's block after b2m_sync_scalars
+// neighbour exchange along z (byte counts; 0 = nothing in that direction; ignored at the ends)
+int b2m_comm_exchange(b2m_ctx *ctx, b2m_comm *c, const void *d_send_up, size_t send_up_bytes, void *d_recv_lo,
+                      size_t recv_lo_bytes, const void *d_send_dn, size_t send_dn_bytes, void *d_recv_hi,
+                      size_t recv_hi_bytes);
+// d_recv = concatenation over ranks of their d_send (bytes[r] each); every rank passes the same bytes[]
+int b2m_comm_allgatherv(b2m_ctx *ctx, b2m_comm *c, const void *d_send, void *d_recv, const size_t *bytes);
+int b2m_comm_gather_items(b2m_ctx *ctx, b2m_comm *c, unsigned n_local, b2m_item **items, unsigned *n);
 
 // per-kernel device timing (opt-in, b2m_set_profile): one CUDA-event pair per launch on ctx->stream
 #define B2M_KT_MAX 256
@@ -97,6 +142,10 @@ struct b2m_ktimer {
 
 struct b2m_ctx {
   int device;
+  b2m_scalars *h_all;      // pinned: scalar blocks of all ranks (slabs), h_all_cap entries
+  b2m_scalars *d_all;
+  int h_all_cap;
+  unsigned slab_t_off;     // slabs: global index of this rank's first surviving triangle (last call)
   cudaStream_t stream;
   b2m_buf buf[BUF_COUNT];
   cudaEvent_t ev[2 * B2M_NSTAGE + 2];
@@ -164,7 +213,7 @@ __host__ __device__ static inline float f32_dec(unsigned int e) {
 // ---------------------------------------------------------------------------------------------
 // volume geometry shared by the kernels
 struct b2m_geom {
-  int nx, ny, nz;      // volume dims
+  int nx, ny, nz;      // volume dims (slabs: the EXT planes of this rank)
   int w;               // 32-bit words per bit row = ceil(nx/32)
   long long nxy;       // nx*ny
   long long n;         // voxels
@@ -186,6 +235,8 @@ static inline b2m_geom b2m_make_geom(const int64_t dims[3]) {
 // composed value of one voxel = what the reference's mutated img holds when marching cubes runs
 // (/root/reference/src/meshify.c:332-365): bubble fill to >= iso, non-kept voxels to mn, faces
 // darkened to <= edge_max.  Never materialised on the hot path: S plus two bit rows.
+// Slabs: S / fill / keep are the EXT buffers pre-offset by -ez0 planes, so kernels index them with
+// GLOBAL z (only planes the rank holds are ever touched); nz is the global NZ.
 struct compose_params {
   const float *S;
   const uint32_t *fill;
@@ -206,33 +257,58 @@ __device__ __forceinline__ float composed_value(const compose_params &c, int x, 
 }
 
 // stages implemented across the .cu files ------------------------------------------------------
-int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom &g, b2m_scalars *d_sc);
-int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, b2m_scalars *d_sc);
+// raw input of the smooth as seen by one rank: own planes plus the halo planes received from the neighbours
+struct smooth_src {
+  const float *lo, *main, *hi;
+  int n_lo, n_main, n_hi;  // planes in each piece; raw plane q = global z - rz0
+  int rz0;                 // global z of raw plane 0
+  int gnz;                 // global NZ
+  int oz0, onz;            // output: global planes [oz0, oz0+onz) -> d_out plane (z - oz0)
+};
+int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc);
+int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, size_t n, b2m_scalars *d_sc);
 int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg);
 
 struct b2m_front_out {
-  const float *S;          // smoothed (or original) volume
-  const uint32_t *fill;    // nullptr or fg|bubbles bit rows
-  const uint32_t *keep;    // nullptr or largest|dilated bit rows
+  const float *S;          // smoothed (or original) volume, EXT layout
+  const uint32_t *fill;    // nullptr or fg|bubbles bit rows, EXT layout
+  const uint32_t *keep;    // nullptr or largest|dilated bit rows, EXT layout
   float iso, vmin, vmax, edge_max;
-  int lo[3], hi[3];        // widened bbox as handed to marching cubes
+  int lo[3], hi[3];        // widened bbox as handed to marching cubes (global)
   int iso_reset;
 };
-int b2m_cc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc, b2m_front_out *fo);
-int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m_opts *o, b2m_front_out *fo,
-                  b2m_result *res);
+int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc,
+               b2m_front_out *fo);
+int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float *d_img, const b2m_geom &g, const b2m_opts *o,
+                  b2m_front_out *fo, b2m_result *res);
 int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out *fo, float *d_composed,
                             uint8_t *d_mask, b2m_scalars *d_sc, int want_min);
 
+// marching-cubes output of one rank, before the weld.  Vertex ids are GLOBAL (reference emission order
+// over the whole volume): own edge vertices e_off .. e_off+nv_edge, own centroid vertices
+// NVE+c_off .. NVE+c_off+nv_c; verts[] holds the own blocks back to back.
 struct b2m_mesh_dev {
-  double *verts;  // BUF_VERTS
-  int *tris;      // BUF_TRIS
-  unsigned int nv, nt;   // pre-weld counts
-  unsigned int nv_edge;  // edge vertices (centroid vertices follow)
-  unsigned int ncand;    // weld candidates in BUF_CAND
+  double *verts;  // BUF_VERTS: [edge block | centroid block]
+  int *tris;      // BUF_TRIS (global vertex ids)
+  unsigned int nv_edge, nv_c, nt;   // own counts
+  unsigned int NVE, NVC, NT;        // global counts
+  unsigned int e_off, c_off, t_off; // global offsets of the own blocks
+  unsigned int nitems;              // own weld items in BUF_CAND
+  const double *halo_verts;         // next rank's first-plane vertices: ids halo0 .. halo1
+  unsigned int halo0, halo1;
+  const double *d_p0;               // device pointer to the weld's key origin (the reference's pts[0])
+  int classic_soup;                 // items are soup copies (classic back-end)
 };
-int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_front_out *fo, b2m_mesh_dev *mesh);
-int b2m_weld_run(b2m_ctx *ctx, b2m_mesh_dev *mesh, int all_candidates, int backend, b2m_result *res);
+struct b2m_weld_out {
+  const double *verts;  // own welded vertices: [edge | centroid | extras]
+  const int *tris;      // own surviving triangles, welded global vertex indices
+  unsigned int nv_local, nve_local, nvc_local, nx_local, nt_local;
+  unsigned int v_edge_off, v_c_off;  // global welded index of the first own edge / centroid vertex
+  unsigned int nv_global, n_dead, n_extra;
+};
+int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o,
+               const b2m_front_out *fo, b2m_mesh_dev *mesh);
+int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items, b2m_weld_out *wo);
 
 // generic primitives (scan.cu)
 int b2m_exclusive_scan_u32(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);

@@ -66,6 +66,7 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
   for (int i = 0; i < 3; i++)
     if (c->stage[i]) { cudaFreeHost(c->stage[i]); cudaEventDestroy(c->stage_ev[i]); }
   cudaFreeHost(c->h_scalars);
+  if (c->h_all) { cudaFreeHost(c->h_all); cudaFree(c->d_all); }
   cudaStreamDestroy(c->stream);
   free(c);
 }

@@ -32,6 +32,8 @@ struct mc_params {
   compose_params c;
   int lo0, lo1, lo2;
   int sx, sy, sz;   // sub-volume size in voxels
+  int zs0, zn;      // slabs: sub-volume planes [zs0, zs0+zn) are owned by this rank (segment arrays hold zn+1 planes:
+                    // the last one is the next rank's first plane, received after the scan)
   int segs;         // 32-voxel segments per sub-volume row
   float pad;        // Lewiner: value of sub-volume voxels that fall outside the volume (already - iso)
   int classic;      // backend == CLASSIC
@@ -326,8 +328,8 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
   const int seg = blockIdx.x;
   const int ybase = (blockIdx.y * MCC_WARPS + wrp) * MCC_ROWS;
   if (ybase >= p.sy) return;  // whole warp; no block-level barriers in this kernel
-  const int z0 = blockIdx.z * MCC_ZC;
-  const int z1 = min(z0 + MCC_ZC, p.sz);
+  const int z0 = p.zs0 + blockIdx.z * MCC_ZC;
+  const int z1 = min(z0 + MCC_ZC, p.zs0 + p.zn);
   const int x = seg * 32 + (int)lane;
   const bool vx = x < p.sx, vx1 = x + 1 < p.sx;
   const int nyv = min(MCC_ROWS + 1, p.sy - ybase);             // valid rows among the 9
@@ -352,11 +354,11 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
     const unsigned andm = a & (a >> 1) & b & (b >> 1) & c & (c >> 1) & d & (d >> 1);
     const unsigned trim = (vx1 && vz1) ? ((orm & ~andm) & vy1m) : 0u;
     const unsigned rows_active = __reduce_or_sync(0xffffffffu, exm | eym | ezm | trim);
-    uint4 *segrow = p.segbits + ((size_t)z * p.sy + ybase) * p.segs + seg;  // + r * p.segs per row
+    uint4 *segrow = p.segbits + ((size_t)(z - p.zs0) * p.sy + ybase) * p.segs + seg;  // + r * p.segs per row
     if (lane < MCC_ROWS && ((rowsv & ~rows_active) >> lane) & 1u) segrow[(size_t)lane * p.segs] = make_uint4(0u, 0u, 0u, 0u);
     for (unsigned ra = rows_active; ra; ra &= ra - 1) {
       const int r = __ffs(ra) - 1;
-      const size_t row = (size_t)z * p.sy + ybase + r;
+      const size_t row = (size_t)(z - p.zs0) * p.sy + ybase + r;  // local row (segment arrays of this rank)
       const bool ex = (exm >> r) & 1u, ey = (eym >> r) & 1u, ez = (ezm >> r) & 1u, tri = (trim >> r) & 1u;
       int ntri = 0, hasc = 0, off = 0, lut = 0;
       if (tri) {
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
       const int excl = incl - pk;
       if (lane == 0) segrow[(size_t)r * p.segs] = make_uint4(xb, yb, zb, (uint32_t)tot);
       if (p.classic && ntri > 0) {
-        unsigned long long key = ((unsigned long long)row << 16) | (unsigned long long)x;
+        unsigned long long key = ((unsigned long long)((size_t)z * p.sy + ybase + r) << 16) | (unsigned long long)x;
         first = key < first ? key : first;
       }
       const bool act = nv > 0 || ntri > 0;
@@ -398,7 +400,10 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
       if (cnt + n > MCC_BUF) {  // flush the warp-private buffer
         __syncwarp();
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&p.sc->n_active, cnt);
+        if (lane == 0) {
+          base = atomicAdd(&p.sc->n_active, cnt);
+          if (base + cnt > p.active_cap) atomicOr(&p.sc->overflow, 1u);
+        }
         base = __shfl_sync(0xffffffffu, base, 0);
         for (unsigned i = lane; i < cnt; i += 32)
           if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
@@ -423,7 +428,10 @@ __global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_con
   __syncwarp();
   if (cnt) {
     unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&p.sc->n_active, cnt);
+    if (lane == 0) {
+      base = atomicAdd(&p.sc->n_active, cnt);
+      if (base + cnt > p.active_cap) atomicOr(&p.sc->overflow, 1u);
+    }
     base = __shfl_sync(0xffffffffu, base, 0);
     for (unsigned i = lane; i < cnt; i += 32)
       if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
@@ -506,7 +514,8 @@ __global__ void __launch_bounds__(1024) k_scan3_single(uint32_t *part, size_t nb
 }
 
 __global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ seg, size_t n, const uint32_t *__restrict__ part,
-                                                            size_t nblk, uint32_t *__restrict__ segt, uint32_t *__restrict__ segc) {
+                                                            size_t nblk, uint32_t *__restrict__ segt, uint32_t *__restrict__ segc,
+                                                            uint32_t voff) {
   __shared__ u3 sm[33];
   size_t base = (size_t)blockIdx.x * S3_TILE + (size_t)threadIdx.x * S3_ITEMS;
   u3 v[S3_ITEMS];
@@ -519,7 +528,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ 
   }
   u3 tot;
   u3 ex = block_excl_scan3(s, &tot, sm);
-  ex = u3_add(ex, u3{part[blockIdx.x], part[nblk + blockIdx.x], part[2 * nblk + blockIdx.x]});
+  ex = u3_add(ex, u3{part[blockIdx.x] + voff, part[nblk + blockIdx.x], part[2 * nblk + blockIdx.x]});
 #pragma unroll
   for (int i = 0; i < S3_ITEMS; i++) {
     size_t idx = base + i;
@@ -528,26 +537,38 @@ __global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ 
   }
 }
 
-static int mc_scan3(b2m_ctx *ctx, mc_params &p, size_t nseg, b2m_scalars *d_sc) {
+// totals first (the vertex base of a rank is the sum of the lower ranks' totals), bases second
+static int mc_scan3_totals(b2m_ctx *ctx, mc_params &p, size_t nseg, b2m_scalars *d_sc) {
+  if (nseg == 0) { CU_TRY(cudaMemsetAsync(&d_sc->tot_v, 0, 12, ctx->stream)); return B2M_OK; }
   size_t nblk = (nseg + S3_TILE - 1) / S3_TILE;
   B2M_TRY(b2m_reserve(ctx, BUF_SCAN1, nblk * 3 * 4));
   uint32_t *part = b2m_ptr<uint32_t>(ctx, BUF_SCAN1);
   KT_LAUNCH(ctx, "scan3_reduce", k_scan3_reduce<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk));
   KT_LAUNCH(ctx, "scan3_single", k_scan3_single<<<1, 1024, 0, ctx->stream>>>(part, nblk, &d_sc->tot_v));
-  KT_LAUNCH(ctx, "scan3_apply", k_scan3_apply<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk, p.segt, p.segc));
+  CU_TRY(cudaGetLastError());
+  return B2M_OK;
+}
+static int mc_scan3_apply(b2m_ctx *ctx, mc_params &p, size_t nseg, uint32_t voff) {
+  if (nseg == 0) return B2M_OK;
+  size_t nblk = (nseg + S3_TILE - 1) / S3_TILE;
+  uint32_t *part = b2m_ptr<uint32_t>(ctx, BUF_SCAN1);
+  KT_LAUNCH(ctx, "scan3_apply", k_scan3_apply<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk, p.segt, p.segc, voff));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
 
 // ---- pass B: emit ------------------------------------------------------------------------------
 struct mc_emit_params {
-  double *verts;
-  int *tris;
-  uint32_t *cand;
-  unsigned int cand_cap;
+  double *verts;         // own vertices: [edge block | centroid block]
+  int *tris;             // own triangles (global vertex ids)
+  b2m_item *items;       // weld items (vertices / soup copies near a grid corner)
+  unsigned int item_cap;
   unsigned int n_active;
-  unsigned int nv_edge;  // total edge vertices (centroid vertices are numbered after them)
-  unsigned long long first_cube;  // classic: (row << 16 | x) of the first active cube
+  unsigned int e_off;    // global id of the first own edge vertex (segbits[].w already includes it)
+  unsigned int nv_edge_l;  // own edge vertices (the own centroid block starts there in verts[])
+  unsigned int c_base;   // global id of the first own centroid vertex = global edge-vertex total + lower ranks' centroids
+  unsigned int t_off;    // global index of the first own triangle
+  unsigned long long first_cube;  // classic: (global row << 16 | x) of the first active cube of the volume
 };
 
 // index of the edge vertex owned by sub-volume voxel (x,row) on `axis`
@@ -561,9 +582,16 @@ __device__ __forceinline__ uint32_t mc_vidx(const mc_params &p, size_t row, int 
   return n;
 }
 
-__device__ __forceinline__ void push_cand(const mc_params &p, const mc_emit_params &e, uint32_t vid) {
+__device__ __forceinline__ void push_item(const mc_params &p, const mc_emit_params &e, double x, double y, double z, uint32_t id,
+                                          uint32_t vid) {
   unsigned pos = atomicAdd(&p.sc->n_cand, 1u);
-  if (pos < e.cand_cap) e.cand[pos] = vid;
+  if (pos < e.item_cap) {
+    b2m_item it;
+    it.pos[0] = x; it.pos[1] = y; it.pos[2] = z; it.id = id; it.vid = vid;
+    e.items[pos] = it;
+  } else {
+    atomicOr(&p.sc->overflow, 16u);
+  }
 }
 
 // Lewiner edge vertex: u = c0/(c0-c1) (0.5 when the denominator is zero), local f32 coordinate
@@ -584,7 +612,8 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
   const bool ex = (r.y >> 16) & 1, ey = (r.y >> 17) & 1, ez = (r.y >> 18) & 1;
   const int ntri = (r.y >> 19) & 15, hasc = (r.y >> 23) & 1, pc = (r.y >> 24) & 31;
   const int pv = r.z & 127, pt = (r.z >> 7) & 511, off = (int)(r.z >> 16);
-  const int z = (int)(row / p.sy), y = (int)(row - (size_t)z * p.sy);
+  const int zl = (int)(row / p.sy), y = (int)(row - (size_t)zl * p.sy);
+  const int z = zl + p.zs0;  // sub-volume plane (global); row / sidx index this rank's segment arrays
   const size_t sidx = row * p.segs + (x >> 5);
   // corner values (only the ones that exist inside the sub-volume)
   const bool vx1 = x + 1 < p.sx, vy1 = y + 1 < p.sy, vz1 = z + 1 < p.sz;
@@ -609,23 +638,23 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
       const float fx = (float)x, fy = (float)y, fz = (float)z;
       if (ex) {
         float px = __fadd_rn(__fadd_rn(fx, lew_u(c[0], c[1])), flo0);
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)px; o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(px, 2e-5f)) push_cand(p, e, vid);
+        if (near_int(px, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
         vid++;
       }
       if (ey) {
         float py = __fadd_rn(__fadd_rn(fy, lew_u(c[0], c[3])), flo1);
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)py; o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(py, 2e-5f)) push_cand(p, e, vid);
+        if (near_int(py, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
         vid++;
       }
       if (ez) {
         float pz = __fadd_rn(__fadd_rn(fz, lew_u(c[0], c[4])), flo2);
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)pz;
-        if (near_int(pz, 2e-5f)) push_cand(p, e, vid);
+        if (near_int(pz, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
       }
     } else {
       // classic: FP64, mu = (iso - v1)/(v2 - v1), p = p1 + mu*(p2-p1) (src/oldcubes.c:35-38) with the
@@ -640,9 +669,8 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
         const bool plus = y <= p.sy - 2;
         double px = plus ? __dadd_rn(gx, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)))
                          : __dadd_rn(gx + 1.0, __dmul_rn(__ddiv_rn(__dsub_rn(iso, v1), __dsub_rn(v0, v1)), -1.0));
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = px; o[1] = gy; o[2] = gz;
-        if (near_int_d(px, 2e-5)) push_cand(p, e, vid);
         vid++;
       }
       if (ey) {
@@ -651,17 +679,15 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
         const bool minus = x <= p.sx - 2;
         double py = minus ? __dadd_rn(gy + 1.0, __dmul_rn(__ddiv_rn(__dsub_rn(iso, v1), __dsub_rn(v0, v1)), -1.0))
                           : __dadd_rn(gy, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = gx; o[1] = py; o[2] = gz;
-        if (near_int_d(py, 2e-5)) push_cand(p, e, vid);
         vid++;
       }
       if (ez) {
         const double v1 = (double)c[4];
         double pz = __dadd_rn(gz, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
-        double *o = e.verts + 3 * (size_t)vid;
+        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = gx; o[1] = gy; o[2] = pz;
-        if (near_int_d(pz, 2e-5)) push_cand(p, e, vid);
       }
     }
   }
@@ -706,13 +732,14 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
 #undef ACC
     if (u > 0.f) { sx = __fdiv_rn(sx, u); sy = __fdiv_rn(sy, u); sz = __fdiv_rn(sz, u); }
     const float ox = __fadd_rn(sx, flo0), oy = __fadd_rn(sy, flo1), oz = __fadd_rn(sz, flo2);
-    const uint32_t vid = e.nv_edge + __ldg(p.segc + sidx) + (uint32_t)pc;
-    double *o = e.verts + 3 * (size_t)vid;
+    const uint32_t cl = __ldg(p.segc + sidx) + (uint32_t)pc;  // index in the own centroid block
+    const uint32_t vid = e.c_base + cl;
+    double *o = e.verts + 3 * (size_t)(e.nv_edge_l + cl);
     o[0] = (double)ox; o[1] = (double)oy; o[2] = (double)oz;
-    if (near_int(ox, 1e-4f) || near_int(oy, 1e-4f) || near_int(oz, 1e-4f)) push_cand(p, e, vid);
+    if (near_int(ox, 1e-4f) || near_int(oy, 1e-4f) || near_int(oz, 1e-4f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
     ev[12] = vid;
   }
-  if (p.classic && (((unsigned long long)row << 16) | (unsigned long long)x) == e.first_cube) {
+  if (p.classic && (((unsigned long long)((size_t)z * p.sy + y) << 16) | (unsigned long long)x) == e.first_cube) {
     // pts[0] of the reference's soup: first table edge of the first active cube, interpolated in
     // THAT cube's direction (src/oldcubes.c:428-451, :22-40)
     const int a0 = p.tab[off];
@@ -726,12 +753,44 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
     p.sc->pts0[2] = __dadd_rn(az, __dmul_rn(mu, bz - az));
   }
   // ---- triangles ----
-  int *t = e.tris + 3 * ((size_t)__ldg(p.segt + sidx) + (size_t)pt);
+  const size_t tl0 = (size_t)__ldg(p.segt + sidx) + (size_t)pt;  // index in the own triangle array
+  int *t = e.tris + 3 * tl0;
   const signed char *tl = p.tab + off;
   for (int k = 0; k < ntri; k++) {
     int a = tl[3 * k], b = tl[3 * k + 1], cc = tl[3 * k + 2];
     if (p.classic) { t[3 * k] = (int)ev[a]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[cc]; }
     else { t[3 * k] = (int)ev[cc]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[a]; }  // reversed (:1134-1136)
+  }
+  if (p.classic) {
+    // weld items of the classic back-end are SOUP COPIES (the reference welds the soup, so equal keys are
+    // ordered by soup index and an edge vertex can be split between clusters, src/meshify.c:60-79):
+    // every triangle corner whose position, interpolated in THIS cube's direction (src/oldcubes.c:22-40,
+    // :428-451), lies within 2e-5 of a grid corner.  f32 pre-filter per edge, exact FP64 only for the few.
+    const double iso = (double)p.c.iso;
+    unsigned nearm = 0;
+#pragma unroll
+    for (int a = 0; a < 12; a++) {
+      const float va = c[MC_EDGE_A[a]], vb = c[MC_EDGE_B[a]];
+      const float den = fabsf(vb - va) * 1e-4f;
+      if (fabsf(p.c.iso - va) <= den || fabsf(p.c.iso - vb) <= den) nearm |= 1u << a;
+    }
+    if (nearm) {
+      for (int k = 0; k < ntri; k++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int a = tl[3 * k + q];
+          if (!((nearm >> a) & 1u)) continue;
+          const int ca = MC_EDGE_A[a], cb = MC_EDGE_B[a];
+          const double mu = __ddiv_rn(__dsub_rn(iso, (double)c[ca]), __dsub_rn((double)c[cb], (double)c[ca]));
+          const double ax = (double)(p.lo0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + z + (ca >> 2));
+          const double bx = (double)(p.lo0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + z + (cb >> 2));
+          const double px = __dadd_rn(ax, __dmul_rn(mu, bx - ax)), py = __dadd_rn(ay, __dmul_rn(mu, by - ay)), pz = __dadd_rn(az, __dmul_rn(mu, bz - az));
+          const double free_axis = a >= 8 ? pz : ((a & 1) ? py : px);
+          if (near_int_d(free_axis, 2e-5))
+            push_item(p, e, px, py, pz, 3u * (uint32_t)(e.t_off + tl0 + k) + (uint32_t)q, ev[a]);
+        }
+      }
+    }
   }
 }
 
@@ -773,13 +832,22 @@ static int upload_tables(b2m_ctx *ctx) {
   return B2M_OK;
 }
 
-int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_front_out *fo, b2m_mesh_dev *mesh) {
+// Slabs: sub-volume planes are owned by the rank that owns the matching volume plane (the last rank also owns
+// the Lewiner pad plane); vertex ids are global: rank r's edge vertices follow those of ranks < r, all centroid
+// vertices follow all edge vertices (the reference's emission order over the whole volume).
+int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o,
+               const b2m_front_out *fo, b2m_mesh_dev *mesh) {
   B2M_TRY(upload_tables(ctx));
   b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  const int W = sl.world;
   mc_params p;
   memset(&p, 0, sizeof(p));
-  p.c.S = fo->S; p.c.fill = fo->fill; p.c.keep = fo->keep;
-  p.c.nx = g.nx; p.c.ny = g.ny; p.c.nz = g.nz; p.c.w = g.w;
+  // EXT buffers shifted so that kernels index them with global z
+  const long long vshift = (long long)sl.ez0 * g.nxy, wshift = (long long)sl.ez0 * g.ny * g.w;
+  p.c.S = fo->S - vshift;
+  p.c.fill = fo->fill ? fo->fill - wshift : nullptr;
+  p.c.keep = fo->keep ? fo->keep - wshift : nullptr;
+  p.c.nx = g.nx; p.c.ny = g.ny; p.c.nz = sl.gnz; p.c.w = g.w;
   p.c.iso = fo->iso; p.c.mn = fo->vmin; p.c.edge_max = fo->edge_max;
   p.classic = o->backend == B2M_BACKEND_CLASSIC;
   p.original_mc = o->original_mc != 0;
@@ -789,8 +857,16 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
   } else {          // hi-lo+1 voxels: one more than the volume can supply when hi == dim (src/MarchingCubes.c:1088-1090)
     p.sx = fo->hi[0] - fo->lo[0] + 1; p.sy = fo->hi[1] - fo->lo[1] + 1; p.sz = fo->hi[2] - fo->lo[2] + 1;
   }
-  mesh->nv = mesh->nt = mesh->nv_edge = mesh->ncand = 0;
+  memset(mesh, 0, sizeof(*mesh));
+  mesh->classic_soup = p.classic;
   if (p.sx < 2 || p.sy < 2 || p.sz < 2) return B2M_FAIL;
+  {  // owned sub-volume planes
+    int a = sl.z0 - p.lo2, b = sl.z0 + sl.nzl - p.lo2;
+    if (a < 0) a = 0;
+    if (sl.z0 + sl.nzl == sl.gnz || b > p.sz) b = p.sz;
+    p.zs0 = a < p.sz ? a : p.sz;
+    p.zn = b > p.zs0 ? b - p.zs0 : 0;
+  }
   p.segs = (p.sx + 31) / 32;
   p.tab = b2m_ptr<signed char>(ctx, BUF_TABLES);
   p.lutinfo = reinterpret_cast<const uint32_t *>(b2m_ptr<char>(ctx, BUF_TABLES) + MCT_INFO_OFF) +
@@ -802,8 +878,13 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
   // extra reduction pass over the volume.
   p.pad = fo->vmin - fo->iso;
   if (!p.classic) {
-    bool touched = fo->hi[0] == g.nx || fo->hi[1] == g.ny || fo->hi[2] == g.nz;
+    bool touched = fo->hi[0] == g.nx || fo->hi[1] == g.ny || fo->hi[2] == sl.gnz;
     if (touched && !(fo->edge_max < fo->iso)) {
+      if (W > 1) {
+        // the wrapped extra column / row of the reference would reach two planes ahead
+        b2m_set_error("slab mode needs darkened faces below the isolevel (edge_max %g >= iso %g)", fo->edge_max, fo->iso);
+        return B2M_EARG;
+      }
       ctx->h_scalars->cmin_enc = 0xffffffffu;
       CU_TRY(cudaMemcpyAsync(&d_sc->cmin_enc, &ctx->h_scalars->cmin_enc, 4, cudaMemcpyHostToDevice, ctx->stream));
       B2M_TRY(b2m_compose_materialize(ctx, g, fo, nullptr, nullptr, d_sc, 1));
@@ -811,77 +892,137 @@ int b2m_mc_run(b2m_ctx *ctx, const b2m_geom &g, const b2m_opts *o, const b2m_fro
       p.pad = f32_dec(ctx->h_scalars->cmin_enc) - fo->iso;
     }
   }
-  const size_t nrows = (size_t)p.sy * p.sz;
-  const size_t nseg = nrows * p.segs;
-  const size_t nvox = nrows * p.sx;
-  B2M_TRY(b2m_reserve(ctx, BUF_SEG, nseg * sizeof(uint4)));
-  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, nseg * 2 * sizeof(uint32_t)));
+  const size_t prow = (size_t)p.sy * p.segs;          // segments per sub-volume plane
+  const size_t nseg = prow * p.zn;                    // own segments
+  const size_t nseg_all = prow * (p.zn + 1);          // + the next rank's first plane
+  const size_t nvox = (size_t)p.sy * p.zn * p.sx;
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG, nseg_all * sizeof(uint4)));
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, (nseg + 1) * 2 * sizeof(uint32_t)));
   p.segbits = b2m_ptr<uint4>(ctx, BUF_SEG);
   p.segt = b2m_ptr<uint32_t>(ctx, BUF_SEG2);
   p.segc = p.segt + nseg;
   size_t cap = nvox / 8 + 65536;
   if (cap > nvox) cap = nvox;
+  if (cap < 1) cap = 1;
   unsigned n_active = 0;
+  dim3 grid(p.segs, b2m_cdiv(p.sy, MCC_ROWS * MCC_WARPS), b2m_cdiv(p.zn > 0 ? p.zn : 1, MCC_ZC));
+  // the retry decision must be the same on every rank (collectives follow): overflow anywhere -> all redo
   for (int attempt = 0; attempt < 2; attempt++) {
     B2M_TRY(b2m_reserve(ctx, BUF_ACTIVE, cap * sizeof(uint4)));
     p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    dim3 grid(p.segs, b2m_cdiv(p.sy, MCC_ROWS * MCC_WARPS), b2m_cdiv(p.sz, MCC_ZC));
-    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
+    if (p.zn > 0) KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
     CU_TRY(cudaGetLastError());
-    if (attempt == 0) {
-      B2M_TRY(mc_scan3(ctx, p, nseg, d_sc));
-    }
-    B2M_TRY(b2m_fetch_scalars(ctx));
+    B2M_TRY(mc_scan3_totals(ctx, p, nseg, d_sc));
+    B2M_TRY(b2m_sync_scalars(ctx, comm));
     n_active = ctx->h_scalars->n_active;
-    if (n_active <= cap) break;
+    bool any_over = false;  // every rank takes the same decision: collectives follow
+    for (int r = 0; r < W; r++) any_over |= (b2m_sc(ctx, comm, r)->overflow & 1u) != 0;
+    if (!any_over) break;
     if (attempt == 1) { b2m_set_error("mc: active list overflow"); return B2M_ECUDA; }
-    // rare: more active voxels than the first guess; redo the classification with an exact capacity.
-    // (segment counts were scanned in place, so they are recomputed and rescanned as well)
-    cap = n_active;
-    B2M_TRY(b2m_reserve(ctx, BUF_ACTIVE, cap * sizeof(uint4)));
-    p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
-    p.active_cap = (unsigned)cap;
-    CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
-    B2M_TRY(mc_scan3(ctx, p, nseg, d_sc));
-    B2M_TRY(b2m_fetch_scalars(ctx));
-    n_active = ctx->h_scalars->n_active;
-    break;
+    // rare: more active voxels than the first guess; redo the classification with an exact capacity
+    if (n_active > cap) cap = n_active;
+    CU_TRY(cudaMemsetAsync(&d_sc->overflow, 0, 4, ctx->stream));
+    CU_TRY(cudaMemsetAsync(&d_sc->first_cube, 0xff, 8, ctx->stream));
+  }
+  unsigned e_off = 0, c_off = 0, t_off = 0;
+  unsigned long long NVE = 0, NVC = 0, NT = 0;
+  for (int r = 0; r < W; r++) {
+    const b2m_scalars *sr = b2m_sc(ctx, comm, r);
+    if (r == sl.rank) { e_off = (unsigned)NVE; c_off = (unsigned)NVC; t_off = (unsigned)NT; }
+    NVE += sr->tot_v; NVC += sr->tot_c; NT += sr->tot_t;
   }
   const unsigned tot_v = ctx->h_scalars->tot_v, tot_t = ctx->h_scalars->tot_t, tot_c = ctx->h_scalars->tot_c;
-  mesh->nv_edge = tot_v;
-  mesh->nv = tot_v + tot_c;
-  mesh->nt = tot_t;
-  if ((unsigned long long)tot_v + tot_c > 0x7fffffffull || tot_t > 0x7fffffffu) {
+  if (NVE + NVC > 0x7fffffffull || NT > 0x7fffffffull || 3ull * NT > 0xffffffffull) {
     b2m_set_error("mesh exceeds the int counts of the meshify() API");
     return B2M_EARG;
   }
+  mesh->nv_edge = tot_v; mesh->nv_c = tot_c; mesh->nt = tot_t;
+  mesh->NVE = (unsigned)NVE; mesh->NVC = (unsigned)NVC; mesh->NT = (unsigned)NT;
+  mesh->e_off = e_off; mesh->c_off = c_off; mesh->t_off = t_off;
   // reference failure rule: < 3 vertices or < 1 triangle (src/MarchingCubes.c:1119, src/oldcubes.c:497)
-  if (p.classic ? (3ull * tot_t < 3) : (mesh->nv < 3 || tot_t < 1)) return B2M_FAIL;
-  B2M_TRY(b2m_reserve(ctx, BUF_VERTS, (size_t)mesh->nv * 24));
-  B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)mesh->nt * 12));
-  size_t ccap = (size_t)mesh->nv / 16 + 4096;
+  if (p.classic ? (3ull * NT < 3) : (NVE + NVC < 3 || NT < 1)) return B2M_FAIL;
+  B2M_TRY(mc_scan3_apply(ctx, p, nseg, e_off));
+  if (W > 1) {
+    // the first own plane of segment records goes down: the rank below needs the vertex numbering of the
+    // plane above its last cubes (Lewiner edge codes 4..7, src/MarchingCubes.c:813-825)
+    if (p.zn == 0) CU_TRY(cudaMemsetAsync(p.segbits, 0, prow * sizeof(uint4), ctx->stream));
+    B2M_TRY(b2m_comm_exchange(ctx, comm, nullptr, 0, nullptr, 0, p.segbits, sl.hl ? prow * sizeof(uint4) : 0,
+                              p.segbits + nseg, sl.hh ? prow * sizeof(uint4) : 0));
+    // n_first = global vertex base of the second own plane (0xffffffff: the first own plane holds every own
+    // vertex): the first-plane vertices are sent down after the emit pass
+    if (p.zn >= 2) CU_TRY(cudaMemcpyAsync(&d_sc->n_first, &p.segbits[prow].w, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    else CU_TRY(cudaMemsetAsync(&d_sc->n_first, 0xff, 4, ctx->stream));
+  }
+  B2M_TRY(b2m_reserve(ctx, BUF_VERTS, ((size_t)tot_v + tot_c) * 24));
+  B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)tot_t * 12));
+  size_t ccap = ((size_t)tot_v + tot_c) / (p.classic ? 4 : 16) + 4096;
   mc_emit_params e;
+  memset(&e, 0, sizeof(e));
+  unsigned long long first_cube = ~0ull;
+  for (int r = 0; r < W; r++) { const unsigned long long f = b2m_sc(ctx, comm, r)->first_cube; if (f < first_cube) first_cube = f; }
   for (int attempt = 0; attempt < 2; attempt++) {
-    B2M_TRY(b2m_reserve(ctx, BUF_CAND, ccap * 4));
+    B2M_TRY(b2m_reserve(ctx, BUF_CAND, ccap * sizeof(b2m_item)));
     e.verts = b2m_ptr<double>(ctx, BUF_VERTS);
     e.tris = b2m_ptr<int>(ctx, BUF_TRIS);
-    e.cand = b2m_ptr<uint32_t>(ctx, BUF_CAND);
-    e.cand_cap = (unsigned)ccap;
+    e.items = b2m_ptr<b2m_item>(ctx, BUF_CAND);
+    e.item_cap = (unsigned)ccap;
     e.n_active = n_active;
-    e.nv_edge = tot_v;
-    e.first_cube = ctx->h_scalars->first_cube;
+    e.e_off = e_off;
+    e.nv_edge_l = tot_v;
+    e.c_base = (unsigned)NVE + c_off;
+    e.t_off = t_off;
+    e.first_cube = first_cube;
     CU_TRY(cudaMemsetAsync(&d_sc->n_cand, 0, 4, ctx->stream));
-    KT_LAUNCH(ctx, "mc_emit", k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
+    if (n_active) KT_LAUNCH(ctx, "mc_emit", k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
     CU_TRY(cudaGetLastError());
-    B2M_TRY(b2m_fetch_scalars(ctx));
-    if (ctx->h_scalars->n_cand <= ccap) break;
-    ccap = ctx->h_scalars->n_cand;
+    if (W > 1 && !p.classic && tot_v + tot_c > 0)
+      CU_TRY(cudaMemcpyAsync(d_sc->v0, e.verts, 24, cudaMemcpyDeviceToDevice, ctx->stream));
+    B2M_TRY(b2m_sync_scalars(ctx, comm));
+    bool any_over = false;  // same decision on every rank
+    for (int r = 0; r < W; r++) any_over |= (b2m_sc(ctx, comm, r)->overflow & 16u) != 0;
+    if (!any_over) break;
+    if (attempt == 1) { b2m_set_error("mc: item list overflow"); return B2M_ECUDA; }
+    if (ctx->h_scalars->n_cand > ccap) ccap = ctx->h_scalars->n_cand;
+    CU_TRY(cudaMemsetAsync(&d_sc->overflow, 0, 4, ctx->stream));
   }
-  mesh->ncand = ctx->h_scalars->n_cand;
+  mesh->nitems = ctx->h_scalars->n_cand;
   mesh->verts = b2m_ptr<double>(ctx, BUF_VERTS);
   mesh->tris = b2m_ptr<int>(ctx, BUF_TRIS);
+  // key origin of the weld = the reference's pts[0]
+  if (W == 1) {
+    mesh->d_p0 = p.classic ? d_sc->pts0 : mesh->verts;
+  } else {
+    double p0[3] = {0, 0, 0};
+    if (p.classic) {
+      for (int r = 0; r < W; r++) {
+        const b2m_scalars *sr = b2m_sc(ctx, comm, r);
+        if (sr->first_cube == first_cube && first_cube != ~0ull) { memcpy(p0, sr->pts0, 24); break; }
+      }
+    } else {
+      for (int r = 0; r < W; r++) {
+        const b2m_scalars *sr = b2m_sc(ctx, comm, r);
+        if (sr->tot_v + sr->tot_c > 0) { memcpy(p0, sr->v0, 24); break; }
+      }
+    }
+    memcpy(ctx->h_scalars->pts0, p0, 24);
+    CU_TRY(cudaMemcpyAsync(d_sc->pts0, ctx->h_scalars->pts0, 24, cudaMemcpyHostToDevice, ctx->stream));
+    mesh->d_p0 = d_sc->pts0;
+    // the next rank's first-plane vertices: the last own cubes reference them
+    const unsigned my_first = ctx->h_scalars->n_first != 0xffffffffu ? ctx->h_scalars->n_first - e_off : tot_v;
+    unsigned up_first = 0, up_off = 0;
+    if (sl.hh) {
+      const b2m_scalars *su = b2m_sc(ctx, comm, sl.rank + 1);
+      up_off = e_off + tot_v;  // = the upper rank's first vertex id
+      up_first = su->n_first != 0xffffffffu ? su->n_first - up_off : su->tot_v;
+    }
+    B2M_TRY(b2m_reserve(ctx, BUF_HALO_V, (size_t)up_first * 24 + 24));
+    B2M_TRY(b2m_comm_exchange(ctx, comm, nullptr, 0, nullptr, 0, mesh->verts, sl.hl ? (size_t)my_first * 24 : 0,
+                              ctx->buf[BUF_HALO_V].p, sl.hh ? (size_t)up_first * 24 : 0));
+    mesh->halo_verts = b2m_ptr<double>(ctx, BUF_HALO_V);
+    mesh->halo0 = up_off;
+    mesh->halo1 = up_off + up_first;
+  }
   return B2M_OK;
 }

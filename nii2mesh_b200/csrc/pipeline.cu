@@ -56,41 +56,88 @@ static int check_dims(const int64_t dims[3]) {
   return B2M_OK;
 }
 
-// smooth -> range -> isolevel sanity -> CC masks -> bright bbox.  src/meshify.c:299-371
-int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m_opts *o, b2m_front_out *fo,
-                  b2m_result *res) {
+static b2m_slab single_slab(int nz) {
+  b2m_slab sl;
+  sl.rank = 0; sl.world = 1; sl.gnz = nz; sl.z0 = 0; sl.nzl = nz; sl.hl = 0; sl.hh = 0; sl.ez0 = 0; sl.nze = nz;
+  return sl;
+}
+
+static int init_scalars(b2m_ctx *ctx) {
   B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
-  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
   b2m_scalars *h = ctx->h_scalars;
   memset(h, 0, sizeof(*h));
   h->vmin_enc = 0xffffffffu; h->vmax_enc = 0u; h->cmin_enc = 0xffffffffu;
   for (int a = 0; a < 3; a++) { h->lo[a] = INT_MAX; h->hi[a] = -1; }
   h->first_cube = ~0ull;
-  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+  CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_SCALARS].p, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
+  return B2M_OK;
+}
 
-  const bool smooth = o->pre_smooth && g.nx >= 5 && g.ny >= 5 && g.nz >= 5;  // meshify.c:171
+// smooth -> range -> isolevel sanity -> CC masks -> bright bbox.  src/meshify.c:299-371
+// d_img = the own planes of this rank (nzl of them); g = geometry of the EXT planes (own + halo).
+int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float *d_img, const b2m_geom &g, const b2m_opts *o,
+                  b2m_front_out *fo, b2m_result *res) {
+  B2M_TRY(init_scalars(ctx));
+  b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
+  const bool slabs = sl.world > 1;
+  const size_t nxy = (size_t)g.nxy;
+
+  const bool smooth = o->pre_smooth && g.nx >= 5 && g.ny >= 5 && sl.gnz >= 5;  // meshify.c:171
   if (smooth) {
     B2M_TRY(stage_begin(ctx, B2M_T_SMOOTH));
     B2M_TRY(b2m_reserve(ctx, BUF_SMOOTH, (size_t)g.n * 4));
     float *S = b2m_ptr<float>(ctx, BUF_SMOOTH);
-    B2M_TRY(b2m_smooth_run(ctx, d_img, S, g, d_sc));  // range reduction fused
+    smooth_src src;
+    memset(&src, 0, sizeof(src));
+    src.main = d_img; src.n_main = sl.nzl; src.rz0 = sl.z0; src.gnz = sl.gnz;
+    src.lo = src.hi = d_img;
+    src.oz0 = sl.ez0; src.onz = sl.nze;
+    if (slabs) {
+      // 3 raw planes from each neighbour: the halo plane of S is recomputed here bit-for-bit (2 for the
+      // z taps of that plane + the plane itself)
+      const int nl = sl.hl ? 3 : 0, nh = sl.hh ? 3 : 0;
+      B2M_TRY(b2m_reserve(ctx, BUF_HALO_LO, 3 * nxy * 4));
+      B2M_TRY(b2m_reserve(ctx, BUF_HALO_HI, 3 * nxy * 4));
+      float *hlo = b2m_ptr<float>(ctx, BUF_HALO_LO), *hhi = b2m_ptr<float>(ctx, BUF_HALO_HI);
+      B2M_TRY(b2m_comm_exchange(ctx, comm, d_img + (size_t)(sl.nzl - 3) * nxy, sl.hh ? 3 * nxy * 4 : 0, hlo, nl * nxy * 4,
+                                d_img, sl.hl ? 3 * nxy * 4 : 0, hhi, nh * nxy * 4));
+      src.lo = hlo; src.n_lo = nl; src.hi = hhi; src.n_hi = nh; src.rz0 = sl.z0 - nl;
+    }
+    B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));  // range reduction fused (halo planes are other ranks' planes: harmless)
     fo->S = S;
     B2M_TRY(stage_end(ctx, B2M_T_SMOOTH));
   } else {
     B2M_TRY(stage_begin(ctx, B2M_T_RANGE));
-    fo->S = d_img;
-    B2M_TRY(b2m_minmax_run(ctx, d_img, g, d_sc));
+    if (!slabs) {
+      fo->S = d_img;
+    } else {
+      // EXT copy of the raw slab: one plane from each neighbour around the own planes
+      B2M_TRY(b2m_reserve(ctx, BUF_SMOOTH, (size_t)g.n * 4));
+      float *S = b2m_ptr<float>(ctx, BUF_SMOOTH);
+      CU_TRY(cudaMemcpyAsync(S + (size_t)sl.hl * nxy, d_img, (size_t)sl.nzl * nxy * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      B2M_TRY(b2m_comm_exchange(ctx, comm, d_img + (size_t)(sl.nzl - 1) * nxy, sl.hh ? nxy * 4 : 0, S, sl.hl ? nxy * 4 : 0,
+                                d_img, sl.hl ? nxy * 4 : 0, S + (size_t)(sl.hl + sl.nzl) * nxy, sl.hh ? nxy * 4 : 0));
+      fo->S = S;
+    }
+    B2M_TRY(b2m_minmax_run(ctx, d_img, (size_t)sl.nzl * nxy, d_sc));
     B2M_TRY(stage_end(ctx, B2M_T_RANGE));
   }
-  B2M_TRY(b2m_fetch_scalars(ctx));
-  const float mn = f32_dec(h->vmin_enc), mx = f32_dec(h->vmax_enc);
-  if (o->verbose && smooth) {
+  B2M_TRY(b2m_sync_scalars(ctx, comm));
+  unsigned mn_enc = 0xffffffffu, mx_enc = 0u;
+  for (int r = 0; r < sl.world; r++) {
+    const b2m_scalars *sr = b2m_sc(ctx, comm, r);
+    if (sr->vmin_enc < mn_enc) mn_enc = sr->vmin_enc;
+    if (sr->vmax_enc > mx_enc) mx_enc = sr->vmax_enc;
+  }
+  const float mn = f32_dec(mn_enc), mx = f32_dec(mx_enc);
+  const bool talk = sl.rank == 0;  // the reference's stdout lines: once per volume
+  if (o->verbose && smooth && talk) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_SMOOTH], ctx->ev[2 * B2M_T_SMOOTH + 1]);
     printf("pre-smooth: %ld ms\n", lroundf(ms));
   }
   if (mn == mx) {  // meshify.c:312-315
-    printf("Error: No variability in image intensity.\n");
+    if (talk) printf("Error: No variability in image intensity.\n");
     return B2M_FAIL;
   }
   float iso = o->isolevel;
@@ -98,25 +145,31 @@ int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m
   if (iso <= mn || iso > mx) {  // meshify.c:316-319
     iso = (float)(0.5 * (double)(mn + mx));
     fo->iso_reset = 1;
-    printf("Suggested isolevel out of range. Intensity range %g..%g, setting isolevel to %g\n", mn, mx, iso);
+    if (talk) printf("Suggested isolevel out of range. Intensity range %g..%g, setting isolevel to %g\n", mn, mx, iso);
   }
-  if (o->verbose) printf("intensity range %g..%g, isolevel %g\n", mn, mx, iso);
+  if (o->verbose && talk) printf("intensity range %g..%g, isolevel %g\n", mn, mx, iso);
   fo->iso = iso; fo->vmin = mn; fo->vmax = mx;
   fo->edge_max = (float)(0.75 * (double)(mn + iso));  // meshify.c:346: f32 add, double multiply, f32 store
 
   const bool cc = o->only_largest || o->fill_bubbles;
   B2M_TRY(stage_begin(ctx, cc ? B2M_T_CC : B2M_T_COMPOSE));
-  B2M_TRY(b2m_cc_run(ctx, g, o, d_sc, fo));
+  B2M_TRY(b2m_cc_run(ctx, comm, sl, g, o, d_sc, fo));
   B2M_TRY(stage_end(ctx, cc ? B2M_T_CC : B2M_T_COMPOSE));
-  B2M_TRY(b2m_fetch_scalars(ctx));
-  if (o->verbose && cc) {
+  B2M_TRY(b2m_sync_scalars(ctx, comm));
+  if (ctx->h_scalars->overflow & ~1u) { b2m_set_error("cc: seam list overflow (flags %u)", ctx->h_scalars->overflow); return B2M_ECUDA; }
+  if (o->verbose && cc && talk) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_CC], ctx->ev[2 * B2M_T_CC + 1]);
     printf("voxel clustering (largest cluster, bubbles): %ld ms\n", lroundf(ms));
   }
-  const int dims[3] = {g.nx, g.ny, g.nz};
+  const int dims[3] = {g.nx, g.ny, sl.gnz};
   for (int a = 0; a < 3; a++) {  // meshify.c:368-371
-    int lo = h->lo[a], hi = h->hi[a];
+    int lo = INT_MAX, hi = -1;
+    for (int r = 0; r < sl.world; r++) {
+      const b2m_scalars *sr = b2m_sc(ctx, comm, r);
+      if (sr->lo[a] < lo) lo = sr->lo[a];
+      if (sr->hi[a] > hi) hi = sr->hi[a];
+    }
     if (hi < 0) { lo = dims[a]; hi = 0; }  // no bright voxel at all (cannot happen: iso <= max)
     fo->lo[a] = lo - 1 > 0 ? lo - 1 : 0;
     fo->hi[a] = hi + 2 < dims[a] ? hi + 2 : dims[a];
@@ -128,37 +181,60 @@ int b2m_front_run(b2m_ctx *ctx, const float *d_img, const b2m_geom &g, const b2m
   return B2M_OK;
 }
 
-static int meshify_device_impl(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *o,
-                               b2m_result *res) {
-  b2m_geom g = b2m_make_geom(dims);
+// the whole path on one slab (world == 1: the whole volume).  wo = this rank's part of the welded mesh.
+static int meshify_slab_impl(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float *d_img, const int64_t gdims[3],
+                             const b2m_opts *o, b2m_result *res, b2m_weld_out *wo) {
+  const int64_t edims[3] = {gdims[0], gdims[1], sl.nze};
+  b2m_geom g = b2m_make_geom(edims);
   b2m_front_out fo;
   memset(&fo, 0, sizeof(fo));
+  memset(wo, 0, sizeof(*wo));
+  const bool talk = sl.rank == 0;
   B2M_TRY(stage_begin(ctx, B2M_T_TOTAL));
-  B2M_TRY(b2m_front_run(ctx, d_img, g, o, &fo, res));
+  B2M_TRY(b2m_front_run(ctx, comm, sl, d_img, g, o, &fo, res));
   b2m_mesh_dev mesh;
-  memset(&mesh, 0, sizeof(mesh));
   B2M_TRY(stage_begin(ctx, B2M_T_MC));
-  int rc = b2m_mc_run(ctx, g, o, &fo, &mesh);
+  int rc = b2m_mc_run(ctx, comm, sl, g, o, &fo, &mesh);
   if (rc != B2M_OK) {
-    if (rc == B2M_FAIL && o->backend == B2M_BACKEND_CLASSIC)
+    if (rc == B2M_FAIL && o->backend == B2M_BACKEND_CLASSIC && talk)
       printf("marching cubes failed to identify triangles with an isolevel of %g\n", fo.iso);
     return rc;
   }
   B2M_TRY(stage_end(ctx, B2M_T_MC));
-  res->pre_nverts = o->backend == B2M_BACKEND_CLASSIC ? (int)(3 * mesh.nt) : (int)mesh.nv;
-  res->pre_ntris = (int)mesh.nt;
-  if (o->verbose) {
+  res->pre_nverts = o->backend == B2M_BACKEND_CLASSIC ? (int)(3 * mesh.NT) : (int)(mesh.NVE + mesh.NVC);
+  res->pre_ntris = (int)mesh.NT;
+  if (o->verbose && talk) {
     float ms = 0.f;
     cudaEventSynchronize(ctx->ev[2 * B2M_T_MC + 1]);
     cudaEventElapsedTime(&ms, ctx->ev[2 * B2M_T_MC], ctx->ev[2 * B2M_T_MC + 1]);
-    printf("marching cubes (%dx%dx%d): %ld ms\n", g.nx, g.ny, g.nz, lroundf(ms));
+    printf("marching cubes (%dx%dx%d): %ld ms\n", g.nx, g.ny, sl.gnz, lroundf(ms));
   }
-  B2M_TRY(b2m_weld_run(ctx, &mesh, 0, o->backend, res));
+  B2M_TRY(b2m_weld_run(ctx, comm, &mesh, 0, wo));
   ctx->ev_mask |= (1u << B2M_T_WELD) | (1u << B2M_T_DEGEN);
+  // global triangle count / offsets
+  unsigned long long NTk = 0;
+  unsigned t_off_new = 0;
+  if (sl.world > 1) {
+    B2M_TRY(b2m_sync_scalars(ctx, comm));
+    for (int r = 0; r < sl.world; r++) {
+      if (r == sl.rank) t_off_new = (unsigned)NTk;
+      NTk += b2m_sc(ctx, comm, r)->n_tri_kept;
+    }
+  } else {
+    NTk = wo->nt_local;
+  }
   B2M_TRY(stage_end(ctx, B2M_T_TOTAL));
   B2M_TRY(collect_times(ctx, res));
-  if (o->verbose) {
-    if (res->nmerged) printf("vertex welding %d -> %d: %ld ms\n", res->pre_nverts, res->nverts, lroundf(res->ms[B2M_T_WELD]));
+  res->nverts = (int)wo->nv_global;
+  res->ntris = (int)NTk;
+  res->nmerged = (int)(wo->n_dead) - (int)(wo->n_extra);
+  res->ndegenerate = (int)(mesh.NT - NTk);
+  res->d_verts = wo->verts;
+  res->d_tris = wo->tris;
+  wo->n_extra = wo->n_extra;
+  ctx->slab_t_off = t_off_new;
+  if (o->verbose && talk) {
+    if (wo->n_dead) printf("vertex welding %d -> %d: %ld ms\n", res->pre_nverts, res->nverts, lroundf(res->ms[B2M_T_WELD]));
     else printf("Unify vertices found no shared vertices\n");
     if (res->ndegenerate)
       printf("remove degenerate triangles %d -> %d: %ld ms\n", res->pre_ntris, res->ntris, lroundf(res->ms[B2M_T_DEGEN]));
@@ -176,9 +252,52 @@ extern "C" int b2m_meshify_device(b2m_ctx *ctx, const float *d_img, const int64_
   ctx->launches = 0;
   ctx->ev_mask = 0;
   ctx->nkt = 0;
-  int rc = meshify_device_impl(ctx, d_img, dims, opts, res);
+  b2m_weld_out wo;
+  int rc = meshify_slab_impl(ctx, nullptr, single_slab((int)dims[2]), d_img, dims, opts, res, &wo);
   if (rc != B2M_OK) cudaStreamSynchronize(ctx->stream);
   return rc;
+}
+
+// z-slab entry point: every rank of `comm` calls it with its own planes [z0, z0+nzl) of a volume of gdims.
+extern "C" int b2m_meshify_slab(b2m_ctx *ctx, b2m_comm *comm, const float *d_slab, const int64_t gdims[3], int64_t z0,
+                                int64_t nzl, const b2m_opts *opts, b2m_slab_result *out) {
+  if (!ctx || !d_slab || !gdims || !opts || !out) { b2m_set_error("null argument"); return B2M_EARG; }
+  const int W = b2m_comm_world(comm), rank = b2m_comm_rank(comm);
+  int rc = B2M_OK;
+  for (int a = 0; a < 3; a++)
+    if (gdims[a] < 1 || gdims[a] > 32767) { b2m_set_error("gdims[%d] outside 1..32767", a); rc = B2M_EARG; }
+  if (rc == B2M_OK && (z0 < 0 || nzl < 1 || z0 + nzl > gdims[2] || (rank == 0) != (z0 == 0) || (rank == W - 1) != (z0 + nzl == gdims[2]))) {
+    b2m_set_error("slab [%lld, %lld) of rank %d/%d does not fit a volume of %lld planes", (long long)z0, (long long)(z0 + nzl), rank, W, (long long)gdims[2]);
+    rc = B2M_EARG;
+  }
+  if (rc == B2M_OK && W > 1 && nzl < 4) { b2m_set_error("slabs need at least 4 planes each"); rc = B2M_EARG; }
+  if (rc == B2M_OK && (unsigned long long)gdims[0] * gdims[1] * (nzl + 2) > 0x7fffffffull) {
+    b2m_set_error("slab of more than 2^31-1 voxels");
+    rc = B2M_EARG;
+  }
+  if (rc != B2M_OK) { b2m_comm_abort(comm); return rc; }
+  CU_TRY(cudaSetDevice(ctx->device));
+  memset(out, 0, sizeof(*out));
+  ctx->launches = 0;
+  ctx->ev_mask = 0;
+  ctx->nkt = 0;
+  b2m_slab sl;
+  sl.rank = rank; sl.world = W; sl.gnz = (int)gdims[2]; sl.z0 = (int)z0; sl.nzl = (int)nzl;
+  sl.hl = rank > 0; sl.hh = rank < W - 1; sl.ez0 = sl.z0 - sl.hl; sl.nze = sl.nzl + sl.hl + sl.hh;
+  b2m_weld_out wo;
+  rc = meshify_slab_impl(ctx, comm, sl, d_slab, gdims, opts, &out->r, &wo);
+  if (rc != B2M_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    if (rc != B2M_FAIL) b2m_comm_abort(comm);  // B2M_FAIL is decided identically on every rank
+    return rc;
+  }
+  out->d_verts = wo.verts; out->d_tris = wo.tris;
+  out->nv_edge = (int)wo.nve_local; out->nv_cent = (int)wo.nvc_local; out->nv_extra = (int)wo.nx_local;
+  out->ntris_local = (int)wo.nt_local;
+  out->v_edge_off = wo.v_edge_off; out->v_cent_off = wo.v_c_off;
+  out->v_extra_off = (int64_t)wo.nv_global - wo.n_extra;
+  out->tri_off = ctx->slab_t_off;
+  return B2M_OK;
 }
 
 extern "C" int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris) {
@@ -226,13 +345,13 @@ extern "C" int b2m_stage_smooth(b2m_ctx *ctx, const float *d_in, float *d_out, c
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     return B2M_FAIL;
   }
-  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  B2M_TRY(init_scalars(ctx));
   b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
-  b2m_scalars *h = ctx->h_scalars;
-  memset(h, 0, sizeof(*h));
-  h->vmin_enc = 0xffffffffu;
-  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
-  B2M_TRY(b2m_smooth_run(ctx, d_in, d_out, g, d_sc));
+  smooth_src src;
+  memset(&src, 0, sizeof(src));
+  src.lo = src.main = src.hi = d_in;
+  src.n_main = g.nz; src.gnz = g.nz; src.onz = g.nz;
+  B2M_TRY(b2m_smooth_run(ctx, src, d_out, g, d_sc));
   CU_TRY(cudaStreamSynchronize(ctx->stream));
   return B2M_OK;
 }
@@ -249,7 +368,7 @@ extern "C" int b2m_stage_front(b2m_ctx *ctx, const float *d_img, const int64_t d
   b2m_geom g = b2m_make_geom(dims);
   b2m_front_out fo;
   memset(&fo, 0, sizeof(fo));
-  B2M_TRY(b2m_front_run(ctx, d_img, g, opts, &fo, res));
+  B2M_TRY(b2m_front_run(ctx, nullptr, single_slab(g.nz), d_img, g, opts, &fo, res));
   if (d_composed || d_mask)
     B2M_TRY(b2m_compose_materialize(ctx, g, &fo, d_composed, d_mask, b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS), 0));
   B2M_TRY(collect_times(ctx, res));
@@ -266,15 +385,12 @@ extern "C" int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims
   ctx->ev_mask = 0;
   ctx->nkt = 0;
   b2m_geom g = b2m_make_geom(dims);
-  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
+  B2M_TRY(init_scalars(ctx));
   b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
   b2m_scalars *h = ctx->h_scalars;
-  memset(h, 0, sizeof(*h));
-  h->vmin_enc = 0xffffffffu; h->cmin_enc = 0xffffffffu; h->first_cube = ~0ull;
-  CU_TRY(cudaMemcpyAsync(d_sc, h, sizeof(*h), cudaMemcpyHostToDevice, ctx->stream));
   // the volume is taken as already composed: no fill/keep masks, no darkening (edge_max = +inf);
   // the pad value needs the true minimum (src/MarchingCubes.c:1097-1100)
-  B2M_TRY(b2m_minmax_run(ctx, d_img, g, d_sc));
+  B2M_TRY(b2m_minmax_run(ctx, d_img, (size_t)g.n, d_sc));
   B2M_TRY(b2m_fetch_scalars(ctx));
   b2m_front_out fo;
   memset(&fo, 0, sizeof(fo));
@@ -290,11 +406,11 @@ extern "C" int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims
   b2m_mesh_dev mesh;
   memset(&mesh, 0, sizeof(mesh));
   B2M_TRY(stage_begin(ctx, B2M_T_MC));
-  int rc = b2m_mc_run(ctx, g, opts, &fo, &mesh);
+  int rc = b2m_mc_run(ctx, nullptr, single_slab(g.nz), g, opts, &fo, &mesh);
   if (rc != B2M_OK) { cudaStreamSynchronize(ctx->stream); return rc; }
   B2M_TRY(stage_end(ctx, B2M_T_MC));
-  res->nverts = (int)mesh.nv; res->ntris = (int)mesh.nt;
-  res->pre_nverts = (int)mesh.nv; res->pre_ntris = (int)mesh.nt;
+  res->nverts = (int)(mesh.nv_edge + mesh.nv_c); res->ntris = (int)mesh.nt;
+  res->pre_nverts = res->nverts; res->pre_ntris = (int)mesh.nt;
   res->d_verts = mesh.verts; res->d_tris = mesh.tris;
   res->iso_used = fo.iso; res->vmin = fo.vmin; res->vmax = fo.vmax;
   B2M_TRY(collect_times(ctx, res));
@@ -307,8 +423,7 @@ extern "C" int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *n
   ctx->launches = 0;
   ctx->ev_mask = 0;
   ctx->nkt = 0;
-  B2M_TRY(b2m_reserve(ctx, BUF_SCALARS, sizeof(b2m_scalars)));
-  CU_TRY(cudaMemsetAsync(ctx->buf[BUF_SCALARS].p, 0, sizeof(b2m_scalars), ctx->stream));
+  B2M_TRY(init_scalars(ctx));
   B2M_TRY(b2m_reserve(ctx, BUF_VERTS, (size_t)*nv * 24));
   B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)*nt * 12));
   CU_TRY(cudaMemcpyAsync(ctx->buf[BUF_VERTS].p, h_verts, (size_t)*nv * 24, cudaMemcpyHostToDevice, ctx->stream));
@@ -317,10 +432,15 @@ extern "C" int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *n
   memset(&mesh, 0, sizeof(mesh));
   mesh.verts = b2m_ptr<double>(ctx, BUF_VERTS);
   mesh.tris = b2m_ptr<int>(ctx, BUF_TRIS);
-  mesh.nv = (unsigned)*nv; mesh.nt = (unsigned)*nt; mesh.nv_edge = mesh.nv;
+  mesh.nv_edge = mesh.NVE = (unsigned)*nv;
+  mesh.nt = mesh.NT = (unsigned)*nt;
+  mesh.d_p0 = mesh.verts;  // the reference's pts[0]
+  b2m_weld_out wo;
+  memset(&wo, 0, sizeof(wo));
+  B2M_TRY(b2m_weld_run(ctx, nullptr, &mesh, 1, &wo));
   b2m_result res;
   memset(&res, 0, sizeof(res));
-  B2M_TRY(b2m_weld_run(ctx, &mesh, 1, B2M_BACKEND_LEWINER, &res));
+  res.d_verts = wo.verts; res.d_tris = wo.tris; res.nverts = (int)wo.nv_local; res.ntris = (int)wo.nt_local;
   B2M_TRY(b2m_fetch_mesh(ctx, &res, h_verts, h_tris));
   *nv = res.nverts;
   *nt = res.ntris;

@@ -131,9 +131,19 @@ __device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly,
 //           ((((a*k2)+b*k1)+c*k0)+d*k1)+e*k2 is advanced by one term per arriving plane, so a
 //           column keeps 4 partial sums instead of a 5-plane ring.
 // Every voxel is read once (plus tile halos that hit L2) and written once: 8 B/voxel.
+// Slabs: the raw input comes in up to three pieces (halo planes from the rank below, own planes, halo
+// planes from the rank above); all z in the kernel are GLOBAL plane numbers.
+__device__ __forceinline__ const float *smooth_plane(const smooth_src &s, int zg, size_t nxy) {
+  int q = zg - s.rz0;
+  if (q < s.n_lo) return s.lo + (size_t)q * nxy;
+  q -= s.n_lo;
+  if (q < s.n_main) return s.main + (size_t)q * nxy;
+  return s.hi + (size_t)(q - s.n_main) * nxy;
+}
+
 template <bool VEC>
-__global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restrict__ in, float *__restrict__ out, int nx,
-                                                           int ny, int nz, int zc, unsigned int *__restrict__ mm_enc) {
+__global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant__ smooth_src src, float *__restrict__ out, int nx,
+                                                           int ny, int zc, unsigned int *__restrict__ mm_enc) {
   extern __shared__ double2 xs2[];  // [2][SX_ROWS][2][32]
   __shared__ float red[2][SX_WARPS];
   __shared__ int s_bad[3];
@@ -141,7 +151,8 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restri
   if (tid < 3) s_bad[tid] = 0;
   __syncthreads();
   const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
-  const int z0 = blockIdx.z * zc, z1 = min(z0 + zc, nz);
+  const int nz = src.gnz;
+  const int z0 = src.oz0 + blockIdx.z * zc, z1 = min(z0 + zc, src.oz0 + src.onz);
   const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
   const int gx = x0 + lane * 4;
   const size_t nxy = (size_t)nx * ny;
@@ -156,12 +167,12 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restri
   // loop-invariant addressing: the row this warp stages (gy = y0 - 2 + warp) and the output row it owns (y0 + warp)
   const int sy = y0 - 2 + warp;
   const bool rowok = sy >= 0 && sy < ny;
-  const float *rowp = in + (size_t)zs * nxy + (size_t)(rowok ? sy : 0) * nx;
+  const size_t rowoff = (size_t)(rowok ? sy : 0) * nx;
   const bool haloL = lane == 0 && x0 > 0, haloR0 = lane == 31 && gx + 4 < nx, haloR1 = lane == 31 && gx + 5 < nx;
   const int oy = y0 + warp;
   const bool yborder = oy < 2 || oy >= ny - 2;
   const bool ook = yz && oy < ny && gx < nx;
-  float *outp = out + (size_t)oy * nx + gx;  // + z * nxy
+  float *outp = out + (size_t)oy * nx + gx;  // + (z - oz0) * nxy
 
   // raw row of the plane being staged, prefetched one plane ahead
   float raw[4], hal[2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
@@ -169,16 +180,16 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restri
     raw[0] = raw[1] = raw[2] = raw[3] = 0.f;
     hal[0] = hal[1] = 0.f;
     if (rowok && zp < ze) {
+      const float *rowp = smooth_plane(src, zp, nxy) + rowoff;
       load_row4<VEC>(rowp, gx, nx, raw);
       if (haloL) { hal[0] = __ldg(rowp + x0 - 2); hal[1] = __ldg(rowp + x0 - 1); }
       if (haloR0) hal[0] = __ldg(rowp + gx + 4);
       if (haloR1) hal[1] = __ldg(rowp + gx + 5);
     }
-    rowp += nxy;
   };
   fetch(zs);
-  size_t zoff = (size_t)zs * nxy;
-  for (int zp = zs; zp < ze; zp++, zoff += nxy) {
+  long long zoff = (long long)(zs - src.oz0) * (long long)nxy;  // may start negative: only used for planes inside [oz0, oz0+onz)
+  for (int zp = zs; zp < ze; zp++, zoff += (long long)nxy) {
     double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
     // ---- x pass ---- (inputs are screened only now, not at fetch time: touching the prefetched
     // registers earlier would stall on loads that are meant to fly across the y/z passes)
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const float *__restri
             }
         }
         if (emit_inner) {
-          float *dst = outp + (zoff - 2 * nxy);
+          float *dst = outp + (zoff - 2 * (long long)nxy);
           if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[0], oi[1], oi[2], oi[3]);
 #pragma unroll
           for (int k = 0; k < 4; k++)
@@ -332,17 +343,18 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
   }
 }
 
-int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
+int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
   const unsigned tx = b2m_cdiv(g.nx, SX_TX), ty = b2m_cdiv(g.ny, SX_TY);
+  const int onz = src.onz;
   // z chunk: enough CTAs to fill the machine a few times over, but >= 16 planes so that the 4 halo
   // planes of a chunk stay a small overhead
   int want = (int)((4 * (size_t)ctx->sm_count + (size_t)tx * ty - 1) / ((size_t)tx * ty));
   if (want < 1) want = 1;
-  int zc = (g.nz + want - 1) / want;
+  int zc = (onz + want - 1) / want;
   if (zc < 16) zc = 16;
   if (zc > 128) zc = 128;
-  dim3 grid(tx, ty, b2m_cdiv(g.nz, zc));
-  const bool vec = (g.nx % 4 == 0) && (((uintptr_t)d_in | (uintptr_t)d_out) % 16 == 0);
+  dim3 grid(tx, ty, b2m_cdiv(onz, zc));
+  const bool vec = (g.nx % 4 == 0) && (((uintptr_t)src.main | (uintptr_t)src.lo | (uintptr_t)src.hi | (uintptr_t)d_out) % 16 == 0);
   static bool attr_done = false;
   if (!attr_done) {
     CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
@@ -350,16 +362,16 @@ int b2m_smooth_run(b2m_ctx *ctx, const float *d_in, float *d_out, const b2m_geom
     attr_done = true;
   }
   if (vec)
-    KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, zc, &d_sc->vmin_enc));
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
   else
-    KT_LAUNCH(ctx, "smooth3", k_smooth3<false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(d_in, d_out, g.nx, g.ny, g.nz, zc, &d_sc->vmin_enc));
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
 
-int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, b2m_scalars *d_sc) {
-  unsigned blocks = (unsigned)min((long long)ctx->sm_count * 16, (g.n / 4 + 255) / 256 + 1);
-  KT_LAUNCH(ctx, "minmax", k_minmax<<<blocks, 256, 0, ctx->stream>>>(d_in, (size_t)g.n, &d_sc->vmin_enc));
+int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, size_t n, b2m_scalars *d_sc) {
+  unsigned blocks = (unsigned)min((long long)ctx->sm_count * 16, (long long)(n / 4 + 255) / 256 + 1);
+  KT_LAUNCH(ctx, "minmax", k_minmax<<<blocks, 256, 0, ctx->stream>>>(d_in, n, &d_sc->vmin_enc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

@@ -33,6 +33,13 @@ class Result(C.Structure):
         return {k: float(self.ms[i]) for i, k in enumerate(STAGES)}
 
 
+class SlabResult(C.Structure):
+    """b2m_slab_result: one rank's part of the mesh of a z-slab run (include/b2m.h)"""
+    _fields_ = [("r", Result), ("d_verts", C.c_void_p), ("d_tris", C.c_void_p), ("nv_edge", C.c_int),
+                ("nv_cent", C.c_int), ("nv_extra", C.c_int), ("ntris_local", C.c_int), ("v_edge_off", C.c_int64),
+                ("v_cent_off", C.c_int64), ("v_extra_off", C.c_int64), ("tri_off", C.c_int64)]
+
+
 class B2MError(RuntimeError):
     pass
 
@@ -77,6 +84,13 @@ def load():
     L.b2m_meshify_device.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(Result)]
     L.b2m_meshify_host.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
     L.b2m_fetch_mesh.argtypes = [vp, C.POINTER(Result), vp, vp]
+    L.b2m_comm_nccl_id.argtypes = [vp]
+    L.b2m_comm_create_nccl.argtypes = [C.POINTER(vp), vp, vp, C.c_int, C.c_int]
+    L.b2m_comm_create_local.argtypes = [C.POINTER(vp), C.c_int]
+    L.b2m_comm_destroy.argtypes = [vp]
+    L.b2m_comm_destroy.restype = None
+    L.b2m_comm_reset.argtypes = [vp]
+    L.b2m_meshify_slab.argtypes = [vp, vp, vp, i64p, C.c_int64, C.c_int64, C.POINTER(Opts), C.POINTER(SlabResult)]
     L.b2m_stage_smooth.argtypes = [vp, vp, vp, i64p]
     L.b2m_stage_front.argtypes = [vp, vp, i64p, C.POINTER(Opts), vp, vp, C.POINTER(Result)]
     L.b2m_stage_mc.argtypes = [vp, vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Opts), C.POINTER(Result)]
@@ -226,6 +240,23 @@ class Engine:
         _libc.free(pt)
         return v, t, r
 
+    def meshify_slab(self, comm, dslab, gshape, z0, iso, original_mc=0, pre_smooth=True, only_largest=True,
+                     fill_bubbles=False, backend=BACKEND_LEWINER, verbose=False):
+        """this rank's call of the collective z-slab path; dslab = planes [z0, z0+len) of a volume of gshape (z,y,x).
+        Returns the SlabResult (blocks stay on the device)."""
+        o = self._opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend, verbose)
+        r = SlabResult()
+        self._chk(self.lib.b2m_meshify_slab(self.ctx, comm, dslab.ptr, _dims(gshape), int(z0), int(dslab.shape[0]),
+                                            C.byref(o), C.byref(r)))
+        return r
+
+    def fetch_slab(self, r):
+        """host copies of one rank's blocks: (verts[nv_edge+nv_cent+nv_extra, 3], tris[ntris_local, 3])"""
+        nv = r.nv_edge + r.nv_cent + r.nv_extra
+        v = self.download(r.d_verts, (nv, 3), np.float64) if nv else np.empty((0, 3), np.float64)
+        t = self.download(r.d_tris, (r.ntris_local, 3), np.int32) if r.ntris_local else np.empty((0, 3), np.int32)
+        return v, t
+
     # ---- stage hooks ----
     def smooth(self, vol):
         d_in = self.upload(vol)
@@ -276,3 +307,71 @@ class Engine:
         nv, nt = C.c_int(len(v)), C.c_int(len(t))
         self._chk(self.lib.b2m_stage_weld(self.ctx, v.ctypes.data, t.ctypes.data, C.byref(nv), C.byref(nt)))
         return v[:nv.value].copy(), t[:nt.value].copy()
+
+
+def assemble_slabs(parts):
+    """[(SlabResult, verts, tris)] of all ranks -> the assembled (verts, tris) of the whole volume"""
+    r0 = parts[0][0].r
+    V = np.full((r0.nverts, 3), np.nan, np.float64)
+    T = np.full((r0.ntris, 3), -1, np.int32)
+    for r, v, t in parts:
+        ne, nc, nx = r.nv_edge, r.nv_cent, r.nv_extra
+        V[r.v_edge_off:r.v_edge_off + ne] = v[:ne]
+        V[r.v_cent_off:r.v_cent_off + nc] = v[ne:ne + nc]
+        V[r.v_extra_off:r.v_extra_off + nx] = v[ne + nc:]
+        T[r.tri_off:r.tri_off + r.ntris_local] = t
+    return V, T
+
+
+class LocalSlabGroup:
+    """`len(cuts)-1` z-slabs of one volume driven by host threads of this process (one b2m_ctx each, all on
+    `devices[i]`, default device 0): the single-process transport of the slab path (b2m_comm_create_local)."""
+
+    def __init__(self, world, devices=None):
+        self.world = world
+        self.engs = [Engine((devices or [0] * world)[i]) for i in range(world)]
+        arr = (C.c_void_p * world)()
+        self.engs[0]._chk(self.engs[0].lib.b2m_comm_create_local(arr, world))
+        self.comms = [C.c_void_p(arr[i]) for i in range(world)]
+
+    def close(self):
+        for c in self.comms:
+            self.engs[0].lib.b2m_comm_destroy(c)
+        self.comms = []
+        for e in self.engs:
+            e.close()
+
+    def meshify(self, vol, cuts, iso, fetch=True, **flags):
+        """vol: host volume (z,y,x); cuts: z boundaries [0, ..., nz].  Returns (verts, tris, [SlabResult])"""
+        import threading
+        assert len(cuts) == self.world + 1 and cuts[0] == 0 and cuts[-1] == vol.shape[0]
+        slabs = [self.engs[i].upload(vol[cuts[i]:cuts[i + 1]]) for i in range(self.world)]
+        try:
+            return self.meshify_device(slabs, vol.shape, cuts, iso, fetch=fetch, **flags)
+        finally:
+            for d in slabs:
+                d.free()
+
+    def meshify_device(self, slabs, gshape, cuts, iso, fetch=True, **flags):
+        import threading
+        out, err = [None] * self.world, [None] * self.world
+
+        def work(i):
+            try:
+                r = self.engs[i].meshify_slab(self.comms[i], slabs[i], gshape, cuts[i], iso, **flags)
+                out[i] = (r,) + (self.engs[i].fetch_slab(r) if fetch else (None, None))
+            except Exception as ex:  # noqa: BLE001
+                err[i] = ex
+        th = [threading.Thread(target=work, args=(i,)) for i in range(self.world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if any(err):
+            for c in self.comms:
+                self.engs[0].lib.b2m_comm_reset(c)
+            raise next(e for e in err if e)
+        if not fetch:
+            return None, None, [o[0] for o in out]
+        V, T = assemble_slabs(out)
+        return V, T, [o[0] for o in out]
