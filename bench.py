@@ -3,21 +3,24 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--size 1024] [--impl reference]
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic G1024
-"gyroid + bumps" 1024^3 float32 volume, Lewiner MC33, -p 1 -l 1 -b 1, isolevel 0.  A step is one
-whole meshify() pass over the volume.
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic "gyroid + bumps"
+float32 volume (128^3 period), Lewiner MC33, -p 1 -l 1 -b 1, isolevel 0.  A step is one whole meshify() pass.
+  N = 1 : G1024, 1024^3 voxels on one B200.
+  N > 1 : ONE volume of N * 2^30 voxels cut into N z-slabs, one rank (process, GPU) per slab, NCCL over NVLink
+          for the halo planes / seam lists (b2m_meshify_slab): 2048x1024x1024, 2048x2048x1024 and, at N = 8,
+          2048^3 (BASELINE configs[4]).  Per-GPU work is fixed (2^30 voxels): weak scaling.
 
-  value : volume resident in HBM, mesh left in HBM; K steps between one CUDA-event pair on the
-          library's stream (b2m_timer_start/stop), barrier + synchronize on both sides, max over ranks.
-  e2e   : the same through the reference-facing C entry point meshify() (include/meshify.h) with a
-          pinned HOST volume in and malloc()'d HOST mesh out, copies inside the timed region.
-  roofline : the dominant kernel of the step, from per-launch CUDA-event pairs recorded live during
-          the timed steps (b2m_set_profile); algorithmic bytes per launch are in KERNEL_BYTES below
-          (DESIGN.md §Kernels), peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
-  cpu_baseline : the unmodified reference (oracle/_ref, built by oracle/build_ref.sh) on a bounded
-          sample (G384, same generator and flags), 1 core — the path has no threading.
-  --impl reference : only that CPU reference, each step one G256 volume of the same workload.
-N > 1: one process per GPU (torchrun), NCCL for the barrier and the max-over-ranks only.
+  value : volume resident in HBM, mesh left in HBM; K steps between one CUDA-event pair on the library's
+          stream (b2m_timer_start/stop), barrier + synchronize on both sides, max over ranks.
+  e2e   : the same through the reference-facing C entry point — meshify() (include/meshify.h) at N = 1,
+          b2m_meshify_slab_host() at N > 1 — with a pinned HOST volume in and malloc()'d HOST mesh out, copies
+          inside the timed region.
+  roofline : the dominant kernel of the step, from per-launch CUDA-event pairs recorded live during the timed
+          steps (b2m_set_profile); algorithmic bytes per launch are in kernel_bytes() below,
+          peak = MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
+  cpu_baseline : the unmodified reference (oracle/_ref, built by oracle/build_ref.sh) on a bounded sample of the
+          same generator and flags; meshify() is single-threaded, so one volume per host core runs concurrently.
+  --impl reference : only that CPU reference, each step = one G256 volume per host core.
 """
 import argparse
 import ctypes as C
@@ -36,6 +39,7 @@ sys.path.insert(0, str(ROOT))
 
 FLAGS = dict(original_mc=0, pre_smooth=1, only_largest=1, fill_bubbles=1, backend=0)
 ISO = 0.0
+METRIC = "Gvoxels/s meshify (smooth+CC+MC+weld)"
 
 
 def peaks():
@@ -49,8 +53,8 @@ def peaks():
 
 
 def kernel_bytes(name, n, nv, nt, nwords):
-    """ALGORITHMIC bytes one launch of kernel `name` must move: n voxels f32,
-    nwords 32-voxel bit words, nv/nt mesh vertices/triangles."""
+    """ALGORITHMIC bytes one launch of kernel `name` must move: n voxels f32 (per GPU),
+    nwords 32-voxel bit words, nv/nt mesh vertices/triangles (per GPU)."""
     table = {
         "smooth3": 8 * n,                        # R V + W V
         "minmax": 4 * n,
@@ -58,10 +62,28 @@ def kernel_bytes(name, n, nv, nt, nwords):
         "mc_classify": 4 * n,                    # R V (composed on the fly)
         "mc_emit": 24 * nv + 12 * nt,            # surface term S
         "tri_remap_degen": 12 * nt + 72 * nt + 4 * nt,
-        "cc_link": nwords * 4, "cc_flatten": nwords * 4, "cc_init": nwords * 4, "cc_best": nwords * 4,
+        "cc_local": nwords * 4, "cc_border": nwords * 4, "cc_flatten": nwords * 4, "cc_best": nwords * 4,
         "cc_select": nwords * 8, "dilate_bbox": nwords * 12,
     }
     return table.get(name)
+
+
+def slab_volume(world, n):
+    """global (nz, ny, nx) of the N-GPU workload: N * n^3 voxels, doubling x, then y, then z"""
+    nz = ny = nx = n
+    k = world
+    for ax in ("x", "y", "z") * 4:
+        if k <= 1:
+            break
+        if ax == "x":
+            nx *= 2
+        elif ax == "y":
+            ny *= 2
+        else:
+            nz *= 2
+        k //= 2
+    assert nx * ny * nz == world * n ** 3, "--gpus must be a power of two"
+    return nz, ny, nx
 
 
 class ClockSampler(threading.Thread):
@@ -99,8 +121,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
 
 
-def ref_meshify_time(n, steps, warmup):
-    """time the unmodified reference (oracle/_ref) on G<n>; falls back to the oracle port"""
+def ref_meshify_time(n, steps, warmup, threads):
+    """time the unmodified reference (oracle/_ref; falls back to the oracle port) on `threads` concurrent
+    G<n> volumes per step (meshify() itself is single-threaded; ctypes releases the GIL)"""
     from nii2mesh_b200 import synth
     import oracle
     vol = synth.gyroid(n)
@@ -110,29 +133,49 @@ def ref_meshify_time(n, steps, warmup):
     else:
         O, kind = oracle.Oracle(), "port"
         fn = lambda: O.meshify(vol, ISO, 0, 1, 1, 1, 0)  # noqa: E731
+    last = [None] * threads
+
+    def one_step():
+        def work(i):
+            last[i] = fn()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
     for _ in range(warmup):
-        fn()
+        one_step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        r = fn()
+        one_step()
     dt = (time.perf_counter() - t0) / steps
-    assert r["rc"] == 0
+    r = last[0]
+    assert all(x["rc"] == 0 for x in last)
     return dt, kind, len(r["verts"]), len(r["tris"])
+
+
+def host_threads():
+    try:
+        c = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        c = os.cpu_count() or 1
+    return max(1, min(c, 32))
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = 256
-    dt, kind, nv, nt = ref_meshify_time(n, args.steps, min(args.warmup, 1))
-    val = n ** 3 / dt / 1e9
-    out = {"impl": "reference", "metric": "Gvoxels/s meshify (smooth+CC+MC+weld)", "value": val, "unit": "Gvoxels/s",
+    n, T = 256, host_threads()
+    dt, kind, nv, nt = ref_meshify_time(n, args.steps, min(args.warmup, 1), T)
+    val = T * n ** 3 / dt / 1e9
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxels/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "G1024 gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
-                                  f"each step = one G{n} volume of the same generator (bounded sample)"},
-           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": 1, "kind": kind,
-                            "sample": f"G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris; meshify() is single-threaded"},
+           "config": {"workload": "gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
+                                  f"each step = {T} G{n} volumes of the same generator, one per host core (bounded sample)"},
+           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "kind": kind,
+                            "sample": f"{T} x G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris each; meshify() is "
+                                      f"single-threaded, one volume per core"},
            "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)
@@ -143,7 +186,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--size", type=int, default=1024, help="cube edge of the per-GPU volume (multiple of 128)")
     ap.add_argument("--impl", default="b2m")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -177,13 +220,31 @@ def main():
     from nii2mesh_b200 import lib, synth
     eng = lib.Engine(local)
     n = args.size
-    N = n ** 3
+    gshape = slab_volume(world, n)          # (nz, ny, nx) of the whole volume
+    GN = gshape[0] * gshape[1] * gshape[2]
+    nzl = gshape[0] // world
+    z0 = rank * nzl
+    sshape = (nzl, gshape[1], gshape[2])    # this rank's slab
+    N = nzl * gshape[1] * gshape[2]
     tile = synth.gyroid_tile(128)
-    dvol = eng.tiled_volume(tile, (n, n, n))
+    dvol = eng.tiled_volume(tile, sshape, z_offset=z0)
+    comm = None
+    if world > 1:
+        # torch.distributed is plumbing only: it carries the 128-byte NCCL id of the library's own communicator
+        from nii2mesh_b200 import slabs
+        comm = slabs.nccl_comm_from_torch(eng, dist, rank, world)
+
+    def step():
+        if world == 1:
+            return eng.meshify_device(dvol, ISO, fetch=False, **FLAGS)[2]
+        sr = eng.meshify_slab(comm, dvol, gshape, z0, ISO, **FLAGS)
+        step.last = sr
+        return sr.r
+    step.last = None
 
     # ---- device-resident throughput -------------------------------------------------------------
     for _ in range(args.warmup):
-        _, _, r = eng.meshify_device(dvol, ISO, fetch=False, **FLAGS)
+        r = step()
     eng.set_profile(True)
     ktot, kcnt = {}, {}
     sampler = ClockSampler(local)
@@ -195,7 +256,7 @@ def main():
     stage = np.zeros(8)
     per_step_k = []
     for _ in range(args.steps):
-        _, _, r = eng.meshify_device(dvol, ISO, fetch=False, **FLAGS)
+        r = step()
         launches += r.launches
         stage += np.array(list(r.ms))
         per_step_k.append(eng.kernel_times())   # reads events already completed (the call synchronises)
@@ -205,95 +266,128 @@ def main():
     eng.set_profile(False)
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
-    value = world * N / (ms_step * 1e-3) / 1e9
+    value = GN / (ms_step * 1e-3) / 1e9
     for ks in per_step_k:
         for name, ms in ks:
             ktot[name] = ktot.get(name, 0.0) + ms
             kcnt[name] = kcnt.get(name, 0) + 1
-    nv, nt = r.nverts, r.ntris
-    nwords = n * n * ((n + 31) // 32)
+    nv, nt = r.nverts, r.ntris                      # global counts
+    if world == 1:
+        lnv, lnt = nv, nt
+    else:
+        sr = step.last
+        lnv, lnt = sr.nv_edge + sr.nv_cent + sr.nv_extra, sr.ntris_local
+    nwords = nzl * gshape[1] * ((gshape[2] + 31) // 32)
     peak, peak_src = peaks()
     top = max(ktot, key=ktot.get)
     top_ms = ktot[top] / kcnt[top]
-    kb = kernel_bytes(top, N, nv, nt, nwords)
+    kb = kernel_bytes(top, N, lnv, lnt, nwords)
     achieved = kb / (top_ms * 1e-3) / 1e9 if kb else None
     # whole-step algorithmic traffic (60 B/voxel for -p1 -l1 -b1, plus the surface term)
-    step_bytes = 60 * N + 24 * nv + 12 * nt
+    step_bytes = 60 * GN + 24 * nv + 12 * nt
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                 "kernel_ms": top_ms, "kernel_share_of_step": ktot[top] / (ms_step * args.steps),
-                "algorithmic_bytes_per_launch": kb,
+                "algorithmic_bytes_per_launch": kb, "scope": "rank 0's GPU" if world > 1 else "the GPU",
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,
-                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                               "frac": step_bytes / (ms_step * 1e-3) / 1e9 / (peak * world)},
                 "kernels_ms_per_step": {k: round(v / args.steps, 4) for k, v in sorted(ktot.items(), key=lambda kv: -kv[1])}}
 
-    # ---- end to end through meshify() (include/meshify.h) with host buffers --------------------------
+    # ---- end to end through the reference-facing entry point with host buffers ---------------------
     e2e = None
     if not args.no_e2e:
         L = eng.lib
         hp = C.c_void_p()
         eng._chk(L.b2m_host_alloc(C.byref(hp), N * 4))
-        hvol = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(n, n, n))
-        reps = n // 128
-        if reps * 128 == n:
-            hvol.reshape(reps, 128, reps, 128, reps, 128)[...] = tile[None, :, None, :, None, :]
+        hvol = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=sshape)
+        rz, ry, rx = nzl // 128, gshape[1] // 128, gshape[2] // 128
+        if (rz * 128, ry * 128, rx * 128) == sshape and z0 % 128 == 0:
+            hvol.reshape(rz, 128, ry, 128, rx, 128)[...] = tile[None, :, None, :, None, :]
         else:
-            hvol[...] = synth.gyroid(n)
-        L.meshify.argtypes = [C.c_void_p, C.POINTER(C.c_short), C.c_int, C.c_float, C.POINTER(C.c_void_p),
-                              C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_bool, C.c_bool,
-                              C.c_bool, C.c_bool]
+            hvol[...] = dvol.to_host()
         libc = C.CDLL(None)
         libc.free.argtypes = [C.c_void_p]
-        dim = (C.c_short * 3)(n, n, n)
         os.environ["B2M_DEVICE"] = str(local)
-
-        def one():
-            pt, pp, cnt, cnv = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
-            rc = L.meshify(hp, dim, 0, ISO, C.byref(pt), C.byref(pp), C.byref(cnt), C.byref(cnv), True, True, True, False)
-            assert rc == 0 and (cnv.value, cnt.value) == (nv, nt)
-            libc.free(pp)
-            libc.free(pt)
         dvol.free()
+        if world == 1:
+            L.meshify.argtypes = [C.c_void_p, C.POINTER(C.c_short), C.c_int, C.c_float, C.POINTER(C.c_void_p),
+                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_bool, C.c_bool,
+                                  C.c_bool, C.c_bool]
+            dim = (C.c_short * 3)(n, n, n)
+
+            def one():
+                pt, pp, cnt, cnv = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+                rc = L.meshify(hp, dim, 0, ISO, C.byref(pt), C.byref(pp), C.byref(cnt), C.byref(cnv), True, True, True, False)
+                assert rc == 0 and (cnv.value, cnt.value) == (nv, nt)
+                libc.free(pp)
+                libc.free(pt)
+                return nv * 24 + nt * 12
+            api = "meshify() (include/meshify.h), pinned host volume in, malloc'd host mesh out"
+        else:
+            o2 = lib.Opts(ISO, 0, 1, 1, 1, 0, 0)
+            gd = (C.c_int64 * 3)(gshape[2], gshape[1], gshape[0])
+
+            def one():
+                pv, pt = C.c_void_p(), C.c_void_p()
+                sr2 = lib.SlabResult()
+                eng._chk(L.b2m_meshify_slab_host(eng.ctx, comm, hp, gd, z0, nzl, C.byref(o2), C.byref(pv), C.byref(pt),
+                                                 C.byref(sr2)))
+                assert (sr2.r.nverts, sr2.r.ntris) == (nv, nt)
+                libc.free(pv)
+                libc.free(pt)
+                return (sr2.nv_edge + sr2.nv_cent + sr2.nv_extra) * 24 + sr2.ntris_local * 12
+            api = ("b2m_meshify_slab_host() (include/b2m.h), one z-slab per rank: pinned host planes in, malloc'd host "
+                   "mesh blocks out")
         ke = max(1, min(args.steps, 5))
         for _ in range(2):
             one()
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
-            one()
+            d2h = one()
         barrier()
         dt = max_over_ranks((time.perf_counter() - t0) / ke)
-        # one untimed call through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
-        r2 = lib.Result()
-        pv, pt = C.c_void_p(), C.c_void_p()
-        o2 = lib.Opts(ISO, 0, 1, 1, 1, 0, 0)
-        eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o2), C.byref(pv), C.byref(pt), C.byref(r2)))
-        libc.free(pv)
-        libc.free(pt)
-        breakdown = {"h2d_ms": round(r2.h2d_ms, 2), "device_ms": round(r2.ms[7], 2), "d2h_ms": round(r2.d2h_ms, 2)}
-        e2e = {"value": world * N / dt / 1e9, "breakdown": breakdown, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
-               "d2h_bytes_per_step": nv * 24 + nt * 12, "ms_per_step": dt * 1e3, "steps": ke,
-               "api": "meshify() (include/meshify.h), pinned host volume in, malloc'd host mesh out"}
+        breakdown = None
+        if world == 1:
+            # one untimed call through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
+            r2 = lib.Result()
+            pv, pt = C.c_void_p(), C.c_void_p()
+            o2 = lib.Opts(ISO, 0, 1, 1, 1, 0, 0)
+            eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o2), C.byref(pv), C.byref(pt), C.byref(r2)))
+            libc.free(pv)
+            libc.free(pt)
+            breakdown = {"h2d_ms": round(r2.h2d_ms, 2), "device_ms": round(r2.ms[7], 2), "d2h_ms": round(r2.d2h_ms, 2)}
+        e2e = {"value": GN / dt / 1e9, "breakdown": breakdown, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
+               "d2h_bytes_per_step": d2h, "bytes_scope": "per rank" if world > 1 else "whole job",
+               "ms_per_step": dt * 1e3, "steps": ke, "api": api}
         L.b2m_host_free(hp)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sn = 384
-        dt, kind, cnv, cnt = ref_meshify_time(sn, 1, 0)
-        cpu = {"value": sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": 1, "kind": kind,
-               "sample": f"G{sn} ({sn}^3 voxels, same generator and flags), 1 run of {dt:.1f} s, {cnv} verts {cnt} tris; "
-                         f"host has {os.cpu_count()} cores, meshify() is single-threaded"}
+        sn, T = 256, host_threads()
+        dt, kind, cnv, cnt = ref_meshify_time(sn, 1, 0, T)
+        cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "kind": kind,
+               "sample": f"{T} x G{sn} ({sn}^3 voxels, same generator and flags) concurrently, one per host core, "
+                         f"{dt:.1f} s, {cnv} verts {cnt} tris each; meshify() itself is single-threaded"}
     if rank == 0:
-        out = {"metric": "Gvoxels/s meshify (smooth+CC+MC+weld)", "value": value, "unit": "Gvoxels/s", "n_gpus": world,
+        if world == 1:
+            workload = f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])"
+            par = "single GPU"
+        else:
+            workload = (f"gyroid+bumps {gshape[2]}x{gshape[1]}x{gshape[0]} f32 ({world} x 2^{int(np.log2(N))} voxels), Lewiner MC33 "
+                        f"-p1 -l1 -b1 iso 0, ONE volume in {world} z-slabs (BASELINE configs[4] family; 2048^3 at 8 GPUs)")
+            par = f"{world} z-slabs of {nzl} planes, one rank per GPU; NCCL halo/seam exchange (b2m_meshify_slab)"
+        out = {"metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])",
-                          "voxels_per_gpu": N, "parallelism": "single GPU" if world == 1 else f"{world} independent volumes, one per GPU",
+               "config": {"workload": workload, "voxels_per_gpu": N, "voxels": GN, "parallelism": par,
                           "l2": "inputs (4 B/voxel volume) larger than the 126 MB L2; no flush needed",
                           "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris}},
                "stage_ms": {k: round(float(v) / args.steps, 4) for k, v in zip(lib.STAGES, stage)},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out), flush=True)
+    if comm is not None:
+        eng.lib.b2m_comm_destroy(comm)
     if world > 1:
         dist.destroy_process_group()
 

@@ -139,6 +139,11 @@ typedef struct {
 int b2m_meshify_slab(b2m_ctx *ctx, b2m_comm *comm, const float *d_slab, const int64_t gdims[3], int64_t z0, int64_t nzl,
                      const b2m_opts *opts, b2m_slab_result *out);
 
+/* Same from HOST memory: H2D of this rank's planes, the slab pipeline, D2H of this rank's blocks into malloc()
+ * blocks the caller free()s (*verts: nv_edge+nv_cent+nv_extra x 3 f64, *tris: ntris_local x 3 i32). */
+int b2m_meshify_slab_host(b2m_ctx *ctx, b2m_comm *comm, const float *h_slab, const int64_t gdims[3], int64_t z0,
+                          int64_t nzl, const b2m_opts *opts, void **verts, void **tris, b2m_slab_result *out);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

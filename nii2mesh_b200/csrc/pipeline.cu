@@ -334,6 +334,36 @@ extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t 
   return B2M_OK;
 }
 
+// z-slab path from HOST memory: this rank's planes in, this rank's mesh blocks out (malloc()'d, caller frees).
+extern "C" int b2m_meshify_slab_host(b2m_ctx *ctx, b2m_comm *comm, const float *h_slab, const int64_t gdims[3], int64_t z0,
+                                     int64_t nzl, const b2m_opts *opts, void **verts, void **tris, b2m_slab_result *out) {
+  if (!ctx || !h_slab || !gdims || !opts || !out || !verts || !tris) { b2m_set_error("null argument"); b2m_comm_abort(comm); return B2M_EARG; }
+  if (nzl < 1 || gdims[0] < 1 || gdims[1] < 1) { b2m_set_error("bad slab"); b2m_comm_abort(comm); return B2M_EARG; }
+  CU_TRY(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)gdims[0] * gdims[1] * nzl;
+  int rc = b2m_reserve(ctx, BUF_INPUT, n * 4);
+  const double t0 = wall_ms();
+  if (rc == B2M_OK) rc = b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_slab, n * 4);
+  if (rc != B2M_OK) { b2m_comm_abort(comm); return rc; }
+  const double t1 = wall_ms();
+  B2M_TRY(b2m_meshify_slab(ctx, comm, b2m_ptr<float>(ctx, BUF_INPUT), gdims, z0, nzl, opts, out));
+  const double t2 = wall_ms();
+  const size_t nv = (size_t)out->nv_edge + out->nv_cent + out->nv_extra, nt = (size_t)out->ntris_local;
+  void *v = malloc(nv * 24 + 8), *t = malloc(nt * 12 + 8);
+  if (!v || !t) { free(v); free(t); b2m_set_error("malloc of the output mesh failed"); return B2M_ENOMEM; }
+  hint_hugepages(v, nv * 24);
+  hint_hugepages(t, nt * 12);
+  rc = B2M_OK;
+  if (nv) rc = b2m_copy_d2h(ctx, v, out->d_verts, nv * 24);
+  if (rc == B2M_OK && nt) rc = b2m_copy_d2h(ctx, t, out->d_tris, nt * 12);
+  if (rc != B2M_OK) { free(v); free(t); return rc; }
+  out->r.h2d_ms = (float)(t1 - t0);
+  out->r.d2h_ms = (float)(wall_ms() - t2);
+  *verts = v;
+  *tris = t;
+  return B2M_OK;
+}
+
 // ---- stage hooks ---------------------------------------------------------------------------------
 extern "C" int b2m_stage_smooth(b2m_ctx *ctx, const float *d_in, float *d_out, const int64_t dims[3]) {
   if (!ctx || !d_in || !d_out || !dims) return B2M_EARG;

@@ -91,6 +91,8 @@ def load():
     L.b2m_comm_destroy.restype = None
     L.b2m_comm_reset.argtypes = [vp]
     L.b2m_meshify_slab.argtypes = [vp, vp, vp, i64p, C.c_int64, C.c_int64, C.POINTER(Opts), C.POINTER(SlabResult)]
+    L.b2m_meshify_slab_host.argtypes = [vp, vp, vp, i64p, C.c_int64, C.c_int64, C.POINTER(Opts), C.POINTER(vp),
+                                        C.POINTER(vp), C.POINTER(SlabResult)]
     L.b2m_stage_smooth.argtypes = [vp, vp, vp, i64p]
     L.b2m_stage_front.argtypes = [vp, vp, i64p, C.POINTER(Opts), vp, vp, C.POINTER(Result)]
     L.b2m_stage_mc.argtypes = [vp, vp, i64p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(Opts), C.POINTER(Result)]
@@ -249,6 +251,38 @@ class Engine:
         self._chk(self.lib.b2m_meshify_slab(self.ctx, comm, dslab.ptr, _dims(gshape), int(z0), int(dslab.shape[0]),
                                             C.byref(o), C.byref(r)))
         return r
+
+    def nccl_comm(self, id128, rank, world):
+        """NCCL transport of the slab path: id128 = bytes from nccl_unique_id() of rank 0"""
+        comm = C.c_void_p()
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(id128))
+        self._chk(self.lib.b2m_comm_create_nccl(C.byref(comm), self.ctx, buf, rank, world))
+        return comm
+
+    def nccl_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        self._chk(self.lib.b2m_comm_nccl_id(buf))
+        return bytes(buf)
+
+    def meshify_slab_host(self, comm, slab, gshape, z0, iso, original_mc=0, pre_smooth=True, only_largest=True,
+                          fill_bubbles=False, backend=BACKEND_LEWINER, hptr=None):
+        """host planes in (numpy array, or a raw host pointer `hptr` with slab = its (nz,ny,nx) shape), host blocks out"""
+        o = self._opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend)
+        r = SlabResult()
+        pv, pt = C.c_void_p(), C.c_void_p()
+        if hptr is None:
+            slab = np.ascontiguousarray(slab, dtype=np.float32)
+            hptr, shape = slab.ctypes.data, slab.shape
+        else:
+            shape = slab
+        self._chk(self.lib.b2m_meshify_slab_host(self.ctx, comm, hptr, _dims(gshape), int(z0), int(shape[0]), C.byref(o),
+                                                 C.byref(pv), C.byref(pt), C.byref(r)))
+        nv = r.nv_edge + r.nv_cent + r.nv_extra
+        v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(max(nv, 1), 3))[:nv].copy()
+        t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(max(r.ntris_local, 1), 3))[:r.ntris_local].copy()
+        _libc.free(pv)
+        _libc.free(pt)
+        return r, v, t
 
     def fetch_slab(self, r):
         """host copies of one rank's blocks: (verts[nv_edge+nv_cent+nv_extra, 3], tris[ntris_local, 3])"""
