@@ -159,11 +159,20 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
   }
 }
 
+// The tile roots (the only nodes that carry counts and can become roots of the global forest) are also appended
+// to a compact list, so that the passes after the border unions (k_cc_flatten / k_cc_best) visit a few hundred
+// thousand entries instead of scanning every bit word of the volume.  list[0] = count; when it exceeds the
+// capacity the full-scan variants of those passes run instead (both are launched, the wrong one exits at once).
+#define CT_LIST 1024
 template <int CONN>
-__global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, uint2 *__restrict__ nodes) {
+__global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, uint2 *__restrict__ nodes,
+                                                       uint32_t *__restrict__ rlist, unsigned rcap) {
   __shared__ uint32_t sb[CT_WORDS];
   __shared__ uint32_t par[CT_WORDS * 16];
+  __shared__ uint32_t s_list[CT_LIST];
+  __shared__ unsigned s_n, s_base;
   const int t = threadIdx.x;
+  if (t == 0) s_n = 0;
   const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
   const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
   const bool valid = xw < g.w && y < g.ny && z < g.nz;
@@ -245,9 +254,21 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     if (r == me) {
       const uint32_t pe = par[me];
       stat = (pe & 0x7fffu) | ((pe & 0x8000u) << 16);
+      const unsigned li = atomicAdd(&s_n, 1u);
+      if (li < CT_LIST) s_list[li] = gparent;
+      else {  // more tile roots than the staging list holds (noise): straight to the global list
+        const unsigned gi = atomicAdd(&rlist[0], 1u);
+        if (gi < rcap) rlist[1 + gi] = gparent;
+      }
     }
     nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)] = make_uint2(gparent, stat);
   }
+  __syncthreads();
+  const unsigned nl = min(s_n, (unsigned)CT_LIST);
+  if (t == 0 && nl) s_base = atomicAdd(&rlist[0], nl);
+  __syncthreads();
+  for (unsigned i = t; i < nl; i += CT_WORDS)
+    if (s_base + i < rcap) rlist[1 + s_base + i] = s_list[i];
 }
 
 // neighbour pairs that straddle two tiles: global lock-free unions between (mostly) tile roots
@@ -276,10 +297,15 @@ __global__ void __launch_bounds__(256) k_cc_border(const uint32_t *__restrict__ 
     const int e = run_end(wv, s);
     const uint32_t rm = bits_range(s, e);
     rest &= ~rm;
-    const uint32_t me = (uint32_t)word * 16u + (uint32_t)(s >> 1);
+    // unions are made between TILE ROOTS (a run node's parent is its tile root and never changes here); lanes of
+    // the warp that want the same pair - the common case along the face of two big components - send one
+    const uint32_t ra = nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)].x;
     cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st) {
       const long long nword = ((long long)(z + dz) * g.ny + (y + dy)) * g.w + (xw + dx);
-      uf_union(nodes, me, (uint32_t)nword * 16u + (uint32_t)(st >> 1));
+      const uint32_t rb = nodes[(uint32_t)nword * 16u + (uint32_t)(st >> 1)].x;
+      const unsigned long long key = ((unsigned long long)ra << 32) | rb;
+      const unsigned peers = __match_any_sync(__activemask(), key);
+      if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) uf_union(nodes, ra, rb);
     });
   }
 }
@@ -297,7 +323,9 @@ __device__ __forceinline__ void flush_stats(uint2 *nodes, uint32_t root, uint32_
 
 // every tile root that lost its root status in k_cc_border hands the count / face flag of its local
 // component to its final root and is pointed straight at it (runs then reach the final root in two hops).
-__global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes) {
+__global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes,
+                                                    const uint32_t *__restrict__ rlist, unsigned rcap) {
+  if (rlist[0] <= rcap) return;  // the list variant does the work
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t wv = word < g.nwords ? __ldg(bits + word) : 0u;
   uint32_t starts = wv & ~(wv << 1);
@@ -320,6 +348,51 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
   }
 }
 
+// list variants: one thread per tile root (k_cc_local's list); they do nothing when the list overflowed
+__global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restrict__ rlist, unsigned rcap, uint2 *nodes) {
+  const unsigned n = rlist[0];
+  if (n > rcap) return;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t root = 0xffffffffu, cnt = 0, flag = 0;
+  if (i < n) {
+    const uint32_t slot = rlist[1 + i];
+    const uint2 nd = nodes[slot];
+    if (nd.x != slot) {
+      root = uf_find(nodes, slot);
+      atomicMin(&nodes[slot].x, root);
+      cnt = nd.y & 0x7fffffffu;
+      flag = nd.y >> 31;
+    }
+  }
+  if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
+}
+__global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict__ rlist, unsigned rcap, const uint2 *__restrict__ nodes,
+                                                      unsigned long long *best, unsigned int *nroots) {
+  const unsigned n = rlist[0];
+  if (n > rcap) return;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long key = 0;
+  unsigned int cnt = 0;
+  if (i < n) {
+    const uint32_t slot = rlist[1 + i];
+    const uint2 nd = nodes[slot];
+    if (nd.x == slot) {
+      cnt = 1;
+      key = ((unsigned long long)(nd.y & 0x7fffffffu) << 32) | (unsigned long long)(0xffffffffu - slot);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, key, d);
+    key = o > key ? o : key;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (key && best) atomicMax(best, key);
+    if (cnt) atomicAdd(nroots, cnt);
+  }
+}
+
 // final root of a run after k_cc_flatten: run -> tile root -> final root
 __device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ nodes, uint32_t slot) {
   uint32_t p = nodes[slot].x;
@@ -335,7 +408,8 @@ __device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ node
 // sizes the smallest slot (earliest first voxel in raster order) wins, as src/bwlabel.c:462-466.
 __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bits, long long nwords,
                                                  const uint2 *__restrict__ nodes, unsigned long long *best,
-                                                 unsigned int *nroots) {
+                                                 unsigned int *nroots, const uint32_t *__restrict__ rlist, unsigned rcap) {
+  if (rlist[0] <= rcap) return;  // the list variant does the work
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t w = word < nwords ? __ldg(bits + word) : 0u;
   uint32_t starts = w & ~(w << 1);
@@ -422,9 +496,20 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
 #define DIL_ZC 16
 // Slabs: the arrays are indexed with GLOBAL z (pre-offset EXT buffers), g.nz is the global NZ and the
 // kernel writes the own planes [zbeg, zend) only.
+// The same pass folds the composition rules (src/meshify.c:332-365) into the marching-cubes inside bits, at
+// word level: mb (in: the MC comparison on S; out: the inside bit of the COMPOSED volume) becomes
+//   Lewiner  ((mb | fill) & keep | ~keep & [mn inside]) & (~face | [edge_max inside])
+//   classic  ((mb & ~fill) & keep | ~keep & [mn inside]) | (face & [edge_max inside])
+// because max(v, iso) is never below iso, non-kept voxels hold mn, and the inside test of min(edge_max, v) is
+// the AND (Lewiner: v - iso > -eps) / OR (classic: v < iso) of the tests of its two arguments.
+struct ibits_params {
+  uint32_t *mb;
+  uint32_t cM, cE;  // all-ones / zero: inside test of mn, of edge_max
+  int classic;
+};
 __global__ void __launch_bounds__(256) k_dilate_bbox(const uint32_t *__restrict__ largest,
                                                      const uint32_t *__restrict__ bright_src, cc_geom g, int zbeg, int zend,
-                                                     uint32_t *__restrict__ keep, int *__restrict__ lohi) {
+                                                     uint32_t *__restrict__ keep, int *__restrict__ lohi, ibits_params ip) {
   const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (y, xw) flattened
   const long long ncol = (long long)g.ny * g.w;
   int lo0 = INT_MAX, lo1 = INT_MAX, lo2 = INT_MAX, hi0 = -1, hi1 = -1, hi2 = -1;
@@ -477,7 +562,23 @@ __global__ void __launch_bounds__(256) k_dilate_bbox(const uint32_t *__restrict_
         keep[word] = k;
         Qm1 = Q0; PF0 = PF1; Q0 = Q1; c0 = c1;
       }
-      const uint32_t bb = __ldg(bright_src + word) & k;
+      const uint32_t bw = __ldg(bright_src + word);
+      if (ip.mb) {
+        const uint32_t m = ip.mb[word];
+        uint32_t t = ip.classic ? (m & ~bw) : (m | bw);
+        t = (t & k) | (~k & ip.cM);
+        uint32_t fm = 0xffffffffu;
+        if (!(y == 0 || y == g.ny - 1 || z == 0 || z == g.nz - 1)) {
+          fm = xw == 0 ? 1u : 0u;
+          const int lastb = g.nx - 1 - xw * 32;
+          if (lastb >= 0 && lastb < 32) fm |= 1u << lastb;
+        }
+        t = ip.classic ? (t | (fm & ip.cE)) : (t & (~fm | ip.cE));
+        const int nb = g.nx - xw * 32;
+        if (nb < 32) t &= (1u << nb) - 1u;
+        ip.mb[word] = t;
+      }
+      const uint32_t bb = bw & k;
       if (bb) {
         lo0 = min(lo0, xw * 32 + __ffs(bb) - 1);
         hi0 = max(hi0, xw * 32 + 31 - __clz(bb));
@@ -530,17 +631,29 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
   return B2M_OK;
 }
 
-static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2 *nodes, int conn) {
+static unsigned cc_list_cap(const cc_geom &cg) { return (unsigned)(cg.nwords / 4 + 4096); }
+
+// labelling + number of components (*nroots) + largest component (*best, optional)
+static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2 *nodes, int conn, unsigned long long *best,
+                    unsigned int *nroots) {
   unsigned blocks = b2m_cdiv(cg.nwords, 256);
   dim3 tiles(b2m_cdiv(cg.w, CT_W), b2m_cdiv(cg.ny, CT_Y), b2m_cdiv(cg.nz, CT_Z));
+  const unsigned rcap = cc_list_cap(cg);
+  B2M_TRY(b2m_reserve(ctx, BUF_CCLIST, ((size_t)rcap + 1) * 4));
+  uint32_t *rlist = b2m_ptr<uint32_t>(ctx, BUF_CCLIST);
+  CU_TRY(cudaMemsetAsync(rlist, 0, 4, ctx->stream));
   if (conn >= 18) {
-    KT_LAUNCH(ctx, "cc_local", k_cc_local<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_local", k_cc_local<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
     KT_LAUNCH(ctx, "cc_border", k_cc_border<18><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
   } else {
-    KT_LAUNCH(ctx, "cc_local", k_cc_local<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_local", k_cc_local<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
     KT_LAUNCH(ctx, "cc_border", k_cc_border<6><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
   }
-  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
+  const unsigned lblocks = b2m_cdiv(rcap, 256);
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes));
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
+  KT_LAUNCH(ctx, "cc_best", k_cc_best_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes, best, nroots));
+  KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes, best, nroots, rlist, rcap));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -886,7 +999,10 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     B2M_TRY(b2m_reserve(ctx, BUF_BG, wbytes));
     bg = b2m_ptr<uint32_t>(ctx, BUF_BG);
   }
-  B2M_TRY(b2m_threshold_run(ctx, fo->S, g, fo->iso, fg, bg));  // all EXT planes: the halo bits equal the neighbour's
+  B2M_TRY(b2m_reserve(ctx, BUF_MB, wbytes));
+  uint32_t *mb = b2m_ptr<uint32_t>(ctx, BUF_MB);
+  const int classic = o->backend == B2M_BACKEND_CLASSIC;
+  B2M_TRY(b2m_threshold_run(ctx, fo->S, g, fo->iso, fg, bg, mb, classic));  // all EXT planes: the halo bits equal the neighbour's
   fo->fill = nullptr;
   fo->keep = nullptr;
   const uint32_t *bright = fg;
@@ -909,8 +1025,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   if (o->fill_bubbles) {
     B2M_TRY(b2m_reserve(ctx, BUF_FILL, wbytes));
     uint32_t *fill = b2m_ptr<uint32_t>(ctx, BUF_FILL);
-    B2M_TRY(cc_label(ctx, bg + own_off, cg, nodes, 6));
-    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bg + own_off, own_words, nodes, nullptr, &d_sc->nroots_bg));
+    B2M_TRY(cc_label(ctx, bg + own_off, cg, nodes, 6, nullptr, &d_sc->nroots_bg));
     long long nroots_ovr = -1;
     if (slabs) {
       seam_result sr;
@@ -931,8 +1046,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     B2M_TRY(b2m_reserve(ctx, BUF_KEEP, wbytes));
     largest = b2m_ptr<uint32_t>(ctx, BUF_LARGEST);
     keep = b2m_ptr<uint32_t>(ctx, BUF_KEEP);
-    B2M_TRY(cc_label(ctx, bright + own_off, cg, nodes, 18));
-    KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bright + own_off, own_words, nodes, &d_sc->best_fg, &d_sc->nroots_fg));
+    B2M_TRY(cc_label(ctx, bright + own_off, cg, nodes, 18, &d_sc->best_fg, &d_sc->nroots_fg));
     long long sel = -2;
     if (slabs) {
       seam_result sr;
@@ -967,9 +1081,22 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     const long long shift = (long long)sl.ez0 * (long long)pw;
     cc_geom dg = {g.nx, g.ny, sl.gnz, g.w, 0, 1, 1};
     dim3 dgrid(b2m_cdiv((size_t)g.ny * g.w, 256), b2m_cdiv(sl.nzl, DIL_ZC));
+    ibits_params ip;
+    ip.mb = mb - shift;
+    ip.classic = classic;
+    if (classic) {
+      ip.cM = fo->vmin < fo->iso ? 0xffffffffu : 0u;
+      ip.cE = fo->edge_max < fo->iso ? 0xffffffffu : 0u;
+    } else {
+      const float dm = fo->vmin - fo->iso, de = fo->edge_max - fo->iso;  // f32 subtractions, as mc_inside_at
+      ip.cM = dm > -FLT_EPSILON ? 0xffffffffu : 0u;
+      ip.cE = de > -FLT_EPSILON ? 0xffffffffu : 0u;
+    }
     KT_LAUNCH(ctx, "dilate_bbox", k_dilate_bbox<<<dgrid, 256, 0, ctx->stream>>>(largest ? largest - shift : nullptr, bright - shift, dg, sl.z0, sl.z0 + sl.nzl,
-                                                                              keep ? keep - shift : nullptr, d_sc->lo));
+                                                                              keep ? keep - shift : nullptr, d_sc->lo, ip));
     if (keep) B2M_TRY(halo_bits(keep));
+    B2M_TRY(halo_bits(mb));
+    fo->ibits = mb;
   }
   CU_TRY(cudaGetLastError());
   return B2M_OK;

@@ -39,6 +39,8 @@ enum {
   BUF_FILL,        // fg | bubbles
   BUF_LARGEST,     // largest 18-connected cluster bits
   BUF_KEEP,        // largest | dilate25(largest)
+  BUF_CCLIST,      // CC: [count, tile-root slots...]
+  BUF_MB,          // marching-cubes inside bits (threshold -> composed in place by k_dilate_bbox)
   BUF_NODES,       // union-find nodes (uint2 {parent, size|faceflag}) : 16 per bit word
   BUF_SCALARS,     // small device scalar block (b2m_scalars)
   BUF_SEG,         // MC per-32-voxel segment records (uint4 {xbits,ybits,zbits,vbase})
@@ -267,12 +269,16 @@ struct smooth_src {
 };
 int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc);
 int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, size_t n, b2m_scalars *d_sc);
-int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg);
+// fg = v >= iso, bg = its complement (optional), mb = the marching-cubes comparison (optional):
+// Lewiner v - iso > -FLT_EPSILON (src/MarchingCubes.c:132-133 after :1112), classic v < iso (src/oldcubes.c:407-414)
+int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg,
+                      uint32_t *d_mb, int classic);
 
 struct b2m_front_out {
   const float *S;          // smoothed (or original) volume, EXT layout
   const uint32_t *fill;    // nullptr or fg|bubbles bit rows, EXT layout
   const uint32_t *keep;    // nullptr or largest|dilated bit rows, EXT layout
+  const uint32_t *ibits;   // marching-cubes inside bit of every voxel of the composed volume, EXT layout
   float iso, vmin, vmax, edge_max;
   int lo[3], hi[3];        // widened bbox as handed to marching cubes (global)
   int iso_reset;

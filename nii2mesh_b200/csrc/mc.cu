@@ -36,10 +36,14 @@ struct mc_params {
                     // the last one is the next rank's first plane, received after the scan)
   int segs;         // 32-voxel segments per sub-volume row
   float pad;        // Lewiner: value of sub-volume voxels that fall outside the volume (already - iso)
+  unsigned pad_inside;  // its inside bit
+  int closed;           // slabs: faces are strictly outside, so every wrapped voxel is outside too and is never read
+                        // (its plane may not be on this rank)
   int classic;      // backend == CLASSIC
   int original_mc;
   const signed char *tab;
   const uint32_t *lutinfo;  // 256 entries: Lewiner MC33, or the classic table when classic / originalMC
+  const uint32_t *ibits;    // inside bit per voxel of the composed volume (bit rows, indexed with global z)
   uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks, .w = packed counts -> vertex base (scan3)
   uint32_t *segt, *segc;  // per segment exclusive triangle / centroid-vertex bases
   uint4 *active;
@@ -211,231 +215,181 @@ __device__ __noinline__ void mc33_select(const signed char *__restrict__ tab, co
 }
 
 // ---- pass A: classify ------------------------------------------------------------------------
-// Warps are independent (no barriers): a warp owns 32 x-columns x MCC_ROWS rows of the sub-volume
-// and marches along z.  Per plane every lane evaluates the inside/outside BIT of its column for
-// MCC_ROWS+1 rows (9 independent loads in flight), so classification works on four 9-bit masks
-// per lane (this plane / next plane, own column / x+1 column via one shuffle); corner VALUES are
-// only re-read for the rare ambiguous MC33 cubes.  Active voxels are appended to a warp-private
-// shared-memory buffer and flushed to the global list with one atomic per ~100 records (a
-// same-address atomic per warp-row serialises in L2 and dominated the first version).
-// Per 32-voxel segment the kernel leaves {xbits, ybits, zbits, packed counts}; packed counts =
-// nv | nt << 7 | nc << 16 (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.
-#define MCC_ROWS 8
-#define MCC_WARPS 4
-#define MCC_ZC 64
-#define MCC_BUF 160
+// Works on BITS, 32 cubes per thread.  The front end leaves one "inside" bit per voxel of the composed volume
+// (p.ibits: threshold at the marching-cubes comparison, bubble fill, largest-cluster mask and face darkening
+// folded in at word level, cc.cu:k_dilate_bbox), so a thread classifies a 32-voxel segment of a sub-volume row
+// with a few word operations: edge-vertex masks are XORs of neighbouring rows, the active-cube mask is
+// OR & ~AND of the eight corner words.  A thread owns one (row y, segment) column and marches along z, keeping
+// the two rows of the current plane in registers.  Only ACTIVE voxels (~5 %) cost per-voxel work: cube index
+// from the eight words -> per-lut summary table; corner VALUES are read only for the ambiguous MC33 cases.
+// Per segment the kernel leaves {xbits, ybits, zbits, packed counts}; packed counts = nv | nt << 7 | nc << 16
+// (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.  Active voxels are appended to a
+// warp-private shared-memory buffer and flushed to the global list with one atomic per ~150 records.
+#define MCB_THREADS 128
+#define MCB_ZC 32
+#define MCB_BUF 192
 
-__device__ __forceinline__ bool mc_inside_at(const mc_params &p, int x, int y, int z) {
-  // inside/outside bit of sub-volume voxel (x,y,z): identical to mc_inside(mc_data()) with a short
-  // path for voxels inside the volume (no wrap, no pad)
-  const int gx = p.lo0 + x, gy = p.lo1 + y, gz = p.lo2 + z;
-  if (gx < p.c.nx && gy < p.c.ny && gz < p.c.nz) {
-    const float v = composed_value(p.c, gx, gy, gz);
-    return p.classic ? (v < p.c.iso) : (__fsub_rn(v, p.c.iso) > -FLT_EPSILON);
-  }
-  return mc_inside(p, mc_data(p, x, y, z));
+// inside bit of one sub-volume voxel given in VOLUME coordinates that may lie one column / row / plane beyond
+// the volume: the reference's linear-index arithmetic wraps the extra column into the next row and the extra row
+// into the next plane; only the extra plane is padding (src/MarchingCubes.c:1106-1115)
+__device__ __forceinline__ uint32_t mc_inside_bit_wrapped(const mc_params &p, int gx, int gy, int gz) {
+  if (gx >= p.c.nx) { if (p.closed) return 0u; gx -= p.c.nx; gy++; }
+  if (gy >= p.c.ny) { if (p.closed) return 0u; gy -= p.c.ny; gz++; }
+  if (gz >= p.c.nz) return p.pad_inside;
+  return (__ldg(p.ibits + ((size_t)gz * p.c.ny + gy) * p.c.w + (gx >> 5)) >> (gx & 31)) & 1u;
 }
 
-// 9-bit inside masks of plane z for this lane's column (rows ybase..ybase+8) and for column x+1.
-// Generic version: every bounds / wrap / pad case (boundary warps only).
-__device__ __noinline__ unsigned mc_plane_masks_slow(const mc_params &p, int seg, int ybase, int z, unsigned lane,
-                                                     unsigned &mx) {
-  const int x = seg * 32 + (int)lane;
-  unsigned m = 0;
-  if (z < p.sz) {
-    if (x < p.sx) {
-      for (int r = 0; r <= MCC_ROWS; r++)
-        if (ybase + r < p.sy) m |= (mc_inside_at(p, x, ybase + r, z) ? 1u : 0u) << r;
-    }
+// the 33 inside bits of sub-volume row (y, z) that start at sub-volume x = seg*32: bits 0..31 -> lo, bit 32 -> hi
+// (zero beyond the sub-volume)
+__device__ __forceinline__ void mc_inside_row(const mc_params &p, int seg, int y, int z, uint32_t &lo, uint32_t &hi) {
+  lo = 0u; hi = 0u;
+  if (y >= p.sy || z >= p.sz) return;
+  const int nsub = min(33, p.sx - seg * 32);
+  const int gx0 = p.lo0 + seg * 32;
+  int gy = p.lo1 + y, gz = p.lo2 + z;
+  if (gy >= p.c.ny) { if (p.closed) return; gy -= p.c.ny; gz++; }  // the wrapped extra row
+  if (gz >= p.c.nz) {                         // the padded extra plane
+    if (p.pad_inside) { lo = nsub >= 32 ? 0xffffffffu : ((1u << nsub) - 1u); hi = nsub >= 33; }
+    return;
   }
-  bool hin = false;
-  const int xe = seg * 32 + 32;
-  if (lane <= MCC_ROWS && z < p.sz && xe < p.sx && ybase + (int)lane < p.sy) hin = mc_inside_at(p, xe, ybase + (int)lane, z);
-  const unsigned hm = __ballot_sync(0xffffffffu, hin);
-  mx = __shfl_down_sync(0xffffffffu, m, 1);
-  if (lane == 31) mx = hm;
-  return m;
+  const int nin = min(nsub, p.c.nx - gx0);    // span bits that lie inside this volume row
+  if (nin > 0) {
+    const uint32_t *r = p.ibits + ((size_t)gz * p.c.ny + gy) * p.c.w;
+    const int wi = gx0 >> 5, sh = gx0 & 31;
+    const uint32_t w0 = __ldg(r + wi);
+    const uint32_t w1 = (wi + 1 < p.c.w) ? __ldg(r + wi + 1) : 0u;
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = (w1 >> sh) & 1u;
+    if (nin < 33) { hi = 0u; if (nin < 32) lo &= (1u << nin) - 1u; }
+  }
+  for (int b = nin > 0 ? nin : 0; b < nsub; b++) {  // at most the one wrapped extra column
+    const uint32_t in = mc_inside_bit_wrapped(p, gx0 + b, gy, gz);
+    if (b < 32) lo |= in << b; else hi = in;
+  }
 }
 
-// inside bit of one in-volume voxel: S value, optional fill / keep bit-row words (offset `wo` from the
-// array base), face darkening.  FILL/KEEP are compile-time so that no null pointer is ever formed.
-template <bool FILL, bool KEEP>
-__device__ __forceinline__ bool mc_inside_fast(const mc_params &p, const float *__restrict__ sp,
-                                               const uint32_t *__restrict__ fp, const uint32_t *__restrict__ kp,
-                                               unsigned bit, bool face) {
-  float v = __ldg(sp);
-  if (FILL) { if ((__ldg(fp) >> bit) & 1u) v = fmaxf(v, p.c.iso); }
-  if (KEEP) { if (!((__ldg(kp) >> bit) & 1u)) v = p.c.mn; }
-  if (face) v = fminf(p.c.edge_max, v);
-  return p.classic ? (v < p.c.iso) : (__fsub_rn(v, p.c.iso) > -FLT_EPSILON);
+__device__ __forceinline__ void mc_flush(const mc_params &p, uint4 *mybuf, unsigned cnt, unsigned lane) {
+  __syncwarp();
+  unsigned base = 0;
+  if (lane == 0) {
+    base = atomicAdd(&p.sc->n_active, cnt);
+    if (base + cnt > p.active_cap) atomicOr(&p.sc->overflow, 1u);
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (unsigned i = lane; i < cnt; i += 32)
+    if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
+  __syncwarp();
 }
 
-// interior: all 33 columns, 9 rows and the plane lie inside the sub-volume AND the volume (warp-uniform
-// test), so there is no wrap/pad and the addresses advance by constant strides.  FILL/KEEP are
-// compile-time so that no pointer is formed from an absent (null) bit-row array.
-template <bool FILL, bool KEEP>
-__device__ __forceinline__ unsigned mc_plane_masks_fast(const mc_params &p, int seg, int ybase, int z, unsigned lane,
-                                                        unsigned &mx) {
-  const int gz = p.lo2 + z;
-  const int gx = p.lo0 + seg * 32 + (int)lane, gy0 = p.lo1 + ybase;
-  const size_t row0 = (size_t)gz * p.c.ny + gy0;
-  const float *sp = p.c.S + row0 * p.c.nx + gx;
-  const uint32_t *fp = FILL ? p.c.fill + row0 * p.c.w + (gx >> 5) : p.c.fill;
-  const uint32_t *kp = KEEP ? p.c.keep + row0 * p.c.w + (gx >> 5) : p.c.keep;
-  const bool zxface = gz == 0 || gz == p.c.nz - 1 || gx == 0 || gx == p.c.nx - 1;
-  const int ylast = p.c.ny - 1 - gy0;  // row r is the y = ny-1 face when r == ylast
-  unsigned m = 0;
-#pragma unroll
-  for (int r = 0; r <= MCC_ROWS; r++) {
-    const bool face = zxface || (r == 0 && gy0 == 0) || r == ylast;
-    const bool in = mc_inside_fast<FILL, KEEP>(p, sp, fp, kp, (unsigned)gx & 31u, face);
-    m |= (in ? 1u : 0u) << r;
-    sp += p.c.nx;
-    if (FILL) fp += p.c.w;
-    if (KEEP) kp += p.c.w;
-  }
-  // halo column x = seg*32 + 32: lane r evaluates row r
-  bool hin = false;
-  if (lane <= MCC_ROWS) {
-    const int hx = p.lo0 + seg * 32 + 32;
-    const size_t hrow = row0 + lane;
-    const bool face = gz == 0 || gz == p.c.nz - 1 || hx == 0 || hx == p.c.nx - 1 || gy0 + (int)lane == 0 ||
-                      gy0 + (int)lane == p.c.ny - 1;
-    hin = mc_inside_fast<FILL, KEEP>(p, p.c.S + hrow * p.c.nx + hx, FILL ? p.c.fill + hrow * p.c.w + (hx >> 5) : p.c.fill,
-                                     KEEP ? p.c.keep + hrow * p.c.w + (hx >> 5) : p.c.keep, (unsigned)hx & 31u, face);
-  }
-  const unsigned hm = __ballot_sync(0xffffffffu, hin);
-  mx = __shfl_down_sync(0xffffffffu, m, 1);
-  if (lane == 31) mx = hm;
-  return m;
-}
-
-__device__ __forceinline__ unsigned mc_plane_masks(const mc_params &p, int seg, int ybase, int z, unsigned lane,
-                                                   unsigned &mx, bool interior_xy) {
-  if (!(interior_xy && z < p.sz && p.lo2 + z < p.c.nz)) return mc_plane_masks_slow(p, seg, ybase, z, lane, mx);
-  if (p.c.fill) {
-    if (p.c.keep) return mc_plane_masks_fast<true, true>(p, seg, ybase, z, lane, mx);
-    return mc_plane_masks_fast<true, false>(p, seg, ybase, z, lane, mx);
-  }
-  if (p.c.keep) return mc_plane_masks_fast<false, true>(p, seg, ybase, z, lane, mx);
-  return mc_plane_masks_fast<false, false>(p, seg, ybase, z, lane, mx);
-}
-
-__global__ void __launch_bounds__(32 * MCC_WARPS) k_mc_classify(const __grid_constant__ mc_params p) {
-  __shared__ uint4 rbuf[MCC_WARPS][MCC_BUF];
+__global__ void __launch_bounds__(MCB_THREADS) k_mc_classify(const __grid_constant__ mc_params p) {
+  __shared__ uint4 rbuf[MCB_THREADS / 32][MCB_BUF];
   const unsigned lane = threadIdx.x & 31;
-  const int wrp = threadIdx.x >> 5;
-  const int seg = blockIdx.x;
-  const int ybase = (blockIdx.y * MCC_WARPS + wrp) * MCC_ROWS;
-  if (ybase >= p.sy) return;  // whole warp; no block-level barriers in this kernel
-  const int z0 = p.zs0 + blockIdx.z * MCC_ZC;
-  const int z1 = min(z0 + MCC_ZC, p.zs0 + p.zn);
-  const int x = seg * 32 + (int)lane;
-  const bool vx = x < p.sx, vx1 = x + 1 < p.sx;
-  const int nyv = min(MCC_ROWS + 1, p.sy - ybase);             // valid rows among the 9
-  const unsigned rowsv = (1u << min(nyv, MCC_ROWS)) - 1u;      // rows r < 8 that exist
-  const unsigned vy1m = (1u << (nyv - 1)) - 1u;                // rows r whose r+1 exists
-  uint4 *mybuf = rbuf[wrp];
+  uint4 *mybuf = rbuf[threadIdx.x >> 5];
+  const long long ncol = (long long)p.sy * p.segs;
+  const long long col = (long long)blockIdx.x * MCB_THREADS + threadIdx.x;  // (row y, segment) column
+  const bool live = col < ncol;
+  const int y = live ? (int)(col / p.segs) : 0;
+  const int seg = live ? (int)(col - (long long)y * p.segs) : 0;
+  const int z0 = p.zs0 + blockIdx.y * MCB_ZC;
+  const int z1 = min(z0 + MCB_ZC, p.zs0 + p.zn);
+  const int xb0 = seg * 32;
+  const int nvx = live ? min(32, p.sx - xb0) : 0;        // voxels of this segment
+  const int nvx1 = live ? min(32, p.sx - 1 - xb0) : 0;   // ... whose x+1 neighbour exists
+  const uint32_t vxm = nvx >= 32 ? 0xffffffffu : ((1u << nvx) - 1u);
+  const uint32_t vx1m = nvx1 >= 32 ? 0xffffffffu : (nvx1 > 0 ? ((1u << nvx1) - 1u) : 0u);
+  const bool vy1 = y + 1 < p.sy;
+  uint32_t a = 0, ah = 0, b = 0, bh = 0;  // plane z: row y, row y+1 (h = bit 32 of the span)
+  if (live) {
+    mc_inside_row(p, seg, y, z0, a, ah);
+    mc_inside_row(p, seg, y + 1, z0, b, bh);
+  }
   unsigned cnt = 0;  // records parked in mybuf (warp-uniform)
   unsigned long long first = ~0ull;
-  unsigned a, b;     // plane z: own column, x+1 column
-  // warp-uniform: the 33 columns and 9 rows this warp touches exist in the sub-volume and in the volume
-  const bool interior_xy = seg * 32 + 32 < p.sx && p.lo0 + seg * 32 + 32 < p.c.nx && ybase + MCC_ROWS < p.sy &&
-                           p.lo1 + ybase + MCC_ROWS < p.c.ny;
-  a = mc_plane_masks(p, seg, ybase, z0, lane, b, interior_xy);
   for (int z = z0; z < z1; z++) {
-    unsigned c, d;   // plane z+1
-    c = mc_plane_masks(p, seg, ybase, z + 1, lane, d, interior_xy);
+    uint32_t c = 0, ch = 0, d = 0, dh = 0;  // plane z+1
+    if (live) {
+      mc_inside_row(p, seg, y, z + 1, c, ch);
+      mc_inside_row(p, seg, y + 1, z + 1, d, dh);
+    }
     const bool vz1 = z + 1 < p.sz;
-    const unsigned exm = (vx && vx1) ? ((a ^ b) & rowsv) : 0u;
-    const unsigned eym = vx ? ((a ^ (a >> 1)) & vy1m) : 0u;
-    const unsigned ezm = (vx && vz1) ? ((a ^ c) & rowsv) : 0u;
-    const unsigned orm = a | (a >> 1) | b | (b >> 1) | c | (c >> 1) | d | (d >> 1);
-    const unsigned andm = a & (a >> 1) & b & (b >> 1) & c & (c >> 1) & d & (d >> 1);
-    const unsigned trim = (vx1 && vz1) ? ((orm & ~andm) & vy1m) : 0u;
-    const unsigned rows_active = __reduce_or_sync(0xffffffffu, exm | eym | ezm | trim);
-    uint4 *segrow = p.segbits + ((size_t)(z - p.zs0) * p.sy + ybase) * p.segs + seg;  // + r * p.segs per row
-    if (lane < MCC_ROWS && ((rowsv & ~rows_active) >> lane) & 1u) segrow[(size_t)lane * p.segs] = make_uint4(0u, 0u, 0u, 0u);
-    for (unsigned ra = rows_active; ra; ra &= ra - 1) {
-      const int r = __ffs(ra) - 1;
-      const size_t row = (size_t)(z - p.zs0) * p.sy + ybase + r;  // local row (segment arrays of this rank)
-      const bool ex = (exm >> r) & 1u, ey = (eym >> r) & 1u, ez = (ezm >> r) & 1u, tri = (trim >> r) & 1u;
-      int ntri = 0, hasc = 0, off = 0, lut = 0;
-      if (tri) {
-        // corner bits: p0=a_r p1=b_r p2=b_{r+1} p3=a_{r+1} p4=c_r p5=d_r p6=d_{r+1} p7=c_{r+1}
-        const unsigned pa = (a >> r) & 3u, pb = (b >> r) & 3u, pc2 = (c >> r) & 3u, pd = (d >> r) & 3u;
-        lut = (int)(((pa & 1u) | ((pa & 2u) << 2) | (pb << 1)) | (((pc2 & 1u) | ((pc2 & 2u) << 2) | (pd << 1)) << 4));
-        const uint32_t info = __ldg(p.lutinfo + lut);
-        if (info >> 31) {  // ambiguous MC33 case: the face / interior tests need the corner values
-          const int y = ybase + r;
-          float cv[8];
-          cv[0] = mc_data(p, x, y, z); cv[1] = mc_data(p, x + 1, y, z); cv[2] = mc_data(p, x + 1, y + 1, z);
-          cv[3] = mc_data(p, x, y + 1, z); cv[4] = mc_data(p, x, y, z + 1); cv[5] = mc_data(p, x + 1, y, z + 1);
-          cv[6] = mc_data(p, x + 1, y + 1, z + 1); cv[7] = mc_data(p, x, y + 1, z + 1);
-          mc33_select(p.tab, cv, lut, 0, off, ntri, hasc);
-        } else {
-          off = (int)(info & 0xffffu);
-          ntri = (int)(info >> 16);
-        }
-      }
-      const unsigned xb = __ballot_sync(0xffffffffu, ex), yb = __ballot_sync(0xffffffffu, ey), zb = __ballot_sync(0xffffffffu, ez);
-      const int nv = (int)ex + (int)ey + (int)ez;
-      const int pk = nv | (ntri << 7) | (hasc << 16);
-      int incl = pk;
+    const uint32_t ax = (a >> 1) | (ah << 31), bx = (b >> 1) | (bh << 31);
+    const uint32_t cx = (c >> 1) | (ch << 31), dx = (d >> 1) | (dh << 31);
+    const uint32_t exm = (a ^ ax) & vx1m;
+    const uint32_t eym = vy1 ? ((a ^ b) & vxm) : 0u;
+    const uint32_t ezm = vz1 ? ((a ^ c) & vxm) : 0u;
+    const uint32_t orm = a | ax | b | bx | c | cx | d | dx, andm = a & ax & b & bx & c & cx & d & dx;
+    const uint32_t trim = (vy1 && vz1) ? ((orm & ~andm) & vx1m) : 0u;
+    const uint32_t actm = exm | eym | ezm | trim;
+    // where this lane's records go: warp-wide exclusive prefix of the record counts
+    const unsigned n = __popc(actm);
+    unsigned incl = n;
 #pragma unroll
-      for (int dd = 1; dd < 32; dd <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, dd);
-        if (lane >= (unsigned)dd) incl += t;
-      }
-      const int tot = __shfl_sync(0xffffffffu, incl, 31);
-      const int excl = incl - pk;
-      if (lane == 0) segrow[(size_t)r * p.segs] = make_uint4(xb, yb, zb, (uint32_t)tot);
-      if (p.classic && ntri > 0) {
-        unsigned long long key = ((unsigned long long)((size_t)z * p.sy + ybase + r) << 16) | (unsigned long long)x;
-        first = key < first ? key : first;
-      }
-      const bool act = nv > 0 || ntri > 0;
-      const unsigned am = __ballot_sync(0xffffffffu, act);
-      const unsigned n = __popc(am);
-      if (cnt + n > MCC_BUF) {  // flush the warp-private buffer
-        __syncwarp();
-        unsigned base = 0;
-        if (lane == 0) {
-          base = atomicAdd(&p.sc->n_active, cnt);
-          if (base + cnt > p.active_cap) atomicOr(&p.sc->overflow, 1u);
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (unsigned i = lane; i < cnt; i += 32)
-          if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
-        __syncwarp();
+    for (int dd = 1; dd < 32; dd <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, dd);
+      if (lane >= (unsigned)dd) incl += t;
+    }
+    const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+    const size_t row = (size_t)(z - p.zs0) * p.sy + y;  // local row (segment arrays of this rank)
+    uint32_t packed = 0;
+    if (tot) {
+      bool direct = false;
+      unsigned gbase = 0;
+      if (cnt + tot > MCB_BUF) {
+        if (cnt) mc_flush(p, mybuf, cnt, lane);
         cnt = 0;
+        if (tot > MCB_BUF) {  // a plane with more records than the buffer holds: straight to the global list
+          direct = true;
+          if (lane == 0) {
+            gbase = atomicAdd(&p.sc->n_active, tot);
+            if (gbase + tot > p.active_cap) atomicOr(&p.sc->overflow, 1u);
+          }
+          gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        }
       }
-      if (act) {
-        const int pv = excl & 127, pt = (excl >> 7) & 511, pc = (excl >> 16) & 63;
+      unsigned slot = (direct ? gbase : cnt) + (incl - n);
+      int pv = 0, pt = 0, pc = 0;
+      for (uint32_t rest = actm; rest; rest &= rest - 1) {
+        const int bb = __ffs(rest) - 1;
+        const uint32_t ex = (exm >> bb) & 1u, ey = (eym >> bb) & 1u, ez = (ezm >> bb) & 1u;
+        int ntri = 0, hasc = 0, off = 0, lut = 0;
+        const int x = xb0 + bb;
+        if ((trim >> bb) & 1u) {
+          lut = (int)(((a >> bb) & 1u) | (((ax >> bb) & 1u) << 1) | (((bx >> bb) & 1u) << 2) | (((b >> bb) & 1u) << 3) |
+                      (((c >> bb) & 1u) << 4) | (((cx >> bb) & 1u) << 5) | (((dx >> bb) & 1u) << 6) | (((d >> bb) & 1u) << 7));
+          const uint32_t info = __ldg(p.lutinfo + lut);
+          if (info >> 31) {  // ambiguous MC33 case: the face / interior tests need the corner values
+            float cv[8];
+            cv[0] = mc_data(p, x, y, z); cv[1] = mc_data(p, x + 1, y, z); cv[2] = mc_data(p, x + 1, y + 1, z);
+            cv[3] = mc_data(p, x, y + 1, z); cv[4] = mc_data(p, x, y, z + 1); cv[5] = mc_data(p, x + 1, y, z + 1);
+            cv[6] = mc_data(p, x + 1, y + 1, z + 1); cv[7] = mc_data(p, x, y + 1, z + 1);
+            mc33_select(p.tab, cv, lut, 0, off, ntri, hasc);
+          } else {
+            off = (int)(info & 0xffffu);
+            ntri = (int)(info >> 16);
+          }
+          if (p.classic && ntri > 0) {
+            const unsigned long long key = ((unsigned long long)((size_t)z * p.sy + y) << 16) | (unsigned long long)x;
+            first = key < first ? key : first;
+          }
+        }
         uint4 rec;
         rec.x = (uint32_t)row;
-        rec.y = (uint32_t)x | ((uint32_t)ex << 16) | ((uint32_t)ey << 17) | ((uint32_t)ez << 18) | ((uint32_t)ntri << 19) |
-                ((uint32_t)hasc << 23) | ((uint32_t)pc << 24);
+        rec.y = (uint32_t)x | (ex << 16) | (ey << 17) | (ez << 18) | ((uint32_t)ntri << 19) | ((uint32_t)hasc << 23) |
+                ((uint32_t)pc << 24);
         rec.z = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)off << 16);
         rec.w = (uint32_t)lut;
-        mybuf[cnt + __popc(am & ((1u << lane) - 1u))] = rec;
+        if (direct) { if (slot < p.active_cap) p.active[slot] = rec; }
+        else mybuf[slot] = rec;
+        slot++;
+        pv += (int)(ex + ey + ez); pt += ntri; pc += hasc;
       }
-      cnt += n;
+      packed = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)pc << 16);
+      if (!direct) cnt += tot;
     }
-    a = c;
-    b = d;
+    if (live) p.segbits[row * p.segs + seg] = make_uint4(exm, eym, ezm, packed);
+    a = c; ah = ch; b = d; bh = dh;
   }
-  __syncwarp();
-  if (cnt) {
-    unsigned base = 0;
-    if (lane == 0) {
-      base = atomicAdd(&p.sc->n_active, cnt);
-      if (base + cnt > p.active_cap) atomicOr(&p.sc->overflow, 1u);
-    }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (unsigned i = lane; i < cnt; i += 32)
-      if (base + i < p.active_cap) p.active[base + i] = mybuf[i];
-  }
+  if (cnt) mc_flush(p, mybuf, cnt, lane);
   if (p.classic) {  // first active cube in raster order: its first soup vertex is the weld's pts[0]
 #pragma unroll
     for (int dd = 16; dd; dd >>= 1) {
@@ -622,7 +576,7 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
   c[1] = vx1 ? mc_data(p, x + 1, y, z) : c[0];
   c[3] = vy1 ? mc_data(p, x, y + 1, z) : c[0];
   c[4] = vz1 ? mc_data(p, x, y, z + 1) : c[0];
-  if (ntri) {
+  if (ntri && (p.classic || hasc)) {  // Lewiner needs the far corners only for a centroid vertex
     c[2] = mc_data(p, x + 1, y + 1, z);
     c[5] = mc_data(p, x + 1, y, z + 1);
     c[6] = mc_data(p, x + 1, y + 1, z + 1);
@@ -695,8 +649,10 @@ __global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) 
   // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
   const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
   uint32_t ev[13];
-  const bool in0 = mc_inside(p, c[0]), in1 = mc_inside(p, c[1]), in2 = mc_inside(p, c[2]), in3 = mc_inside(p, c[3]);
-  const bool in4 = mc_inside(p, c[4]), in5 = mc_inside(p, c[5]), in6 = mc_inside(p, c[6]), in7 = mc_inside(p, c[7]);
+  // inside bits of the corners = the cube index the classify pass built from the inside-bit rows
+  const unsigned lut = r.w;
+  const bool in0 = lut & 1u, in1 = (lut >> 1) & 1u, in2 = (lut >> 2) & 1u, in3 = (lut >> 3) & 1u;
+  const bool in4 = (lut >> 4) & 1u, in5 = (lut >> 5) & 1u, in6 = (lut >> 6) & 1u, in7 = (lut >> 7) & 1u;
   ev[0] = in0 != in1 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
   ev[1] = in1 != in2 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
   ev[2] = in3 != in2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
@@ -847,6 +803,7 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   p.c.S = fo->S - vshift;
   p.c.fill = fo->fill ? fo->fill - wshift : nullptr;
   p.c.keep = fo->keep ? fo->keep - wshift : nullptr;
+  p.ibits = fo->ibits - wshift;
   p.c.nx = g.nx; p.c.ny = g.ny; p.c.nz = sl.gnz; p.c.w = g.w;
   p.c.iso = fo->iso; p.c.mn = fo->vmin; p.c.edge_max = fo->edge_max;
   p.classic = o->backend == B2M_BACKEND_CLASSIC;
@@ -879,6 +836,13 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   p.pad = fo->vmin - fo->iso;
   if (!p.classic) {
     bool touched = fo->hi[0] == g.nx || fo->hi[1] == g.ny || fo->hi[2] == sl.gnz;
+    const float de = fo->edge_max - fo->iso;
+    if (W > 1 && touched && de > -FLT_EPSILON) {
+      // the wrapped extra column / row of the reference would reach two planes ahead
+      b2m_set_error("slab mode needs darkened faces below the isolevel (edge_max %g >= iso %g)", fo->edge_max, fo->iso);
+      return B2M_EARG;
+    }
+    p.closed = W > 1;
     if (touched && !(fo->edge_max < fo->iso)) {
       if (W > 1) {
         // the wrapped extra column / row of the reference would reach two planes ahead
@@ -891,6 +855,11 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
       B2M_TRY(b2m_fetch_scalars(ctx));
       p.pad = f32_dec(ctx->h_scalars->cmin_enc) - fo->iso;
     }
+  }
+  {
+    float pv = p.pad;
+    if (fabsf(pv) < FLT_EPSILON) pv = FLT_EPSILON;
+    p.pad_inside = p.classic ? 0u : (pv > 0.0f ? 1u : 0u);
   }
   const size_t prow = (size_t)p.sy * p.segs;          // segments per sub-volume plane
   const size_t nseg = prow * p.zn;                    // own segments
@@ -905,14 +874,14 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   if (cap > nvox) cap = nvox;
   if (cap < 1) cap = 1;
   unsigned n_active = 0;
-  dim3 grid(p.segs, b2m_cdiv(p.sy, MCC_ROWS * MCC_WARPS), b2m_cdiv(p.zn > 0 ? p.zn : 1, MCC_ZC));
+  dim3 grid(b2m_cdiv((size_t)p.sy * p.segs, MCB_THREADS), b2m_cdiv(p.zn > 0 ? p.zn : 1, MCB_ZC));
   // the retry decision must be the same on every rank (collectives follow): overflow anywhere -> all redo
   for (int attempt = 0; attempt < 2; attempt++) {
     B2M_TRY(b2m_reserve(ctx, BUF_ACTIVE, cap * sizeof(uint4)));
     p.active = b2m_ptr<uint4>(ctx, BUF_ACTIVE);
     p.active_cap = (unsigned)cap;
     CU_TRY(cudaMemsetAsync(&d_sc->n_active, 0, 4, ctx->stream));
-    if (p.zn > 0) KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, 32 * MCC_WARPS, 0, ctx->stream>>>(p));
+    if (p.zn > 0) KT_LAUNCH(ctx, "mc_classify", k_mc_classify<<<grid, MCB_THREADS, 0, ctx->stream>>>(p));
     CU_TRY(cudaGetLastError());
     B2M_TRY(mc_scan3_totals(ctx, p, nseg, d_sc));
     B2M_TRY(b2m_sync_scalars(ctx, comm));

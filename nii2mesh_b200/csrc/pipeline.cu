@@ -433,6 +433,12 @@ extern "C" int b2m_stage_mc(b2m_ctx *ctx, const float *d_img, const int64_t dims
     if (lo[a] < 0 || hi[a] > dims[a] || lo[a] > hi[a]) { b2m_set_error("bad bbox"); return B2M_EARG; }
     fo.lo[a] = lo[a]; fo.hi[a] = hi[a];
   }
+  // inside bits of the (already composed) volume: the marching-cubes comparison alone
+  B2M_TRY(b2m_reserve(ctx, BUF_FG, (size_t)g.nwords * 4));
+  B2M_TRY(b2m_reserve(ctx, BUF_MB, (size_t)g.nwords * 4));
+  B2M_TRY(b2m_threshold_run(ctx, d_img, g, fo.iso, b2m_ptr<uint32_t>(ctx, BUF_FG), nullptr, b2m_ptr<uint32_t>(ctx, BUF_MB),
+                            opts->backend == B2M_BACKEND_CLASSIC));
+  fo.ibits = b2m_ptr<uint32_t>(ctx, BUF_MB);
   b2m_mesh_dev mesh;
   memset(&mesh, 0, sizeof(mesh));
   B2M_TRY(stage_begin(ctx, B2M_T_MC));

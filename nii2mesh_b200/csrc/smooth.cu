@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
 // bytes in flight).
 #define THR_WPW 8
 __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
-                                                   float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg) {
+                                                   float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg,
+                                                   uint32_t *__restrict__ mb, int classic) {
   const unsigned lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -329,16 +330,18 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
         v[j] = ok[j] ? __ldg(in + row * nx + x) : 0.f;
       }
     }
-    uint32_t mine_fg = 0, mine_bg = 0;
+    uint32_t mine_fg = 0, mine_bg = 0, mine_mb = 0;
 #pragma unroll
     for (int j = 0; j < THR_WPW; j++) {
       const unsigned m = __ballot_sync(0xffffffffu, ok[j] && v[j] >= iso);
       const unsigned vm = __ballot_sync(0xffffffffu, ok[j]);
-      if (lane == (unsigned)j) { mine_fg = m; mine_bg = ~m & vm; }
+      const unsigned mm = __ballot_sync(0xffffffffu, ok[j] && (classic ? (v[j] < iso) : (__fsub_rn(v[j], iso) > -FLT_EPSILON)));
+      if (lane == (unsigned)j) { mine_fg = m; mine_bg = ~m & vm; mine_mb = mm; }
     }
     if (lane < THR_WPW && w0 + lane < nwords) {
       fg[w0 + lane] = mine_fg;
       if (bg) bg[w0 + lane] = mine_bg;
+      if (mb) mb[w0 + lane] = mine_mb;
     }
   }
 }
@@ -376,12 +379,13 @@ int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, size_t n, b2m_scalars *d_sc)
   return B2M_OK;
 }
 
-int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg) {
+int b2m_threshold_run(b2m_ctx *ctx, const float *d_in, const b2m_geom &g, float iso, uint32_t *d_fg, uint32_t *d_bg,
+                      uint32_t *d_mb, int classic) {
   long long warps = (g.nwords + THR_WPW - 1) / THR_WPW;
   long long blocks = (warps + 7) / 8;
   const long long cap = (long long)ctx->sm_count * 64;  // grid-stride beyond a few waves
   if (blocks > cap) blocks = cap;
-  KT_LAUNCH(ctx, "threshold", k_threshold<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg));
+  KT_LAUNCH(ctx, "threshold", k_threshold<<<(unsigned)blocks, 256, 0, ctx->stream>>>(d_in, g.nx, g.w, g.nwords, iso, d_fg, d_bg, d_mb, classic));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
