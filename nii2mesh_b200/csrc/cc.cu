@@ -30,11 +30,29 @@ struct cc_geom {
 };
 #define CC_SENT 0xffffffffu /* slabs: parent of a seam root that belongs to the selected (largest) component */
 
-__device__ __forceinline__ uint32_t ld_parent(const uint2 *nodes, uint32_t a) {
+// Union-find nodes.  A run's slot id is  word*16 + (ordinal of the run inside its word)  - ordered like the
+// raster order of the runs' first voxels - but the nodes are STORED with every word's first run in a dense
+// array (8 bytes per word, neighbouring words share sectors) and the rare further runs behind it: in smooth
+// volumes nearly every access then lands in the dense part instead of pulling one 32-byte sector per 8-byte node.
+struct cc_nodes {
+  uint2 *p;
+  uint32_t nw;  // words of the labelled region
+  __device__ __forceinline__ uint2 &operator[](uint32_t slot) const {
+    const uint32_t j = slot & 15u, wd = slot >> 4;
+    return p[j ? nw + wd * 15u + (j - 1u) : wd];
+  }
+};
+// slot of the run of word `word` (bits wv) that starts at bit s
+__device__ __forceinline__ uint32_t run_slot(uint32_t word, uint32_t wv, int s) {
+  const uint32_t starts = wv & ~(wv << 1);
+  return word * 16u + (uint32_t)__popc(starts & ((1u << s) - 1u));
+}
+
+__device__ __forceinline__ uint32_t ld_parent(const cc_nodes &nodes, uint32_t a) {
   return __ldcg(reinterpret_cast<const unsigned int *>(&nodes[a].x));
 }
 
-__device__ __forceinline__ uint32_t uf_find(uint2 *nodes, uint32_t a) {
+__device__ __forceinline__ uint32_t uf_find(const cc_nodes &nodes, uint32_t a) {
   uint32_t p = ld_parent(nodes, a);
   while (p != a) {
     uint32_t gp = ld_parent(nodes, p);
@@ -45,7 +63,7 @@ __device__ __forceinline__ uint32_t uf_find(uint2 *nodes, uint32_t a) {
   return a;
 }
 
-__device__ __forceinline__ void uf_union(uint2 *nodes, uint32_t a, uint32_t b) {
+__device__ __forceinline__ void uf_union(const cc_nodes &nodes, uint32_t a, uint32_t b) {
   for (;;) {
     a = uf_find(nodes, a);
     b = uf_find(nodes, b);
@@ -132,23 +150,23 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
       const int b = __ffs(t) - 1;
       const int st = run_start(nw, b);
       const int en = run_end(nw, st);
-      link(0, dy, dz, st);
+      link(0, dy, dz, st, nw);
       t &= ~bits_range(st, en);
     }
     if (wide) {
       if (s == 0) {
         const uint32_t pw = fetch(-1, dy, dz);
-        if (pw >> 31) link(-1, dy, dz, run_start(pw, 31));
+        if (pw >> 31) link(-1, dy, dz, run_start(pw, 31), pw);
       }
       if (e == 31) {
         const uint32_t nx = fetch(1, dy, dz);
-        if (nx & 1u) link(1, dy, dz, 0);
+        if (nx & 1u) link(1, dy, dz, 0, nx);
       }
     }
   };
   if (s == 0) {  // the run continues from the previous word of this row
     const uint32_t pw = fetch(-1, 0, 0);
-    if (pw >> 31) link(-1, 0, 0, run_start(pw, 31));
+    if (pw >> 31) link(-1, 0, 0, run_start(pw, 31), pw);
   }
   const bool wide = CONN >= 18;
   row(-1, 0, wide);
@@ -165,7 +183,7 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
 // capacity the full-scan variants of those passes run instead (both are launched, the wrong one exits at once).
 #define CT_LIST 1024
 template <int CONN>
-__global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, uint2 *__restrict__ nodes,
+__global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                        uint32_t *__restrict__ rlist, unsigned rcap) {
   __shared__ uint32_t sb[CT_WORDS];
   __shared__ uint32_t par[CT_WORDS * 16];
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     const uint32_t rm = bits_range(s, e);
     rest &= ~rm;
     const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
-    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st) {
+    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st, uint32_t) {
       const int nt = ((lz + dz) * CT_Y + (ly + dy)) * CT_W + (lx + dx);
       lunion(par, me, (uint32_t)nt * 16u + (uint32_t)(st >> 1));
     });
@@ -249,7 +267,9 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     const int rt = (int)(r >> 4);
     const int rx = rt % CT_W, ry = (rt / CT_W) % CT_Y, rz = rt / (CT_W * CT_Y);
     const long long rword = ((long long)(tz0 + rz) * g.ny + (ty0 + ry)) * g.w + (tx0 + rx);
-    const uint32_t gparent = (uint32_t)rword * 16u + (r & 15u);
+    // local slots are position based (start bit >> 1); the published ids use the run's ordinal in its word
+    const uint32_t rwv = sb[rt];
+    const uint32_t gparent = (uint32_t)rword * 16u + (uint32_t)__popc((rwv & ~(rwv << 1)) & ((1u << (2u * (r & 15u))) - 1u));
     uint32_t stat = 0;
     if (r == me) {
       const uint32_t pe = par[me];
@@ -261,7 +281,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
         if (gi < rcap) rlist[1 + gi] = gparent;
       }
     }
-    nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)] = make_uint2(gparent, stat);
+    nodes[run_slot((uint32_t)word, wv, s)] = make_uint2(gparent, stat);
   }
   __syncthreads();
   const unsigned nl = min(s_n, (unsigned)CT_LIST);
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
 
 // neighbour pairs that straddle two tiles: global lock-free unions between (mostly) tile roots
 template <int CONN>
-__global__ void __launch_bounds__(256) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes) {
+__global__ void __launch_bounds__(256, 6) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes) {
   const long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (word >= g.nwords) return;
   const long long rowi = word / g.w;
@@ -299,10 +319,10 @@ __global__ void __launch_bounds__(256) k_cc_border(const uint32_t *__restrict__ 
     rest &= ~rm;
     // unions are made between TILE ROOTS (a run node's parent is its tile root and never changes here); lanes of
     // the warp that want the same pair - the common case along the face of two big components - send one
-    const uint32_t ra = nodes[(uint32_t)word * 16u + (uint32_t)(s >> 1)].x;
-    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st) {
+    const uint32_t ra = nodes[run_slot((uint32_t)word, wv, s)].x;
+    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st, uint32_t nwv) {
       const long long nword = ((long long)(z + dz) * g.ny + (y + dy)) * g.w + (xw + dx);
-      const uint32_t rb = nodes[(uint32_t)nword * 16u + (uint32_t)(st >> 1)].x;
+      const uint32_t rb = nodes[run_slot((uint32_t)nword, nwv, st)].x;
       const unsigned long long key = ((unsigned long long)ra << 32) | rb;
       const unsigned peers = __match_any_sync(__activemask(), key);
       if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) uf_union(nodes, ra, rb);
@@ -310,7 +330,7 @@ __global__ void __launch_bounds__(256) k_cc_border(const uint32_t *__restrict__ 
   }
 }
 
-__device__ __forceinline__ void flush_stats(uint2 *nodes, uint32_t root, uint32_t cnt, uint32_t flag) {
+__device__ __forceinline__ void flush_stats(const cc_nodes &nodes, uint32_t root, uint32_t cnt, uint32_t flag) {
   // warp-aggregated: lanes holding the same root combine before touching memory
   unsigned peers = __match_any_sync(__activemask(), root);
   uint32_t tot = __reduce_add_sync(peers, cnt);
@@ -323,7 +343,7 @@ __device__ __forceinline__ void flush_stats(uint2 *nodes, uint32_t root, uint32_
 
 // every tile root that lost its root status in k_cc_border hands the count / face flag of its local
 // component to its final root and is pointed straight at it (runs then reach the final root in two hops).
-__global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, uint2 *nodes,
+__global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                     const uint32_t *__restrict__ rlist, unsigned rcap) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,7 +355,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
     if (starts) {
       const int s = __ffs(starts) - 1;
       starts &= starts - 1;
-      const uint32_t slot = (uint32_t)word * 16u + (uint32_t)(s >> 1);
+      const uint32_t slot = run_slot((uint32_t)word, wv, s);
       const uint2 nd = nodes[slot];
       if ((nd.y & 0x7fffffffu) && nd.x != slot) {  // a tile root (it owns a count) that is no longer a root
         root = uf_find(nodes, slot);
@@ -349,7 +369,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
 }
 
 // list variants: one thread per tile root (k_cc_local's list); they do nothing when the list overflowed
-__global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restrict__ rlist, unsigned rcap, uint2 *nodes) {
+__global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restrict__ rlist, unsigned rcap, cc_nodes nodes) {
   const unsigned n = rlist[0];
   if (n > rcap) return;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,7 +386,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restr
   }
   if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
 }
-__global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict__ rlist, unsigned rcap, const uint2 *__restrict__ nodes,
+__global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict__ rlist, unsigned rcap, cc_nodes nodes,
                                                       unsigned long long *best, unsigned int *nroots) {
   const unsigned n = rlist[0];
   if (n > rcap) return;
@@ -394,7 +414,7 @@ __global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict
 }
 
 // final root of a run after k_cc_flatten: run -> tile root -> final root
-__device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ nodes, uint32_t slot) {
+__device__ __forceinline__ uint32_t cc_final_root(const cc_nodes &nodes, uint32_t slot) {
   uint32_t p = nodes[slot].x;
   while (p != slot) {
     if (p == CC_SENT) return CC_SENT;
@@ -407,7 +427,7 @@ __device__ __forceinline__ uint32_t cc_final_root(const uint2 *__restrict__ node
 // number of components and the largest one: key = (size << 32) | ~rootslot, so that among equal
 // sizes the smallest slot (earliest first voxel in raster order) wins, as src/bwlabel.c:462-466.
 __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bits, long long nwords,
-                                                 const uint2 *__restrict__ nodes, unsigned long long *best,
+                                                 cc_nodes nodes, unsigned long long *best,
                                                  unsigned int *nroots, const uint32_t *__restrict__ rlist, unsigned rcap) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
   long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,7 +438,7 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
   while (starts) {
     int s = __ffs(starts) - 1;
     starts &= starts - 1;
-    uint32_t slot = (uint32_t)word * 16u + (uint32_t)(s >> 1);
+    uint32_t slot = run_slot((uint32_t)word, w, s);
     uint2 nd = nodes[slot];
     if (nd.x == slot) {
       cnt++;
@@ -445,7 +465,7 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
 // sel == -1 no local winner (runs of seam roots marked CC_SENT are still selected); sel == -2 reads
 // *best (single volume).  nroots_ovr >= 0 replaces *nroots by the global component count.
 __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ bits, long long nwords,
-                                                   const uint2 *__restrict__ nodes, int mode,
+                                                   cc_nodes nodes, int mode,
                                                    const unsigned long long *__restrict__ best,
                                                    const unsigned int *__restrict__ nroots,
                                                    const uint32_t *__restrict__ other, uint32_t *__restrict__ out,
@@ -465,7 +485,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
       int e = run_end(wv, s);
       uint32_t rm = bits_range(s, e);
       rest &= ~rm;
-      const uint32_t r = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+      const uint32_t r = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
       if (r == bestslot || r == CC_SENT) res |= rm;
     }
   } else {
@@ -477,7 +497,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
         int e = run_end(wv, s);
         uint32_t rm = bits_range(s, e);
         rest &= ~rm;
-        uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+        uint32_t root = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
         if (!(nodes[root].y >> 31)) res |= rm;
       }
     }
@@ -634,7 +654,7 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
 static unsigned cc_list_cap(const cc_geom &cg) { return (unsigned)(cg.nwords / 4 + 4096); }
 
 // labelling + number of components (*nroots) + largest component (*best, optional)
-static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2 *nodes, int conn, unsigned long long *best,
+static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_nodes nodes, int conn, unsigned long long *best,
                     unsigned int *nroots) {
   unsigned blocks = b2m_cdiv(cg.nwords, 256);
   dim3 tiles(b2m_cdiv(cg.w, CT_W), b2m_cdiv(cg.ny, CT_Y), b2m_cdiv(cg.nz, CT_Z));
@@ -668,7 +688,7 @@ static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, uint2
 // because ids are ordered by (rank, slot)).  Global sizes / face flags come back into the local
 // forest through the seam roots only; everything else stays slab-local.
 // ================================================================================================
-__global__ void __launch_bounds__(256) k_seam_collect(const uint32_t *__restrict__ bits, cc_geom g, const uint2 *__restrict__ nodes,
+__global__ void __launch_bounds__(256) k_seam_collect(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                       int do_first, int do_last, uint64_t *__restrict__ list, unsigned cap,
                                                       unsigned int *__restrict__ count, unsigned int *__restrict__ overflow) {
   const long long pw = (long long)g.ny * g.w;
@@ -682,7 +702,7 @@ __global__ void __launch_bounds__(256) k_seam_collect(const uint32_t *__restrict
   while (starts) {
     const int s = __ffs(starts) - 1;
     starts &= starts - 1;
-    const uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+    const uint32_t root = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
     const unsigned pos = atomicAdd(count, 1u);
     if (pos < cap) list[pos] = root; else atomicOr(overflow, 4u);
   }
@@ -708,7 +728,7 @@ __device__ __forceinline__ unsigned seam_lower_bound(const uint32_t *__restrict_
   return lo;
 }
 // dense[word in plane * 16 + run slot] = index of the run's root in U, for the LAST own plane (sent up)
-__global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__ bits, cc_geom g, const uint2 *__restrict__ nodes,
+__global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                     const uint32_t *__restrict__ U, unsigned m, uint32_t *__restrict__ dense) {
   const long long pw = (long long)g.ny * g.w;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -719,7 +739,7 @@ __global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__
   while (starts) {
     const int s = __ffs(starts) - 1;
     starts &= starts - 1;
-    const uint32_t root = cc_final_root(nodes, (uint32_t)word * 16u + (uint32_t)(s >> 1));
+    const uint32_t root = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
     dense[(size_t)t * 16 + (s >> 1)] = seam_lower_bound(U, m, root);
   }
 }
@@ -727,7 +747,7 @@ __global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__
 // (18-connectivity: face + the four edge neighbours in that plane; 6-connectivity: face only)
 template <int CONN>
 __global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ below, cc_geom g,
-                                                    const uint2 *__restrict__ nodes, const uint32_t *__restrict__ U, unsigned m,
+                                                    cc_nodes nodes, const uint32_t *__restrict__ U, unsigned m,
                                                     unsigned off_me, unsigned off_below, const uint32_t *__restrict__ dense_below,
                                                     int mb, uint64_t *__restrict__ pairs, unsigned cap,
                                                     unsigned int *__restrict__ count, unsigned int *__restrict__ overflow) {
@@ -742,7 +762,7 @@ __global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__
     const int e = run_end(wv, s);
     const uint32_t rm = bits_range(s, e);
     rest &= ~rm;
-    const uint32_t root = cc_final_root(nodes, (uint32_t)t * 16u + (uint32_t)(s >> 1));
+    const uint32_t root = cc_final_root(nodes, run_slot((uint32_t)t, wv, s));
     const uint64_t me = (uint64_t)(off_me + seam_lower_bound(U, m, root));
     auto emit = [&](int nxw, int ny_, int st) {
       const uint64_t nb = (uint64_t)(off_below + __ldg(dense_below + ((size_t)ny_ * g.w + nxw) * 16 + (st >> 1)));
@@ -783,7 +803,7 @@ __global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__
   }
 }
 // per own seam root: (local slot, count | face flag)
-__global__ void __launch_bounds__(256) k_seam_entries(const uint32_t *__restrict__ U, unsigned m, const uint2 *__restrict__ nodes,
+__global__ void __launch_bounds__(256) k_seam_entries(const uint32_t *__restrict__ U, unsigned m, cc_nodes nodes,
                                                       uint2 *__restrict__ ent) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) ent[i] = make_uint2(U[i], nodes[U[i]].y);
@@ -840,7 +860,7 @@ __global__ void __launch_bounds__(256) k_seam_best(unsigned n, const uint32_t *_
 }
 // mode 1: global face flags into the own seam roots; mode 0: mark the own seam roots of component gstar
 __global__ void __launch_bounds__(256) k_seam_apply(unsigned m, unsigned off, const uint32_t *__restrict__ U, const uint32_t *__restrict__ par,
-                                                    const uint32_t *__restrict__ gflag, uint2 *nodes, int mode, long long gstar) {
+                                                    const uint32_t *__restrict__ gflag, cc_nodes nodes, int mode, long long gstar) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const uint32_t r = par[off + i];
@@ -865,7 +885,7 @@ static int seam_bits(unsigned long long n) {
 // labelled `bits_own` (own planes, geometry cg) -> seam resolution.  `below` = the neighbour's last plane
 // (EXT plane 0) when this rank has a lower neighbour.
 static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
-                    const cc_geom &cg, uint2 *nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
+                    const cc_geom &cg, cc_nodes nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
   const int W = sl.world, me = sl.rank;
   const size_t pw = (size_t)cg.ny * cg.w;
   const unsigned pblocks = b2m_cdiv(pw, 256);
@@ -1006,7 +1026,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   fo->fill = nullptr;
   fo->keep = nullptr;
   const uint32_t *bright = fg;
-  uint2 *nodes = nullptr;
+  cc_nodes nodes = {nullptr, (uint32_t)own_words};
   const size_t own_off = (size_t)sl.hl * pw;                   // first own word in an EXT bit buffer
   if (cc) {
     if ((unsigned long long)own_words * 16ull > 0xffffffffull || (unsigned long long)own_words * 32ull > 0x7fffffffull) {
@@ -1014,7 +1034,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
       return B2M_EARG;
     }
     B2M_TRY(b2m_reserve(ctx, BUF_NODES, (size_t)own_words * 16 * sizeof(uint2)));
-    nodes = b2m_ptr<uint2>(ctx, BUF_NODES);
+    nodes.p = b2m_ptr<uint2>(ctx, BUF_NODES);
   }
   // one halo plane of an EXT bit buffer from each neighbour (own boundary planes go the other way)
   auto halo_bits = [&](uint32_t *ext) -> int {

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
 // lanes 0..THR_WPW-1 store the words (the one-word-per-warp first version ran at 1.2 TB/s: too few
 // bytes in flight).
 #define THR_WPW 8
-__global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
+__global__ void __launch_bounds__(256, 6) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
                                                    float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg,
                                                    uint32_t *__restrict__ mb, int classic) {
   const unsigned lane = threadIdx.x & 31;
@@ -330,18 +330,40 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
         v[j] = ok[j] ? __ldg(in + row * nx + x) : 0.f;
       }
     }
-    uint32_t mine_fg = 0, mine_bg = 0, mine_mb = 0;
+    // every lane gets every ballot, so lane 0 stores the 8 words of each array as two 16-byte vectors (the kernel is
+    // ALU-bound - 93 % ALU pipe in ncu - and the per-word "lane == j" selects were 40 % of its ALU work)
+    const bool whole = nx == w * 32;
+    uint32_t mf[THR_WPW], mv[THR_WPW], mm[THR_WPW];
 #pragma unroll
     for (int j = 0; j < THR_WPW; j++) {
-      const unsigned m = __ballot_sync(0xffffffffu, ok[j] && v[j] >= iso);
-      const unsigned vm = __ballot_sync(0xffffffffu, ok[j]);
-      const unsigned mm = __ballot_sync(0xffffffffu, ok[j] && (classic ? (v[j] < iso) : (__fsub_rn(v[j], iso) > -FLT_EPSILON)));
-      if (lane == (unsigned)j) { mine_fg = m; mine_bg = ~m & vm; mine_mb = mm; }
+      mf[j] = __ballot_sync(0xffffffffu, ok[j] && v[j] >= iso);
+      mv[j] = whole ? (ok[j] ? 0xffffffffu : 0u) : __ballot_sync(0xffffffffu, ok[j]);
+      mm[j] = 0u;
+      if (mb) mm[j] = classic ? __ballot_sync(0xffffffffu, ok[j] && v[j] < iso)
+                              : __ballot_sync(0xffffffffu, ok[j] && __fsub_rn(v[j], iso) > -FLT_EPSILON);
     }
-    if (lane < THR_WPW && w0 + lane < nwords) {
-      fg[w0 + lane] = mine_fg;
-      if (bg) bg[w0 + lane] = mine_bg;
-      if (mb) mb[w0 + lane] = mine_mb;
+    if (lane == 0) {
+      if (w0 + THR_WPW <= nwords) {
+        uint4 *f4 = reinterpret_cast<uint4 *>(fg + w0);
+        f4[0] = make_uint4(mf[0], mf[1], mf[2], mf[3]); f4[1] = make_uint4(mf[4], mf[5], mf[6], mf[7]);
+        if (bg) {
+          uint4 *b4 = reinterpret_cast<uint4 *>(bg + w0);
+          b4[0] = make_uint4(~mf[0] & mv[0], ~mf[1] & mv[1], ~mf[2] & mv[2], ~mf[3] & mv[3]);
+          b4[1] = make_uint4(~mf[4] & mv[4], ~mf[5] & mv[5], ~mf[6] & mv[6], ~mf[7] & mv[7]);
+        }
+        if (mb) {
+          uint4 *m4 = reinterpret_cast<uint4 *>(mb + w0);
+          m4[0] = make_uint4(mm[0], mm[1], mm[2], mm[3]); m4[1] = make_uint4(mm[4], mm[5], mm[6], mm[7]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < THR_WPW; j++)
+          if (w0 + j < nwords) {
+            fg[w0 + j] = mf[j];
+            if (bg) bg[w0 + j] = ~mf[j] & mv[j];
+            if (mb) mb[w0 + j] = mm[j];
+          }
+      }
     }
   }
 }

@@ -315,9 +315,13 @@ __global__ void __launch_bounds__(256) k_w_patch(unsigned n, const uint32_t *__r
 // remap triangle indices to the welded numbering and flag the degenerate ones (src/meshify.c:118-145)
 __global__ void __launch_bounds__(256) k_tri_remap_degen(int *__restrict__ tris, unsigned nt, const double *__restrict__ verts,
                                                          const double *__restrict__ halo, weld_geom g, weld_tables w,
-                                                         uint32_t *__restrict__ keepflag, unsigned int *__restrict__ overflow) {
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nt) return;
+                                                         uint32_t *__restrict__ keepbits, uint32_t *__restrict__ keepcnt,
+                                                         unsigned int *__restrict__ overflow) {
+  // keep flags leave the kernel as one bit per triangle + a count per 32 triangles (the compaction offsets come
+  // from a scan over nt/32 counts instead of nt flags)
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t keep = 0;
+  if (i < nt) {
   int idx[3];
   double p[3][3];
 #pragma unroll
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(256) k_tri_remap_degen(int *__restrict__ tris,
   double bb = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(l, m), n), aa), cc);
   double amb = __dsub_rn(aa, bb);
   double t1 = __dsub_rn(cc, amb);
-  uint32_t keep = 1;
+  keep = 1;
   if (t1 <= 0.0) keep = 0;
   else {
     double prod = __dmul_rn(__dmul_rn(__dmul_rn(__dadd_rn(aa, __dadd_rn(bb, cc)), t1), __dadd_rn(cc, amb)),
@@ -353,17 +357,20 @@ __global__ void __launch_bounds__(256) k_tri_remap_degen(int *__restrict__ tris,
     double area4 = __dmul_rn(0.25, __dsqrt_rn(prod));
     if (area4 < (double)FLT_EPSILON) keep = 0;
   }
-  keepflag[i] = keep;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, keep != 0);
+  if ((threadIdx.x & 31) == 0 && i < nt) { keepbits[i >> 5] = m; keepcnt[i >> 5] = (uint32_t)__popc(m); }
 }
 
 __global__ void __launch_bounds__(256) k_compact_tris(const int *__restrict__ tin, int *__restrict__ tout,
-                                                      const uint32_t *__restrict__ keepflag_scanned,
-                                                      const uint32_t *__restrict__ total, unsigned nt) {
+                                                      const uint32_t *__restrict__ keepbits,
+                                                      const uint32_t *__restrict__ cnt_scanned, unsigned nt) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nt) return;
-  uint32_t me = keepflag_scanned[i];
-  uint32_t next = (i + 1 < nt) ? keepflag_scanned[i + 1] : *total;
-  if (next == me) return;  // flag was 0
+  const uint32_t m = __ldg(keepbits + (i >> 5));
+  const unsigned bit = i & 31u;
+  if (!((m >> bit) & 1u)) return;
+  const uint32_t me = __ldg(cnt_scanned + (i >> 5)) + (uint32_t)__popc(m & ((1u << bit) - 1u));
   size_t o = 3 * (size_t)me;
   tout[o] = tin[3 * (size_t)i]; tout[o + 1] = tin[3 * (size_t)i + 1]; tout[o + 2] = tin[3 * (size_t)i + 2];
 }
@@ -488,10 +495,11 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
   int *tris = mesh->tris;
   unsigned nt_out = nt;
   if (nt > 0) {
-    B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, (size_t)nt * 4 + 16));
-    uint32_t *tf = b2m_ptr<uint32_t>(ctx, BUF_FLAGS);
-    KT_LAUNCH(ctx, "tri_remap_degen", k_tri_remap_degen<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, nt, verts, mesh->halo_verts, g, w, tf, &d_sc->overflow));
-    B2M_TRY(b2m_exclusive_scan_u32(ctx, tf, tf, nt, &d_sc->n_tri_kept));
+    const size_t nw32 = ((size_t)nt + 31) / 32;
+    B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, nw32 * 8 + 64));
+    uint32_t *kb = b2m_ptr<uint32_t>(ctx, BUF_FLAGS), *kc = kb + nw32;
+    KT_LAUNCH(ctx, "tri_remap_degen", k_tri_remap_degen<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, nt, verts, mesh->halo_verts, g, w, kb, kc, &d_sc->overflow));
+    B2M_TRY(b2m_exclusive_scan_u32(ctx, kc, kc, nw32, &d_sc->n_tri_kept));
     CU_TRY(cudaGetLastError());
     B2M_TRY(b2m_fetch_scalars(ctx));
     if (ctx->h_scalars->overflow & 2u) { b2m_set_error("weld: triangle references a vertex outside this rank's blocks"); return B2M_ECUDA; }
@@ -499,7 +507,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
     if (nt_out != nt) {
       B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)nt_out * 12));
       int *t2 = b2m_ptr<int>(ctx, BUF_TRIS2);
-      KT_LAUNCH(ctx, "compact_tris", k_compact_tris<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, t2, tf, &d_sc->n_tri_kept, nt));
+      KT_LAUNCH(ctx, "compact_tris", k_compact_tris<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, t2, kb, kc, nt));
       tris = t2;
     }
   }
