@@ -162,7 +162,7 @@ def host_threads():
     return max(1, min(c, 32))
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     if rank != 0:
         return
     n, T = 256, host_threads()
@@ -178,10 +178,17 @@ def run_reference(args, rank):
                                       f"single-threaded, one volume per core"},
            "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
+    # ONE JSON line on stdout: anything else a library prints there (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -195,7 +202,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
     args.warmup = max(args.warmup, 3)
 
@@ -335,6 +342,7 @@ def main():
                 assert (sr2.r.nverts, sr2.r.ntris) == (nv, nt)
                 libc.free(pv)
                 libc.free(pt)
+                one.last = (sr2.r.h2d_ms, sr2.r.ms[7], sr2.r.d2h_ms)
                 return (sr2.nv_edge + sr2.nv_cent + sr2.nv_extra) * 24 + sr2.ntris_local * 12
             api = ("b2m_meshify_slab_host() (include/b2m.h), one z-slab per rank: pinned host planes in, malloc'd host "
                    "mesh blocks out")
@@ -348,6 +356,10 @@ def main():
         barrier()
         dt = max_over_ranks((time.perf_counter() - t0) / ke)
         breakdown = None
+        if world > 1:
+            h, dv, dd = one.last
+            breakdown = {"h2d_ms": round(max_over_ranks(h), 2), "device_ms": round(max_over_ranks(dv), 2),
+                         "d2h_ms": round(max_over_ranks(dd), 2), "note": "max over ranks, last timed call"}
         if world == 1:
             # one untimed call through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
             r2 = lib.Result()
@@ -385,7 +397,7 @@ def main():
                           "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris}},
                "stage_ms": {k: round(float(v) / args.steps, 4) for k, v in zip(lib.STAGES, stage)},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if comm is not None:
         eng.lib.b2m_comm_destroy(comm)
     if world > 1:

@@ -18,7 +18,7 @@ CC = ["meshify_host.c"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing", "-Xcompiler", "-fopenmp",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing",
 ]
 
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libb2m build failed")
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
-                           "-lcudart_static", "-lgomp", "-lm", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
+                           "-lcudart_static", "-lm", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
     return LIB
 
 

@@ -148,6 +148,11 @@ struct b2m_ctx {
   b2m_scalars *d_all;
   int h_all_cap;
   unsigned slab_t_off;     // slabs: global index of this rank's first surviving triangle (last call)
+  // called once per hot-path call when the marching-cubes totals are known (own vertices / triangles before the
+  // weld): the host entry points use it to allocate and pre-fault the output blocks while the GPU keeps working
+  void (*counts_hook)(void *user, size_t nverts, size_t ntris);
+  void *hook_user;
+  size_t last_nvox, last_nv, last_nt;  // geometry and marching-cubes totals of the previous host call
   cudaStream_t stream;
   b2m_buf buf[BUF_COUNT];
   cudaEvent_t ev[2 * B2M_NSTAGE + 2];
@@ -185,6 +190,8 @@ int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
 #define B2M_STAGE_BYTES ((size_t)32 << 20)
 int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int b2m_touch_async(void *a, size_t na, void *b, size_t nb);
+void b2m_touch_wait(void);
 
 #define B2M_LAUNCHED(ctx) ((ctx)->launches++)
 

@@ -151,8 +151,12 @@ static int stage_init(b2m_ctx *ctx) {
     }
   return B2M_OK;
 }
-// multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded
-// copy); runs serially when called from inside a caller's own OpenMP region
+// multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded copy).
+// A small persistent pthread pool, not OpenMP: launchers such as torchrun export OMP_NUM_THREADS=1, and the copy
+// must not depend on the host program's OpenMP settings.  Slices of 4 MiB are handed out through an atomic counter;
+// the calling thread works too.  One job at a time (callers from several host threads serialise on the pool).
+#include <pthread.h>
+#include <atomic>
 static int par_threads(void) {
   static int n = 0;
   if (!n) {
@@ -160,18 +164,104 @@ static int par_threads(void) {
     const char *e = getenv("B2M_COPY_THREADS");
     n = e ? atoi(e) : (int)(c > 16 ? 16 : c);
     if (n < 1) n = 1;
+    if (n > 64) n = 64;
   }
   return n;
 }
-static void par_memcpy(void *dst, const void *src, size_t n) {
-  const size_t slice = (size_t)4 << 20;
-  const long long ns = (long long)((n + slice - 1) / slice);
-#pragma omp parallel for schedule(static) num_threads(par_threads()) if (ns > 1)
-  for (long long i = 0; i < ns; i++) {
-    const size_t o = (size_t)i * slice;
-    memcpy((char *)dst + o, (const char *)src + o, n - o < slice ? n - o : slice);
+namespace {
+struct copy_pool {
+  pthread_mutex_t job_mu = PTHREAD_MUTEX_INITIALIZER;   // one job at a time
+  pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_cond_t cv_go = PTHREAD_COND_INITIALIZER, cv_done = PTHREAD_COND_INITIALIZER;
+  char *dst = nullptr;
+  const char *src = nullptr;   // null: "touch" job - fault the pages of dst (and of dst2) in, one write per page
+  char *dst2 = nullptr;
+  size_t n2 = 0;
+  long long nslices1 = 0;
+  size_t n = 0, slice = (size_t)1 << 20;
+  long long nslices = 0;
+  std::atomic<long long> next{0};
+  int generation = 0, running = 0, started = 0;
+} g_pool;
+static void pool_work(copy_pool *p) {
+  for (;;) {
+    const long long i = p->next.fetch_add(1);
+    if (i >= p->nslices) break;
+    if (p->src) {
+      const size_t o = (size_t)i * p->slice;
+      memcpy(p->dst + o, p->src + o, p->n - o < p->slice ? p->n - o : p->slice);
+    } else {
+      char *base = i < p->nslices1 ? p->dst : p->dst2;
+      const size_t tot = i < p->nslices1 ? p->n : p->n2;
+      const size_t o = (size_t)(i < p->nslices1 ? i : i - p->nslices1) * p->slice;
+      const size_t len = tot - o < p->slice ? tot - o : p->slice;
+      for (size_t q = 0; q < len; q += 4096) ((volatile char *)base)[o + q] = 0;
+    }
   }
 }
+static void *pool_main(void *arg) {
+  copy_pool *p = (copy_pool *)arg;
+  int seen = 0;
+  pthread_mutex_lock(&p->mu);
+  for (;;) {
+    while (p->generation == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+    seen = p->generation;
+    pthread_mutex_unlock(&p->mu);
+    pool_work(p);
+    pthread_mutex_lock(&p->mu);
+    if (--p->running == 0) pthread_cond_signal(&p->cv_done);
+  }
+  return nullptr;
+}
+}  // namespace
+static void pool_start_locked(copy_pool *p, int nt) {  // job_mu held, job fields set
+  if (!p->started) {
+    for (int i = 0; i < nt - 1; i++) {
+      pthread_t t;
+      if (pthread_create(&t, nullptr, pool_main, p) == 0) { pthread_detach(t); p->started++; }
+    }
+    if (!p->started) p->started = -1;  // no workers: the caller works alone
+  }
+  p->next.store(0);
+  pthread_mutex_lock(&p->mu);
+  p->running = p->started > 0 ? p->started : 0;
+  p->generation++;
+  pthread_cond_broadcast(&p->cv_go);
+  pthread_mutex_unlock(&p->mu);
+}
+static void pool_finish_locked(copy_pool *p) {
+  pthread_mutex_lock(&p->mu);
+  while (p->running > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+  pthread_mutex_unlock(&p->mu);
+  pthread_mutex_unlock(&p->job_mu);
+}
+static void par_memcpy(void *dst, const void *src, size_t n) {
+  copy_pool *p = &g_pool;
+  const int nt = par_threads();
+  if (nt <= 1 || n <= p->slice) { memcpy(dst, src, n); return; }
+  pthread_mutex_lock(&p->job_mu);
+  p->dst = (char *)dst; p->src = (const char *)src; p->n = n;
+  p->nslices = (long long)((n + p->slice - 1) / p->slice);
+  pool_start_locked(p, nt);
+  pool_work(p);
+  pool_finish_locked(p);
+}
+// fault in the pages of two fresh host blocks on the pool threads while the caller does something else (the GPU
+// pipeline); b2m_touch_wait() must follow before the next bulk copy.  Returns 0 if nothing was started.
+int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
+  copy_pool *p = &g_pool;
+  const int nt = par_threads();
+  if (nt <= 1 || na + nb < ((size_t)64 << 20)) return 0;
+  pthread_mutex_lock(&p->job_mu);
+  p->src = nullptr;
+  p->dst = (char *)a; p->n = na; p->dst2 = (char *)b; p->n2 = nb;
+  p->nslices1 = (long long)((na + p->slice - 1) / p->slice);
+  p->nslices = p->nslices1 + (long long)((nb + p->slice - 1) / p->slice);
+  pool_start_locked(p, nt);
+  if (p->started <= 0) { pool_work(p); pool_finish_locked(p); return 0; }
+  return 1;
+}
+void b2m_touch_wait(void) { pool_finish_locked(&g_pool); }
 
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
   if (!bytes) return B2M_OK;

@@ -912,6 +912,7 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   mesh->e_off = e_off; mesh->c_off = c_off; mesh->t_off = t_off;
   // reference failure rule: < 3 vertices or < 1 triangle (src/MarchingCubes.c:1119, src/oldcubes.c:497)
   if (p.classic ? (3ull * NT < 3) : (NVE + NVC < 3 || NT < 1)) return B2M_FAIL;
+  if (ctx->counts_hook) ctx->counts_hook(ctx->hook_user, (size_t)tot_v + tot_c, (size_t)tot_t);
   B2M_TRY(mc_scan3_apply(ctx, p, nseg, e_off));
   if (W > 1) {
     // the first own plane of segment records goes down: the rank below needs the vertex numbering of the

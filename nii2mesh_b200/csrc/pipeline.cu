@@ -308,6 +308,54 @@ extern "C" int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts
   return B2M_OK;
 }
 
+// output blocks allocated as soon as the marching-cubes totals are known, pre-faulted on the copy pool while the
+// emit / weld kernels run (first-touch faults of fresh malloc() pages were half of the D2H time)
+struct host_out {
+  void *v, *t;
+  size_t cap_v, cap_t;  // bytes
+  size_t seen_v, seen_t;  // marching-cubes totals of this call (remembered for the next call on the same geometry)
+  int touching;
+};
+static void host_out_hook(void *user, size_t nverts, size_t ntris);
+// A repeated call on a volume of the same size starts allocating / pre-faulting its output blocks right away, from
+// the previous call's totals, so the page faults overlap the H2D copy as well (wrong guesses are re-allocated).
+static void host_out_early(b2m_ctx *ctx, host_out *h, size_t nvox) {
+  if (ctx->last_nvox == nvox && ctx->last_nv) host_out_hook(h, ctx->last_nv + ctx->last_nv / 64, ctx->last_nt + ctx->last_nt / 64);
+  h->seen_v = h->seen_t = 0;
+}
+static void host_out_remember(b2m_ctx *ctx, const host_out *h, size_t nvox) {
+  ctx->last_nvox = nvox; ctx->last_nv = h->seen_v; ctx->last_nt = h->seen_t;
+}
+static void host_out_hook(void *user, size_t nverts, size_t ntris) {
+  host_out *h = (host_out *)user;
+  h->seen_v = nverts; h->seen_t = ntris;
+  if (h->v || h->t) return;
+  h->cap_v = (nverts + 4096) * 24 + 8;  // a little head-room for the split-off vertices of the classic weld
+  h->cap_t = ntris * 12 + 8;
+  h->v = malloc(h->cap_v);
+  h->t = malloc(h->cap_t);
+  if (!h->v || !h->t) return;
+  hint_hugepages(h->v, h->cap_v);  // fresh mmap'd blocks: 2 MB pages cut the first-touch faults 512x
+  hint_hugepages(h->t, h->cap_t);
+  h->touching = b2m_touch_async(h->v, nverts * 24, h->t, ntris * 12);
+}
+static int host_out_finish(b2m_ctx *ctx, host_out *h, int rc, const void *d_verts, size_t nv, const void *d_tris, size_t nt,
+                           void **verts, void **tris) {
+  ctx->counts_hook = nullptr;
+  if (h->touching) b2m_touch_wait();
+  if (rc == B2M_OK) {
+    if (!h->v || h->cap_v < nv * 24 + 8) { free(h->v); h->v = malloc(nv * 24 + 8); if (h->v) hint_hugepages(h->v, nv * 24); }
+    if (!h->t || h->cap_t < nt * 12 + 8) { free(h->t); h->t = malloc(nt * 12 + 8); if (h->t) hint_hugepages(h->t, nt * 12); }
+    if (!h->v || !h->t) { b2m_set_error("malloc of the output mesh failed"); rc = B2M_ENOMEM; }
+  }
+  if (rc == B2M_OK && nv) rc = b2m_copy_d2h(ctx, h->v, d_verts, nv * 24);
+  if (rc == B2M_OK && nt) rc = b2m_copy_d2h(ctx, h->t, d_tris, nt * 12);
+  if (rc != B2M_OK) { free(h->v); free(h->t); return rc; }
+  *verts = h->v;
+  *tris = h->t;
+  return B2M_OK;
+}
+
 extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t dims[3], const b2m_opts *opts,
                                 void **verts, void **tris, b2m_result *res) {
   if (!ctx || !h_img || !dims || !opts || !res || !verts || !tris) { b2m_set_error("null argument"); return B2M_EARG; }
@@ -315,22 +363,22 @@ extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t 
   CU_TRY(cudaSetDevice(ctx->device));
   size_t n = (size_t)dims[0] * dims[1] * dims[2];
   B2M_TRY(b2m_reserve(ctx, BUF_INPUT, n * 4));
+  host_out ho;
+  memset(&ho, 0, sizeof(ho));
+  host_out_early(ctx, &ho, n);
   const double t0 = wall_ms();
-  B2M_TRY(b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_img, n * 4));
+  int rc = b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_img, n * 4);
   const double t1 = wall_ms();
-  B2M_TRY(b2m_meshify_device(ctx, b2m_ptr<float>(ctx, BUF_INPUT), dims, opts, res));
+  ctx->counts_hook = host_out_hook;
+  ctx->hook_user = &ho;
+  if (rc == B2M_OK) rc = b2m_meshify_device(ctx, b2m_ptr<float>(ctx, BUF_INPUT), dims, opts, res);
   const double t2 = wall_ms();
-  void *v = malloc((size_t)res->nverts * 24 + 8), *t = malloc((size_t)res->ntris * 12 + 8);
-  if (!v || !t) { free(v); free(t); b2m_set_error("malloc of the output mesh failed"); return B2M_ENOMEM; }
-  hint_hugepages(v, (size_t)res->nverts * 24);  // fresh mmap'd blocks: 2 MB pages cut the first-touch faults 512x
-  hint_hugepages(t, (size_t)res->ntris * 12);
-  int rc = b2m_fetch_mesh(ctx, res, v, t);
-  if (rc != B2M_OK) { free(v); free(t); return rc; }
+  host_out_remember(ctx, &ho, n);
+  rc = host_out_finish(ctx, &ho, rc, res->d_verts, (size_t)res->nverts, res->d_tris, (size_t)res->ntris, verts, tris);
+  if (rc != B2M_OK) return rc;
   res->h2d_ms = (float)(t1 - t0);
   res->d2h_ms = (float)(wall_ms() - t2);
   if (opts->verbose) printf("host copies: H2D %.1f ms, D2H %.1f ms\n", res->h2d_ms, res->d2h_ms);
-  *verts = v;
-  *tris = t;
   return B2M_OK;
 }
 
@@ -342,25 +390,28 @@ extern "C" int b2m_meshify_slab_host(b2m_ctx *ctx, b2m_comm *comm, const float *
   CU_TRY(cudaSetDevice(ctx->device));
   const size_t n = (size_t)gdims[0] * gdims[1] * nzl;
   int rc = b2m_reserve(ctx, BUF_INPUT, n * 4);
+  host_out ho;
+  memset(&ho, 0, sizeof(ho));
+  if (rc == B2M_OK) host_out_early(ctx, &ho, n);
   const double t0 = wall_ms();
   if (rc == B2M_OK) rc = b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_slab, n * 4);
-  if (rc != B2M_OK) { b2m_comm_abort(comm); return rc; }
+  if (rc != B2M_OK) {
+    b2m_comm_abort(comm);
+    if (ho.touching) b2m_touch_wait();
+    free(ho.v); free(ho.t);
+    return rc;
+  }
   const double t1 = wall_ms();
-  B2M_TRY(b2m_meshify_slab(ctx, comm, b2m_ptr<float>(ctx, BUF_INPUT), gdims, z0, nzl, opts, out));
+  ctx->counts_hook = host_out_hook;
+  ctx->hook_user = &ho;
+  rc = b2m_meshify_slab(ctx, comm, b2m_ptr<float>(ctx, BUF_INPUT), gdims, z0, nzl, opts, out);
   const double t2 = wall_ms();
+  host_out_remember(ctx, &ho, n);
   const size_t nv = (size_t)out->nv_edge + out->nv_cent + out->nv_extra, nt = (size_t)out->ntris_local;
-  void *v = malloc(nv * 24 + 8), *t = malloc(nt * 12 + 8);
-  if (!v || !t) { free(v); free(t); b2m_set_error("malloc of the output mesh failed"); return B2M_ENOMEM; }
-  hint_hugepages(v, nv * 24);
-  hint_hugepages(t, nt * 12);
-  rc = B2M_OK;
-  if (nv) rc = b2m_copy_d2h(ctx, v, out->d_verts, nv * 24);
-  if (rc == B2M_OK && nt) rc = b2m_copy_d2h(ctx, t, out->d_tris, nt * 12);
-  if (rc != B2M_OK) { free(v); free(t); return rc; }
+  rc = host_out_finish(ctx, &ho, rc, out->d_verts, nv, out->d_tris, nt, verts, tris);
+  if (rc != B2M_OK) return rc;
   out->r.h2d_ms = (float)(t1 - t0);
   out->r.d2h_ms = (float)(wall_ms() - t2);
-  *verts = v;
-  *tris = t;
   return B2M_OK;
 }
 

@@ -308,13 +308,41 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
 // lanes 0..THR_WPW-1 store the words (the one-word-per-warp first version ran at 1.2 TB/s: too few
 // bytes in flight).
 #define THR_WPW 8
-__global__ void __launch_bounds__(256, 6) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
+__global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
                                                    float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg,
                                                    uint32_t *__restrict__ mb, int classic) {
   const unsigned lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long w0 = warp * THR_WPW; w0 < nwords; w0 += nwarps * THR_WPW) {
+    if (nx == w * 32 && w0 + THR_WPW <= nwords) {
+      // fast path (whole-word rows, 8 full words): no validity predicates, constant load offsets; per word one
+      // compare + ballot for fg and one subtract + compare + ballot for mb
+      const float *p = in + w0 * 32 + lane;
+      float v[THR_WPW];
+#pragma unroll
+      for (int j = 0; j < THR_WPW; j++) v[j] = __ldg(p + j * 32);
+      uint32_t mf[THR_WPW], mm[THR_WPW];
+#pragma unroll
+      for (int j = 0; j < THR_WPW; j++) {
+        mf[j] = __ballot_sync(0xffffffffu, v[j] >= iso);
+        mm[j] = 0u;
+        if (mb) mm[j] = classic ? __ballot_sync(0xffffffffu, v[j] < iso) : __ballot_sync(0xffffffffu, __fsub_rn(v[j], iso) > -FLT_EPSILON);
+      }
+      if (lane == 0) {
+        uint4 *f4 = reinterpret_cast<uint4 *>(fg + w0);
+        f4[0] = make_uint4(mf[0], mf[1], mf[2], mf[3]); f4[1] = make_uint4(mf[4], mf[5], mf[6], mf[7]);
+        if (bg) {
+          uint4 *b4 = reinterpret_cast<uint4 *>(bg + w0);
+          b4[0] = make_uint4(~mf[0], ~mf[1], ~mf[2], ~mf[3]); b4[1] = make_uint4(~mf[4], ~mf[5], ~mf[6], ~mf[7]);
+        }
+        if (mb) {
+          uint4 *m4 = reinterpret_cast<uint4 *>(mb + w0);
+          m4[0] = make_uint4(mm[0], mm[1], mm[2], mm[3]); m4[1] = make_uint4(mm[4], mm[5], mm[6], mm[7]);
+        }
+      }
+      continue;
+    }
     float v[THR_WPW];
     bool ok[THR_WPW];
 #pragma unroll
