@@ -381,6 +381,14 @@ def main():
         cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "kind": kind,
                "sample": f"{T} x G{sn} ({sn}^3 voxels, same generator and flags) concurrently, one per host core, "
                          f"{dt:.1f} s, {cnv} verts {cnt} tris each; meshify() itself is single-threaded"}
+    # known answer of the G family: the reference's PRE-weld counts are exactly cubic in the number
+    # of 128-voxel tiles per axis; they pin the full-size runs no CPU oracle can reach (2048^3: 336 902 112 / 673 869 568)
+    known = None
+    if gshape[0] == gshape[1] == gshape[2] and gshape[0] % 128 == 0:
+        t = gshape[0] // 128
+        exp = (79416 * t ** 3 + 45456 * t ** 2 - 1410 * t, 158848 * t ** 3 + 90912 * t ** 2 - 2832 * t)
+        known = {"pre_nverts": exp[0], "pre_ntris": exp[1], "match": (r.pre_nverts, r.pre_ntris) == exp}
+        assert known["match"], f"pre-weld counts {r.pre_nverts}/{r.pre_ntris} differ from the reference's {exp}"
     if rank == 0:
         if world == 1:
             workload = f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])"
@@ -394,7 +402,8 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": workload, "voxels_per_gpu": N, "voxels": GN, "parallelism": par,
                           "l2": "inputs (4 B/voxel volume) larger than the 126 MB L2; no flush needed",
-                          "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris}},
+                          "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris},
+                          "known_answer": known},
                "stage_ms": {k: round(float(v) / args.steps, 4) for k, v in zip(lib.STAGES, stage)},
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         emit(out)
