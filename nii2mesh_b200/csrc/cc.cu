@@ -292,17 +292,23 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
 }
 
 // neighbour pairs that straddle two tiles: global lock-free unions between (mostly) tile roots
+// One CTA per tile (the thread <-> word mapping of k_cc_local).  Along the face of two big components every word
+// asks for the same (tile root, tile root) pair: lanes of a warp that hold the same pair send one request
+// (__match_any_sync), and a small shared-memory cache of recently requested pairs drops the repeats across the
+// warps of the tile (whoever put the pair there completes the union inside this kernel).
+#define CB_CACHE 128
 template <int CONN>
-__global__ void __launch_bounds__(256, 6) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes) {
-  const long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (word >= g.nwords) return;
-  const long long rowi = word / g.w;
-  const int xw = (int)(word - rowi * g.w);
-  const int z = (int)(rowi / g.ny);
-  const int y = (int)(rowi - (long long)z * g.ny);
-  const int lx = xw % CT_W, ly = y % CT_Y, lz = z % CT_Z;
+__global__ void __launch_bounds__(CT_WORDS, 3) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes) {
+  __shared__ unsigned long long cache[CB_CACHE];
+  const int t = threadIdx.x;
+  if (t < CB_CACHE) cache[t] = 0ull;
+  __syncthreads();
+  const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
+  const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
+  if (xw >= g.w || y >= g.ny || z >= g.nz) return;
   // only words on a tile face can have a backward neighbour in another tile
   if (!(lx == 0 || lx == CT_W - 1 || ly == 0 || ly == CT_Y - 1 || lz == 0)) return;
+  const long long word = ((long long)z * g.ny + y) * g.w + xw;
   const uint32_t wv = __ldg(bits + word);
   if (!wv) return;
   auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
@@ -325,7 +331,10 @@ __global__ void __launch_bounds__(256, 6) k_cc_border(const uint32_t *__restrict
       const uint32_t rb = nodes[run_slot((uint32_t)nword, nwv, st)].x;
       const unsigned long long key = ((unsigned long long)ra << 32) | rb;
       const unsigned peers = __match_any_sync(__activemask(), key);
-      if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) uf_union(nodes, ra, rb);
+      if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u)) {
+        const unsigned h = ((ra * 0x9E3779B1u) ^ (rb * 0x85EBCA77u)) >> 25;  // 7 bits
+        if (atomicExch(&cache[h], key) != key) uf_union(nodes, ra, rb);
+      }
     });
   }
 }
@@ -346,7 +355,9 @@ __device__ __forceinline__ void flush_stats(const cc_nodes &nodes, uint32_t root
 __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                     const uint32_t *__restrict__ rlist, unsigned rcap) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
-  long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long nround = (g.nwords + 31) / 32 * 32;  // whole warps iterate together
+  for (long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x; word < nround; word += stride) {
   uint32_t wv = word < g.nwords ? __ldg(bits + word) : 0u;
   uint32_t starts = wv & ~(wv << 1);
   // all lanes iterate together until every lane is out of runs (keeps the match/reduce converged)
@@ -365,6 +376,7 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
       }
     }
     if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
+  }
   }
 }
 
@@ -430,11 +442,12 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
                                                  cc_nodes nodes, unsigned long long *best,
                                                  unsigned int *nroots, const uint32_t *__restrict__ rlist, unsigned rcap) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
-  long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t w = word < nwords ? __ldg(bits + word) : 0u;
-  uint32_t starts = w & ~(w << 1);
+  const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long key = 0;
   unsigned int cnt = 0;
+  for (long long word = (long long)blockIdx.x * blockDim.x + threadIdx.x; word < nwords; word += stride) {
+  uint32_t w = __ldg(bits + word);
+  uint32_t starts = w & ~(w << 1);
   while (starts) {
     int s = __ffs(starts) - 1;
     starts &= starts - 1;
@@ -445,6 +458,7 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
       unsigned long long k = ((unsigned long long)(nd.y & 0x7fffffffu) << 32) | (unsigned long long)(0xffffffffu - slot);
       key = k > key ? k : key;
     }
+  }
   }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -651,7 +665,11 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
   return B2M_OK;
 }
 
-static unsigned cc_list_cap(const cc_geom &cg) { return (unsigned)(cg.nwords / 4 + 4096); }
+static unsigned cc_list_cap(const cc_geom &cg) {
+  const char *e = getenv("B2M_CC_LIST_CAP");  // tests: a tiny capacity forces the full-scan fallback
+  if (e) return (unsigned)atoi(e);
+  return (unsigned)(cg.nwords / 4 + 4096);
+}
 
 // labelling + number of components (*nroots) + largest component (*best, optional)
 static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_nodes nodes, int conn, unsigned long long *best,
@@ -664,16 +682,17 @@ static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_no
   CU_TRY(cudaMemsetAsync(rlist, 0, 4, ctx->stream));
   if (conn >= 18) {
     KT_LAUNCH(ctx, "cc_local", k_cc_local<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
-    KT_LAUNCH(ctx, "cc_border", k_cc_border<18><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_border", k_cc_border<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
   } else {
     KT_LAUNCH(ctx, "cc_local", k_cc_local<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
-    KT_LAUNCH(ctx, "cc_border", k_cc_border<6><<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes));
+    KT_LAUNCH(ctx, "cc_border", k_cc_border<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
   }
-  const unsigned lblocks = b2m_cdiv(rcap, 256);
+  const unsigned lblocks = rcap ? b2m_cdiv(rcap, 256) : 1u;
   KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes));
-  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
+  const unsigned sblocks = min(blocks, (unsigned)ctx->sm_count * 8u);  // grid-stride: these exit at once in the common case
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<sblocks, 256, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
   KT_LAUNCH(ctx, "cc_best", k_cc_best_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes, best, nroots));
-  KT_LAUNCH(ctx, "cc_best", k_cc_best<<<blocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes, best, nroots, rlist, rcap));
+  KT_LAUNCH(ctx, "cc_best", k_cc_best<<<sblocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes, best, nroots, rlist, rcap));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

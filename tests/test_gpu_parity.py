@@ -264,3 +264,16 @@ def test_sphere512_classic_known_counts(eng):
         assert (r.pre_nverts, r.pre_ntris, r.nverts, r.ntris) == (2791860, 5331520, 2791807, 5330338)
     finally:
         d.free()
+
+
+def test_cc_tile_root_list_overflow_fallback(eng, orc, monkeypatch):
+    """the compact tile-root list of the CC passes overflows on noise volumes: the full-scan variants must give the
+    same masks (forced here with a zero capacity)"""
+    monkeypatch.setenv("B2M_CC_LIST_CAP", "0")
+    for name in ("blobs", "sphere40", "blobs2"):
+        vol, iso = VOLS[name]
+        for ps, ol, fb in ((0, 1, 1), (1, 1, 0), (0, 0, 1)):
+            a = eng.front(vol, iso, ps, ol, fb)
+            b = orc.front(vol, iso, ps, ol, fb)
+            assert np.array_equal(a["mask"] != 0, b["mask"] != 0), (name, ps, ol, fb)
+            assert bits_differ(a["img"], b["img"]) == 0, (name, ps, ol, fb)
