@@ -46,6 +46,9 @@ __device__ __forceinline__ double round_to_f32(double d) {
   }
   return (double)(float)d;
 }
+__device__ __forceinline__ unsigned input_bias(float f) {  // < 0x64000000 iff 2^-100 <= |f| < 2^100
+  return (__float_as_uint(f) & 0x7fffffffu) - 0x0d800000u;
+}
 __device__ __forceinline__ bool input_unsafe(float f) {
   const unsigned u = __float_as_uint(f);
   return u != 0u && ((u & 0x7fffffffu) - 0x0d800000u) >= 0x64000000u;  // not +0 and outside [2^-100, 2^100)
@@ -57,18 +60,18 @@ __device__ __forceinline__ void load_row4(const float *__restrict__ row, int gx,
     if (gx < nx) {
       float4 t = __ldg(reinterpret_cast<const float4 *>(row + gx));
       f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-    } else {
-      f[0] = f[1] = f[2] = f[3] = 0.f;
     }
   } else {
 #pragma unroll
-    for (int k = 0; k < 4; k++) f[k] = (gx + k < nx) ? __ldg(row + gx + k) : 0.f;
+    for (int k = 0; k < 4; k++)
+      if (gx + k < nx) f[k] = __ldg(row + gx + k);
   }
 }
 
 // x pass of one staged row: 4 outputs per lane from the lane's float4 and its neighbours' (shuffled as
 // floats), rounded to the f32 grid, parked in shared memory as doubles
-template <bool FAST>
+// XEDGE: the tile touches x < 2 or x >= nx-2 (block-uniform), only then the pass-through selects are needed
+template <bool FAST, bool XEDGE>
 __device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2], int lane, int gx, int nx,
                                            double2 *__restrict__ dst) {
   float f[8];
@@ -88,15 +91,15 @@ __device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2
   for (int k = 0; k < 4; k++) {
     const int x = gx + k;
     const double r = round_to_f32<FAST>(fir5(v[k], v[k + 1], v[k + 2], v[k + 3], v[k + 4]));
-    o[k] = (x < 2 || x >= nx - 2) ? v[k + 2] : r;
+    o[k] = (XEDGE && (x < 2 || x >= nx - 2)) ? v[k + 2] : r;
   }
   dst[lane] = make_double2(o[0], o[1]);
   dst[32 + lane] = make_double2(o[2], o[3]);
 }
 
 // y pass (1 row x 4 voxels per lane out of 5 staged rows) + z streaming accumulators
-template <bool FAST>
-__device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly, int lane, bool yborder,
+template <bool FAST, bool YBORDER>
+__device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly, int lane,
                                         double S[4][4], float ob[4], float oi[4]) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -109,8 +112,7 @@ __device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly,
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
       const int k = 2 * h + kk;
-      const double f = round_to_f32<FAST>(fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]));
-      const double ys = yborder ? c[2][kk] : f;
+      const double ys = YBORDER ? c[2][kk] : round_to_f32<FAST>(fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]));
       const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
       const double fin = __dadd_rn(S[k][3], q2);
       S[k][3] = __dadd_rn(S[k][2], q1);
@@ -172,15 +174,23 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   const int oy = y0 + warp;
   const bool yborder = oy < 2 || oy >= ny - 2;
   const bool ook = yz && oy < ny && gx < nx;
+  const bool xedge = x0 == 0 || x0 + SX_TX > nx - 2;  // block-uniform
   float *outp = out + (size_t)oy * nx + gx;  // + (z - oz0) * nxy
 
   // raw row of the plane being staged, prefetched one plane ahead
   float raw[4], hal[2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
+  // values that are never used (rows / columns outside the volume, halo slots of inner lanes) are 1.0 so that they
+  // pass the input screen; the plane pointer runs along z and is recomputed only where the source piece changes
+  const int zb1 = src.rz0 + src.n_lo, zb2 = zb1 + src.n_main;
+  const float *rowp = nullptr;
   auto fetch = [&](int zp) {
-    raw[0] = raw[1] = raw[2] = raw[3] = 0.f;
-    hal[0] = hal[1] = 0.f;
+    raw[0] = raw[1] = raw[2] = raw[3] = 1.f;
+    hal[0] = hal[1] = 1.f;
+    if (zp < ze) {
+      if (zp == zs || zp == zb1 || zp == zb2) rowp = smooth_plane(src, zp, nxy) + rowoff;
+      else rowp += nxy;
+    }
     if (rowok && zp < ze) {
-      const float *rowp = smooth_plane(src, zp, nxy) + rowoff;
       load_row4<VEC>(rowp, gx, nx, raw);
       if (haloL) { hal[0] = __ldg(rowp + x0 - 2); hal[1] = __ldg(rowp + x0 - 1); }
       if (haloR0) hal[0] = __ldg(rowp + gx + 4);
@@ -193,11 +203,26 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
     double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
     // ---- x pass ---- (inputs are screened only now, not at fetch time: touching the prefetched
     // registers earlier would stall on loads that are meant to fly across the y/z passes)
-    const bool raw_bad = input_unsafe(raw[0]) | input_unsafe(raw[1]) | input_unsafe(raw[2]) | input_unsafe(raw[3]) |
-                         input_unsafe(hal[0]) | input_unsafe(hal[1]);
-    const bool warp_bad = __any_sync(0xffffffffu, raw_bad);
-    if (!warp_bad) x_pass_row<true>(raw, hal, lane, gx, nx, buf + warp * 64);
-    else x_pass_row<false>(raw, hal, lane, gx, nx, buf + warp * 64);
+    // cheap screen first: one unsigned max over the six biased magnitudes says "all inside [2^-100, 2^100)";
+    // only warps that hold something else (zeros included) run the exact per-value test
+    bool warp_bad = false;
+    {
+      unsigned m = input_bias(raw[0]);
+      m = max(m, input_bias(raw[1])); m = max(m, input_bias(raw[2])); m = max(m, input_bias(raw[3]));
+      m = max(m, input_bias(hal[0])); m = max(m, input_bias(hal[1]));
+      if (__any_sync(0xffffffffu, m >= 0x64000000u)) {
+        const bool raw_bad = input_unsafe(raw[0]) | input_unsafe(raw[1]) | input_unsafe(raw[2]) | input_unsafe(raw[3]) |
+                             input_unsafe(hal[0]) | input_unsafe(hal[1]);
+        warp_bad = __any_sync(0xffffffffu, raw_bad);
+      }
+    }
+    if (xedge) {
+      if (!warp_bad) x_pass_row<true, true>(raw, hal, lane, gx, nx, buf + warp * 64);
+      else x_pass_row<false, true>(raw, hal, lane, gx, nx, buf + warp * 64);
+    } else {
+      if (!warp_bad) x_pass_row<true, false>(raw, hal, lane, gx, nx, buf + warp * 64);
+      else x_pass_row<false, false>(raw, hal, lane, gx, nx, buf + warp * 64);
+    }
     // tile-wide "unsafe input" flag for this plane through shared memory (three slots: the slot of
     // plane zp+2 is cleared after this barrier, one full barrier before its writers can run)
     if (warp_bad && lane == 0) s_bad[zp % 3] = 1;
@@ -208,8 +233,12 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
     // ---- y pass + z pass ----
     if (yz) {
       float ob[4], oi[4];
-      if (!cta_bad) yz_pass<true>(buf, warp, lane, yborder, S, ob, oi);
-      else yz_pass<false>(buf, warp, lane, yborder, S, ob, oi);
+      if (!yborder) {
+        if (!cta_bad) yz_pass<true, false>(buf, warp, lane, S, ob, oi);
+        else yz_pass<false, false>(buf, warp, lane, S, ob, oi);
+      } else {
+        yz_pass<false, true>(buf, warp, lane, S, ob, oi);
+      }
       const bool zborder = zp < 2 || zp >= nz - 2;
       const int zo = zp - 2;
       const bool emit_border = zborder && zp >= z0 && zp < z1;
