@@ -52,6 +52,28 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture
+    (profiles/r1_ncu_full_summary.csv: G1024, same flags; `ncu --set full`), or None"""
+    import csv
+    p = ROOT / "profiles" / "r1_ncu_full_summary.csv"
+    if not p.exists():
+        return None
+    try:
+        rows = list(csv.reader(p.open()))
+        hdr = rows[0]
+        ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(rows[1][ir], 1e9)
+        best = None
+        for r in rows[2:]:
+            if ("k_" + kernel) in r[ik]:
+                t = (float(r[ir]) + float(r[iw])) * unit
+                best = t if best is None else max(best, t)   # several launches (6-/18-connectivity): the larger
+        return best
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def kernel_bytes(name, n, nv, nt, nwords):
     """ALGORITHMIC bytes one launch of kernel `name` must move: n voxels f32 (per GPU),
     nwords 32-voxel bit words, nv/nt mesh vertices/triangles (per GPU)."""
@@ -293,7 +315,8 @@ def main():
     # whole-step algorithmic traffic (60 B/voxel for -p1 -l1 -b1, plus the surface term)
     step_bytes = 60 * GN + 24 * nv + 12 * nt
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                "frac": (achieved / peak) if achieved else None,
+                "traffic": ncu_traffic(top) if (world == 1 and n == 1024) else None, "peak_source": peak_src,
                 "kernel_ms": top_ms, "kernel_share_of_step": ktot[top] / (ms_step * args.steps),
                 "algorithmic_bytes_per_launch": kb, "scope": "rank 0's GPU" if world > 1 else "the GPU",
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,

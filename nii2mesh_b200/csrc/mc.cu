@@ -557,7 +557,7 @@ __device__ __forceinline__ float lew_u(float c0, float c1) {
 __device__ __forceinline__ bool near_int(float f, float tol) { return fabsf(__fsub_rn(f, rintf(f))) < tol; }
 __device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f - rint(f)) < tol; }
 
-__global__ void __launch_bounds__(128) k_mc_emit(mc_params p, mc_emit_params e) {
+__global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params e) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= e.n_active) return;
   const uint4 r = p.active[i];
