@@ -46,6 +46,7 @@ struct mc_params {
   const uint32_t *ibits;    // inside bit per voxel of the composed volume (bit rows, indexed with global z)
   uint4 *segbits;   // per segment: x/y/z edge-vertex bit masks, .w = packed counts -> vertex base (scan3)
   uint32_t *segt, *segc;  // per segment exclusive triangle / centroid-vertex bases
+  uint32_t *segcnt;       // per segment packed counts (dense copy for the scan: 4 B instead of a 16-byte stride)
   uint4 *active;
   unsigned int active_cap;
   b2m_scalars *sc;
@@ -386,7 +387,10 @@ __global__ void __launch_bounds__(MCB_THREADS) k_mc_classify(const __grid_consta
       packed = (uint32_t)pv | ((uint32_t)pt << 7) | ((uint32_t)pc << 16);
       if (!direct) cnt += tot;
     }
-    if (live) p.segbits[row * p.segs + seg] = make_uint4(exm, eym, ezm, packed);
+    if (live) {
+      p.segbits[row * p.segs + seg] = make_uint4(exm, eym, ezm, packed);
+      p.segcnt[row * p.segs + seg] = packed;
+    }
     a = c; ah = ch; b = d; bh = dh;
   }
   if (cnt) mc_flush(p, mybuf, cnt, lane);
@@ -437,7 +441,7 @@ __device__ __forceinline__ u3 block_excl_scan3(u3 a, u3 *total, u3 *sm) {
   return res;
 }
 
-__global__ void __launch_bounds__(S3_THREADS) k_scan3_reduce(const uint4 *__restrict__ seg, size_t n, uint32_t *__restrict__ part,
+__global__ void __launch_bounds__(S3_THREADS) k_scan3_reduce(const uint32_t *__restrict__ segcnt, size_t n, uint32_t *__restrict__ part,
                                                              size_t nblk) {
   __shared__ u3 sm[33];
   size_t base = (size_t)blockIdx.x * S3_TILE;
@@ -445,7 +449,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_scan3_reduce(const uint4 *__rest
 #pragma unroll
   for (int i = 0; i < S3_ITEMS; i++) {
     size_t idx = base + (size_t)i * S3_THREADS + threadIdx.x;
-    if (idx < n) s = u3_add(s, u3_unpack(__ldg(&seg[idx].w)));
+    if (idx < n) s = u3_add(s, u3_unpack(__ldg(segcnt + idx)));
   }
   u3 tot;
   block_excl_scan3(s, &tot, sm);
@@ -467,9 +471,9 @@ __global__ void __launch_bounds__(1024) k_scan3_single(uint32_t *part, size_t nb
   if (threadIdx.x == 0) { tot[0] = carry.v; tot[1] = carry.t; tot[2] = carry.c; }
 }
 
-__global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ seg, size_t n, const uint32_t *__restrict__ part,
-                                                            size_t nblk, uint32_t *__restrict__ segt, uint32_t *__restrict__ segc,
-                                                            uint32_t voff) {
+__global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ seg, const uint32_t *__restrict__ segcnt, size_t n,
+                                                            const uint32_t *__restrict__ part, size_t nblk,
+                                                            uint32_t *__restrict__ segt, uint32_t *__restrict__ segc, uint32_t voff) {
   __shared__ u3 sm[33];
   size_t base = (size_t)blockIdx.x * S3_TILE + (size_t)threadIdx.x * S3_ITEMS;
   u3 v[S3_ITEMS];
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ 
 #pragma unroll
   for (int i = 0; i < S3_ITEMS; i++) {
     size_t idx = base + i;
-    v[i] = idx < n ? u3_unpack(seg[idx].w) : u3{0, 0, 0};
+    v[i] = idx < n ? u3_unpack(__ldg(segcnt + idx)) : u3{0, 0, 0};
     s = u3_add(s, v[i]);
   }
   u3 tot;
@@ -497,7 +501,7 @@ static int mc_scan3_totals(b2m_ctx *ctx, mc_params &p, size_t nseg, b2m_scalars 
   size_t nblk = (nseg + S3_TILE - 1) / S3_TILE;
   B2M_TRY(b2m_reserve(ctx, BUF_SCAN1, nblk * 3 * 4));
   uint32_t *part = b2m_ptr<uint32_t>(ctx, BUF_SCAN1);
-  KT_LAUNCH(ctx, "scan3_reduce", k_scan3_reduce<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk));
+  KT_LAUNCH(ctx, "scan3_reduce", k_scan3_reduce<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segcnt, nseg, part, nblk));
   KT_LAUNCH(ctx, "scan3_single", k_scan3_single<<<1, 1024, 0, ctx->stream>>>(part, nblk, &d_sc->tot_v));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
@@ -506,7 +510,7 @@ static int mc_scan3_apply(b2m_ctx *ctx, mc_params &p, size_t nseg, uint32_t voff
   if (nseg == 0) return B2M_OK;
   size_t nblk = (nseg + S3_TILE - 1) / S3_TILE;
   uint32_t *part = b2m_ptr<uint32_t>(ctx, BUF_SCAN1);
-  KT_LAUNCH(ctx, "scan3_apply", k_scan3_apply<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, nseg, part, nblk, p.segt, p.segc, voff));
+  KT_LAUNCH(ctx, "scan3_apply", k_scan3_apply<<<(unsigned)nblk, S3_THREADS, 0, ctx->stream>>>(p.segbits, p.segcnt, nseg, part, nblk, p.segt, p.segc, voff));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -866,10 +870,11 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   const size_t nseg_all = prow * (p.zn + 1);          // + the next rank's first plane
   const size_t nvox = (size_t)p.sy * p.zn * p.sx;
   B2M_TRY(b2m_reserve(ctx, BUF_SEG, nseg_all * sizeof(uint4)));
-  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, (nseg + 1) * 2 * sizeof(uint32_t)));
+  B2M_TRY(b2m_reserve(ctx, BUF_SEG2, (nseg + 1) * 3 * sizeof(uint32_t)));
   p.segbits = b2m_ptr<uint4>(ctx, BUF_SEG);
   p.segt = b2m_ptr<uint32_t>(ctx, BUF_SEG2);
   p.segc = p.segt + nseg;
+  p.segcnt = p.segc + nseg;
   size_t cap = nvox / 8 + 65536;
   if (cap > nvox) cap = nvox;
   if (cap < 1) cap = 1;

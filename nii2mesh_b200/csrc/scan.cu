@@ -94,7 +94,7 @@ static int scan_rec(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t 
     if (d_total) CU_TRY(cudaMemsetAsync(d_total, 0, 4, ctx->stream));
     return B2M_OK;
   }
-  if (n <= 4096 && d_in == d_out) {
+  if (n <= 32768 && d_in == d_out) {  // one block, a few trips: cheaper than three launches (radix-sort histograms of small lists)
     KT_LAUNCH(ctx, "scan_single", k_scan_single<<<1, 1024, 0, ctx->stream>>>(d_out, n, d_total));
     CU_TRY(cudaGetLastError());
     return B2M_OK;
