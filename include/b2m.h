@@ -144,6 +144,24 @@ int b2m_meshify_slab(b2m_ctx *ctx, b2m_comm *comm, const float *d_slab, const in
 int b2m_meshify_slab_host(b2m_ctx *ctx, b2m_comm *comm, const float *h_slab, const int64_t gdims[3], int64_t z0,
                           int64_t nzl, const b2m_opts *opts, void **verts, void **tris, b2m_slab_result *out);
 
+/* ---- atlas front-end: one mesh per label of an indexed volume (replaces the label loop of src/nii2mesh.c:492-583) ----
+ * b2m_atlas_scan: nlabel = trunc(max(img)) (:494-501) and, per label i = 0..nlabel, the number of voxels with
+ * i-0.5 < img < i+0.5 (:553-563) and their bounding box, from ONE pass over the volume.  *infos is a malloc()'d array
+ * of nlabel+1 entries (b2m_atlas_free).  Returns B2M_FAIL (and prints the reference's message) when max(img) < 1.
+ * b2m_meshify_label_device: the reference's per-label meshify() - binary volume of that label, isolevel as given
+ * (the reference uses 0.5), -l forced off (:493) - computed on the label's bounding box only; the mesh is the one the
+ * reference gets from the whole binary volume, bit for bit.  Labels with nvox == 0 are skipped by the reference
+ * (:564-567): calling this for one is a usage error. */
+typedef struct {
+  int label;
+  long long nvox;
+  int lo[3], hi[3]; /* inclusive bounding box of the label's voxels (undefined when nvox == 0) */
+} b2m_label_info;
+int b2m_atlas_scan(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], int *nlabel, b2m_label_info **infos);
+void b2m_atlas_free(b2m_label_info *infos);
+int b2m_meshify_label_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_label_info *info,
+                             const b2m_opts *opts, b2m_result *res);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

@@ -40,6 +40,7 @@ enum {
   BUF_LARGEST,     // largest 18-connected cluster bits
   BUF_KEEP,        // largest | dilate25(largest)
   BUF_CCLIST,      // CC: [count, tile-root slots...]
+  BUF_ATLAS,       // atlas: per-label table (scan) / cropped binary sub-volume (one label)
   BUF_MB,          // marching-cubes inside bits (threshold -> composed in place by k_dilate_bbox)
   BUF_NODES,       // union-find nodes (uint2 {parent, size|faceflag}) : 16 per bit word
   BUF_SCALARS,     // small device scalar block (b2m_scalars)
@@ -152,6 +153,7 @@ struct b2m_ctx {
   // weld): the host entry points use it to allocate and pre-fault the output blocks while the GPU keeps working
   void (*counts_hook)(void *user, size_t nverts, size_t ntris);
   void *hook_user;
+  int origin[3];           // atlas: where the (cropped) volume of the current call sits in the caller's volume
   size_t last_nvox, last_nv, last_nt;  // geometry and marching-cubes totals of the previous host call
   cudaStream_t stream;
   b2m_buf buf[BUF_COUNT];

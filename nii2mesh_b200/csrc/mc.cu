@@ -31,6 +31,7 @@
 struct mc_params {
   compose_params c;
   int lo0, lo1, lo2;
+  int org0, org1, org2;  // atlas: position of this (cropped) volume inside the caller's volume; exported coordinates only
   int sx, sy, sz;   // sub-volume size in voxels
   int zs0, zn;      // slabs: sub-volume planes [zs0, zs0+zn) are owned by this rank (segment arrays hold zn+1 planes:
                     // the last one is the next rank's first plane, received after the scan)
@@ -588,7 +589,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
   } else {
     c[2] = c[5] = c[6] = c[7] = c[0];
   }
-  const float flo0 = (float)p.lo0, flo1 = (float)p.lo1, flo2 = (float)p.lo2;
+  const float flo0 = (float)(p.lo0 + p.org0), flo1 = (float)(p.lo1 + p.org1), flo2 = (float)(p.lo2 + p.org2);
   // ---- own edge vertices ----
   if (ex | ey | ez) {
     uint32_t vid = __ldg(&p.segbits[sidx].w) + (uint32_t)pv;
@@ -619,7 +620,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
       // direction of the LAST cube (raster order) that touches the edge: that soup copy has the
       // highest index, so its coordinates survive the reference's weld (src/meshify.c:99-100).
       const double iso = (double)p.c.iso;
-      const double gx = (double)(p.lo0 + x), gy = (double)(p.lo1 + y), gz = (double)(p.lo2 + z);
+      const double gx = (double)(p.lo0 + p.org0 + x), gy = (double)(p.lo1 + p.org1 + y), gz = (double)(p.lo2 + p.org2 + z);
       const double v0 = (double)c[0];
       if (ex) {
         const double v1 = (double)c[1];
@@ -706,8 +707,8 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     const int ca = MC_EDGE_A[a0], cb = MC_EDGE_B[a0];
     const double iso = (double)p.c.iso;
     const double mu = __ddiv_rn(__dsub_rn(iso, (double)c[ca]), __dsub_rn((double)c[cb], (double)c[ca]));
-    const double ax = (double)(p.lo0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + z + (ca >> 2));
-    const double bx = (double)(p.lo0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + z + (cb >> 2));
+    const double ax = (double)(p.lo0 + p.org0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + p.org1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + p.org2 + z + (ca >> 2));
+    const double bx = (double)(p.lo0 + p.org0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + p.org1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + p.org2 + z + (cb >> 2));
     p.sc->pts0[0] = __dadd_rn(ax, __dmul_rn(mu, bx - ax));
     p.sc->pts0[1] = __dadd_rn(ay, __dmul_rn(mu, by - ay));
     p.sc->pts0[2] = __dadd_rn(az, __dmul_rn(mu, bz - az));
@@ -742,8 +743,8 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
           if (!((nearm >> a) & 1u)) continue;
           const int ca = MC_EDGE_A[a], cb = MC_EDGE_B[a];
           const double mu = __ddiv_rn(__dsub_rn(iso, (double)c[ca]), __dsub_rn((double)c[cb], (double)c[ca]));
-          const double ax = (double)(p.lo0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + z + (ca >> 2));
-          const double bx = (double)(p.lo0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + z + (cb >> 2));
+          const double ax = (double)(p.lo0 + p.org0 + x + ((ca ^ (ca >> 1)) & 1)), ay = (double)(p.lo1 + p.org1 + y + ((ca >> 1) & 1)), az = (double)(p.lo2 + p.org2 + z + (ca >> 2));
+          const double bx = (double)(p.lo0 + p.org0 + x + ((cb ^ (cb >> 1)) & 1)), by = (double)(p.lo1 + p.org1 + y + ((cb >> 1) & 1)), bz = (double)(p.lo2 + p.org2 + z + (cb >> 2));
           const double px = __dadd_rn(ax, __dmul_rn(mu, bx - ax)), py = __dadd_rn(ay, __dmul_rn(mu, by - ay)), pz = __dadd_rn(az, __dmul_rn(mu, bz - az));
           const double free_axis = a >= 8 ? pz : ((a & 1) ? py : px);
           if (near_int_d(free_axis, 2e-5))
@@ -813,6 +814,7 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   p.classic = o->backend == B2M_BACKEND_CLASSIC;
   p.original_mc = o->original_mc != 0;
   p.lo0 = fo->lo[0]; p.lo1 = fo->lo[1]; p.lo2 = fo->lo[2];
+  p.org0 = ctx->origin[0]; p.org1 = ctx->origin[1]; p.org2 = ctx->origin[2];
   if (p.classic) {  // voxels lo .. hi-1 (src/oldcubes.c:475-478)
     p.sx = fo->hi[0] - fo->lo[0]; p.sy = fo->hi[1] - fo->lo[1]; p.sz = fo->hi[2] - fo->lo[2];
   } else {          // hi-lo+1 voxels: one more than the volume can supply when hi == dim (src/MarchingCubes.c:1088-1090)

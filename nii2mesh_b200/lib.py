@@ -40,6 +40,11 @@ class SlabResult(C.Structure):
                 ("v_cent_off", C.c_int64), ("v_extra_off", C.c_int64), ("tri_off", C.c_int64)]
 
 
+class LabelInfo(C.Structure):
+    """b2m_label_info: voxel count and bounding box of one atlas label"""
+    _fields_ = [("label", C.c_int), ("nvox", C.c_longlong), ("lo", C.c_int * 3), ("hi", C.c_int * 3)]
+
+
 class B2MError(RuntimeError):
     pass
 
@@ -84,6 +89,10 @@ def load():
     L.b2m_meshify_device.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(Result)]
     L.b2m_meshify_host.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
     L.b2m_fetch_mesh.argtypes = [vp, C.POINTER(Result), vp, vp]
+    L.b2m_atlas_scan.argtypes = [vp, vp, i64p, C.POINTER(C.c_int), C.POINTER(C.POINTER(LabelInfo))]
+    L.b2m_atlas_free.argtypes = [C.POINTER(LabelInfo)]
+    L.b2m_atlas_free.restype = None
+    L.b2m_meshify_label_device.argtypes = [vp, vp, i64p, C.POINTER(LabelInfo), C.POINTER(Opts), C.POINTER(Result)]
     L.b2m_comm_nccl_id.argtypes = [vp]
     L.b2m_comm_create_nccl.argtypes = [C.POINTER(vp), vp, vp, C.c_int, C.c_int]
     L.b2m_comm_create_local.argtypes = [C.POINTER(vp), C.c_int]
@@ -240,6 +249,33 @@ class Engine:
         t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(r.ntris, 3)).copy()
         _libc.free(pv)
         _libc.free(pt)
+        return v, t, r
+
+    # ---- atlas front-end (src/nii2mesh.c:492-583) ----
+    def atlas_scan(self, dvol):
+        """[LabelInfo] for labels 0..nlabel of an indexed volume on the device (one pass)"""
+        n, p = C.c_int(), C.POINTER(LabelInfo)()
+        self._chk(self.lib.b2m_atlas_scan(self.ctx, dvol.ptr, _dims(dvol.shape), C.byref(n), C.byref(p)))
+        out = []
+        for i in range(n.value + 1):
+            li = LabelInfo()
+            C.memmove(C.byref(li), C.byref(p[i]), C.sizeof(LabelInfo))
+            out.append(li)
+        self.lib.b2m_atlas_free(p)
+        return out
+
+    def meshify_label(self, dvol, info, iso=0.5, original_mc=0, pre_smooth=True, fill_bubbles=False,
+                      backend=BACKEND_LEWINER, fetch=True):
+        """the reference's per-label meshify() (binary volume of the label, -l off) on the label's bounding box"""
+        o = self._opts(iso, original_mc, pre_smooth, 0, fill_bubbles, backend)
+        r = Result()
+        self._chk(self.lib.b2m_meshify_label_device(self.ctx, dvol.ptr, _dims(dvol.shape), C.byref(info), C.byref(o),
+                                                    C.byref(r)))
+        if not fetch:
+            return None, None, r
+        v = np.empty((r.nverts, 3), np.float64)
+        t = np.empty((r.ntris, 3), np.int32)
+        self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
         return v, t, r
 
     def meshify_slab(self, comm, dslab, gshape, z0, iso, original_mc=0, pre_smooth=True, only_largest=True,
