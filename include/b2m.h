@@ -162,6 +162,12 @@ void b2m_atlas_free(b2m_label_info *infos);
 int b2m_meshify_label_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_label_info *info,
                              const b2m_opts *opts, b2m_result *res);
 
+/* ---- automatic isolevel (-i d / m / b): replaces setThreshold(), src/isolevel.c:245-277 ----
+ * dark_medium_bright_123 = 1 dark, 2 medium, 3 bright (src/nii2mesh.c:398-407).  Range, NaN count and the two
+ * histograms are GPU reductions; the 256-bin Otsu search runs on the host.  The value equals the reference's float. */
+int b2m_isolevel_device(b2m_ctx *ctx, const float *d_img, size_t nvox, int dark_medium_bright_123, float *isolevel);
+int b2m_isolevel_host(b2m_ctx *ctx, const float *h_img, size_t nvox, int dark_medium_bright_123, float *isolevel);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

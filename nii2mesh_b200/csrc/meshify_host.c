@@ -17,6 +17,7 @@
 
 #include "../../include/b2m.h"
 #include "../../include/meshify.h"
+#include "../../include/isolevel.h"
 
 int b2m_get_default_backend(void);
 
@@ -60,6 +61,19 @@ int meshify(float *img, short dim[3], int originalMC, float isolevel, vec3i **t,
   *nt = res.ntris;
   *np = res.nverts;
   return EXIT_SUCCESS;
+}
+
+/* -i d / m / b (src/isolevel.c:245-277, called from src/nii2mesh.c:586): same prototype, GPU histograms inside */
+float setThreshold(float *img, int nvox, int darkMediumBright123) {
+  b2m_ctx *ctx = get_ctx();
+  float iso = NAN;
+  if (!ctx) return iso; /* no CUDA device: there is no CPU path */
+  if (nvox < 1) return 1;
+  if (b2m_isolevel_host(ctx, img, (size_t)nvox, darkMediumBright123, &iso) != B2M_OK) {
+    fprintf(stderr, "setThreshold: %s\n", b2m_last_error());
+    return NAN;
+  }
+  return iso;
 }
 
 /* voxel -> world transform of the vertices (src/meshify.c:1021-1045).  Each coordinate is the FP64

@@ -93,6 +93,10 @@ def load():
     L.b2m_atlas_free.argtypes = [C.POINTER(LabelInfo)]
     L.b2m_atlas_free.restype = None
     L.b2m_meshify_label_device.argtypes = [vp, vp, i64p, C.POINTER(LabelInfo), C.POINTER(Opts), C.POINTER(Result)]
+    L.b2m_isolevel_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+    L.b2m_isolevel_host.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
+    L.setThreshold.argtypes = [vp, C.c_int, C.c_int]
+    L.setThreshold.restype = C.c_float
     L.b2m_comm_nccl_id.argtypes = [vp]
     L.b2m_comm_create_nccl.argtypes = [C.POINTER(vp), vp, vp, C.c_int, C.c_int]
     L.b2m_comm_create_local.argtypes = [C.POINTER(vp), C.c_int]
@@ -250,6 +254,17 @@ class Engine:
         _libc.free(pv)
         _libc.free(pt)
         return v, t, r
+
+    def isolevel(self, vol_or_dvol, dark_medium_bright_123):
+        """-i d / m / b: the reference's setThreshold() (src/isolevel.c:245-277); 1 = dark, 2 = medium, 3 = bright"""
+        iso = C.c_float()
+        if isinstance(vol_or_dvol, DeviceVolume):
+            n = int(np.prod(vol_or_dvol.shape))
+            self._chk(self.lib.b2m_isolevel_device(self.ctx, vol_or_dvol.ptr, n, int(dark_medium_bright_123), C.byref(iso)))
+        else:
+            v = np.ascontiguousarray(vol_or_dvol, dtype=np.float32)
+            self._chk(self.lib.b2m_isolevel_host(self.ctx, v.ctypes.data, v.size, int(dark_medium_bright_123), C.byref(iso)))
+        return float(iso.value)
 
     # ---- atlas front-end (src/nii2mesh.c:492-583) ----
     def atlas_scan(self, dvol):

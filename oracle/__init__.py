@@ -97,6 +97,13 @@ class Oracle:
                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float)]
 
+    def set_threshold(self, vol, dark_medium_bright_123):
+        """restatement of setThreshold() (src/isolevel.c:245-277): -i d / m / b"""
+        v = _f32(vol)
+        self.lib.orc_set_threshold.restype = C.c_float
+        self.lib.orc_set_threshold.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        return float(self.lib.orc_set_threshold(v.ctypes.data, v.size, int(dark_medium_bright_123)))
+
     def smooth(self, vol):
         v = _f32(vol).copy()
         nz, ny, nx = v.shape
@@ -208,6 +215,13 @@ class Ref:
                                     C.POINTER(C.c_int)]
         L.unify_vertices.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_bool]
         L.remove_degenerate_triangles.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_bool]
+
+    def set_threshold(self, vol, dark_medium_bright_123):
+        """setThreshold() (src/isolevel.c:245-277): -i d / m / b"""
+        v = _f32(vol)
+        self.lib.setThreshold.restype = C.c_float
+        self.lib.setThreshold.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        return float(self.lib.setThreshold(v.ctypes.data, v.size, int(dark_medium_bright_123)))
 
     def smooth(self, vol):
         v = _f32(vol).copy()

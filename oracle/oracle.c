@@ -647,4 +647,115 @@ int orc_meshify(float *img, int nx, int ny, int nz, int originalMC, float isolev
   return 0;
 }
 
+/* ---- isolevel selection: setThreshold() (/root/reference/src/isolevel.c:245-277) ---------------------------------
+ * robust range = 2nd..98th percentile on a 1001-bin histogram (nifti_robust_range :35-139, ignoreZeroVoxels = 0), a
+ * 256-bin histogram over it (:251-262), Otsu on that (nii_otsu :141-243: mode 5 -> dark / bright, mode 3 -> medium). */
+static int orc_robust_range(const float *img, int nvox, float *pct2, float *pct98) {
+  *pct2 = 0.0f; *pct98 = 1.0f;
+  if (nvox < 1) return 1;
+  float mn = INFINITY, mx = -INFINITY;
+  size_t nNan = 0;
+  for (int i = 0; i < nvox; i++) {
+    if (isnan(img[i])) { nNan++; continue; }
+    mn = fminf(img[i], mn);
+    mx = fmaxf(img[i], mx);
+  }
+  if (mn > mx) return 0;
+  if (mn == mx) { *pct2 = mn; *pct98 = mx; return 0; }
+  size_t nZero = nNan; /* zeros are not ignored (:74-76) */
+  size_t n2pct = (size_t)round(((size_t)nvox - nZero) * 0.02);
+  if (n2pct < 1 || ((size_t)nvox - nZero) < 100) { *pct2 = mn; *pct98 = mx; return 0; }
+  enum { nBins = 1001 };
+  float scl = (nBins - 1) / (mx - mn);
+  static int hist[nBins];
+  for (int i = 0; i < nBins; i++) hist[i] = 0;
+  for (int i = 0; i < nvox; i++) {
+    if (isnan(img[i])) continue;
+    hist[(int)round((img[i] - mn) * scl)]++;
+  }
+  size_t n = 0, lo = 0;
+  while (n < n2pct) { n += hist[lo]; lo++; }
+  lo--;
+  n = 0;
+  int hi = nBins;
+  while (n < n2pct) { hi--; n += hist[hi]; }
+  if ((int)lo == hi) {
+    int ok = -1;
+    while (ok != 0) {
+      if (lo > 0) { lo--; if (hist[lo] > 0) ok = 0; }
+      if (ok != 0 && hi < nBins - 1) { hi++; if (hist[hi] > 0) ok = 0; }
+      if (lo == 0 && hi == nBins - 1) ok = 0;
+    }
+  }
+  *pct2 = lo / scl + mn;
+  *pct98 = hi / scl + mn;
+  return 0;
+}
+
+static void orc_otsu(const int *H, int nBin, int mode, int *dark, int *mid, int *bright) {
+  *dark = *mid = *bright = 0;
+  double Sum = 0.0;
+  for (int v = 0; v < nBin; v++) Sum = Sum + H[v];
+  if (Sum <= 0) return;
+  double *P = (double *)malloc((size_t)nBin * nBin * sizeof(double));
+  double *S = (double *)malloc((size_t)nBin * nBin * sizeof(double));
+  P[0] = H[0]; S[0] = H[0]; /* sic: un-normalised (:159-160) */
+  for (int v = 1; v < nBin; v++) {
+    double Prob = H[v] / Sum;
+    P[v] = P[v - 1] + Prob;
+    S[v] = S[v - 1] + (v + 1) * Prob;
+  }
+  for (int u = 1; u < nBin; u++)
+    for (int v = u; v < nBin; v++) {
+      P[u * nBin + v] = P[v] - P[u - 1];
+      S[u * nBin + v] = S[v] - S[u - 1];
+    }
+  for (int u = 0; u < nBin; u++)
+    for (int v = u; v < nBin; v++)
+      if (P[u * nBin + v] != 0) P[u * nBin + v] = (S[u * nBin + v] * S[u * nBin + v]) / P[u * nBin + v];
+  if (mode == 5) {
+    int lo = (int)(0.25 * nBin), mi = (int)(0.50 * nBin), hi = (int)(0.75 * nBin);
+    double max = P[lo] + P[(lo + 1) * nBin + mi] + P[(mi + 1) * nBin + hi] + P[(hi + 1) * nBin + 255];
+    for (int l = 0; l < nBin - 3; l++)
+      for (int m = l + 1; m < nBin - 2; m++)
+        for (int h = m + 1; h < nBin - 1; h++) {
+          double v = P[l] + P[(l + 1) * nBin + m] + P[(m + 1) * nBin + h] + P[(h + 1) * nBin + 255];
+          if (v > max) { lo = l; mi = m; hi = h; max = v; }
+        }
+    *dark = lo; *mid = mi; *bright = hi;
+  } else {
+    int thresh = (int)(0.25 * nBin);
+    double max = P[thresh] + P[(thresh + 1) * nBin + nBin - 1];
+    for (int i = 0; i < nBin - 1; i++) {
+      double v = P[i] + P[(i + 1) * nBin + nBin - 1];
+      if (v > max) { thresh = i; max = v; }
+    }
+    *dark = *mid = *bright = thresh;
+  }
+  free(P); free(S);
+}
+
+float orc_set_threshold(const float *img, int nvox, int darkMediumBright123) {
+  float mn, mx;
+  if (orc_robust_range(img, nvox, &mn, &mx) != 0) return 1;
+  enum { kOtsuBins = 256 };
+  float scl = (kOtsuBins - 1) / (mx - mn);
+  int hist[kOtsuBins];
+  for (int i = 0; i < kOtsuBins; i++) hist[i] = 0;
+  for (int i = 0; i < nvox; i++) {
+    if (isnan(img[i])) continue;
+    int idx = (int)round((img[i] - mn) * scl);
+    idx = idx < kOtsuBins - 1 ? idx : kOtsuBins - 1;
+    idx = idx > 0 ? idx : 0;
+    hist[idx]++;
+  }
+  int dark, mid, bright;
+  if (darkMediumBright123 == 1 || darkMediumBright123 == 3) {
+    orc_otsu(hist, kOtsuBins, 5, &dark, &mid, &bright);
+    return darkMediumBright123 == 1 ? (dark / scl) + mn : (bright / scl) + mn;
+  }
+  orc_otsu(hist, kOtsuBins, 3, &dark, &mid, &bright);
+  return (mid / scl) + mn;
+}
+
 void orc_free(void *p) { free(p); }

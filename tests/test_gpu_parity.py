@@ -277,3 +277,21 @@ def test_cc_tile_root_list_overflow_fallback(eng, orc, monkeypatch):
             b = orc.front(vol, iso, ps, ol, fb)
             assert np.array_equal(a["mask"] != 0, b["mask"] != 0), (name, ps, ol, fb)
             assert bits_differ(a["img"], b["img"]) == 0, (name, ps, ol, fb)
+
+
+def test_isolevel_selection(eng, orc, libb2m):
+    """-i d / m / b through b2m_isolevel_device / _host and the reference-named setThreshold(): the reference's float"""
+    import test_oracle
+    for name, vol in test_oracle._isolevel_cases().items():
+        d = eng.upload(vol)
+        try:
+            for mode in (1, 2, 3):
+                want = orc.set_threshold(vol, mode)
+                got_d, got_h = eng.isolevel(d, mode), eng.isolevel(vol, mode)
+                assert got_d == want or (np.isnan(got_d) and np.isnan(want)), (name, mode, got_d, want)
+                assert got_h == got_d or (np.isnan(got_h) and np.isnan(got_d)), (name, mode)
+        finally:
+            d.free()
+    bet = np.ascontiguousarray(VOLS["bet"][0])
+    iso = libb2m.setThreshold(bet.ctypes.data, bet.size, 2)
+    assert iso == orc.set_threshold(bet, 2) and abs(iso - 67.729) < 1e-3   # BASELINE config 1: "default medium isolevel"

@@ -139,3 +139,23 @@ def test_canon_detects_differences(orc):
     bad[0] = bad[0][[1, 0, 2]]  # flipped winding
     with pytest.raises(AssertionError):
         assert_same_mesh(v, bad, v, t)
+
+
+def _isolevel_cases():
+    rng = np.random.default_rng(1)
+    out = {k: v[0] for k, v in cases.volumes().items()}
+    out["binary"] = (rng.random((20, 20, 20)) > 0.7).astype(np.float32)
+    out["const"] = np.full((5, 5, 5), 2.0, np.float32)
+    out["tiny"] = rng.standard_normal((3, 4, 5)).astype(np.float32)                      # < 100 voxels: full range
+    out["nan"] = np.where(rng.random((16, 16, 16)) > 0.9, np.nan, rng.standard_normal((16, 16, 16))).astype(np.float32)
+    out["spike"] = np.concatenate([np.zeros(5000), np.ones(5000), [1000.0]]).astype(np.float32).reshape(1, 1, -1)
+    return out
+
+
+def test_isolevel_restatement_equals_reference(orc, ref_lewiner):
+    """-i d / m / b: setThreshold() (src/isolevel.c:245-277): robust range + Otsu; BASELINE config 1 uses bet 'medium'"""
+    for name, vol in _isolevel_cases().items():
+        for mode in (1, 2, 3):
+            a, b = orc.set_threshold(vol, mode), ref_lewiner.set_threshold(vol, mode)
+            assert a == b or (np.isnan(a) and np.isnan(b)), (name, mode, a, b)
+    assert abs(orc.set_threshold(cases.volumes()["bet"][0], 2) - 67.729) < 1e-3
