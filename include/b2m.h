@@ -168,6 +168,20 @@ int b2m_meshify_label_device(b2m_ctx *ctx, const float *d_img, const int64_t dim
 int b2m_isolevel_device(b2m_ctx *ctx, const float *d_img, size_t nvox, int dark_medium_bright_123, float *isolevel);
 int b2m_isolevel_host(b2m_ctx *ctx, const float *h_img, size_t nvox, int dark_medium_bright_123, float *isolevel);
 
+/* ---- the formats either side of the path, on the GPU ----
+ * b2m_ingest_*: load_nii()'s voxel conversion (src/nii2mesh.c:155-172): raw u8 / i16 / u16 / f32 voxels (NIfTI
+ * datatype codes 2 / 4 / 512 / 16) -> f32, (raw * scl_slope) + scl_inter in f32, scl_slope 0 -> 1.  The raw bytes
+ * cross PCIe; d_out is a device buffer of nvox floats.
+ * b2m_apply_sform_device: apply_sform() (src/meshify.c:1021-1045) on the device mesh of res, in place.
+ * b2m_meshify_raw_host: ingest + meshify + (optional) sform + D2H in one call: what nii2() does around meshify(). */
+int b2m_ingest_host(b2m_ctx *ctx, const void *h_raw, int datatype, size_t nvox, float scl_slope, float scl_inter, float *d_out);
+int b2m_ingest_device(b2m_ctx *ctx, const void *d_raw, int datatype, size_t nvox, float scl_slope, float scl_inter, float *d_out);
+int b2m_apply_sform_device(b2m_ctx *ctx, const b2m_result *res, const float srow_x[4], const float srow_y[4],
+                           const float srow_z[4]);
+int b2m_meshify_raw_host(b2m_ctx *ctx, const void *h_raw, int datatype, const int64_t dims[3], float scl_slope,
+                         float scl_inter, const b2m_opts *opts, const float *srow_x, const float *srow_y,
+                         const float *srow_z, void **verts, void **tris, b2m_result *res);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

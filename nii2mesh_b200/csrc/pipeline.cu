@@ -382,6 +382,38 @@ extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t 
   return B2M_OK;
 }
 
+// meshify() from the RAW voxels of a NIfTI file and with the voxel->world transform fused in: what nii2() does around
+// meshify() (load_nii's type conversion, src/nii2mesh.c:155-172; apply_sform, src/nii2mesh.c:328), minus the 4-byte
+// widening before the PCIe copy and the host pass over the vertices.  srow_* may be NULL (voxel coordinates).
+extern "C" int b2m_ingest_host(b2m_ctx *ctx, const void *h_raw, int datatype, size_t nvox, float scl_slope, float scl_inter, float *d_out);
+extern "C" int b2m_apply_sform_device(b2m_ctx *ctx, const b2m_result *res, const float srow_x[4], const float srow_y[4], const float srow_z[4]);
+extern "C" int b2m_meshify_raw_host(b2m_ctx *ctx, const void *h_raw, int datatype, const int64_t dims[3], float scl_slope,
+                                    float scl_inter, const b2m_opts *opts, const float *srow_x, const float *srow_y,
+                                    const float *srow_z, void **verts, void **tris, b2m_result *res) {
+  if (!ctx || !h_raw || !dims || !opts || !res || !verts || !tris) { b2m_set_error("null argument"); return B2M_EARG; }
+  B2M_TRY(check_dims(dims));
+  CU_TRY(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  B2M_TRY(b2m_reserve(ctx, BUF_INPUT, n * 4));
+  host_out ho;
+  memset(&ho, 0, sizeof(ho));
+  host_out_early(ctx, &ho, n);
+  const double t0 = wall_ms();
+  int rc = b2m_ingest_host(ctx, h_raw, datatype, n, scl_slope, scl_inter, b2m_ptr<float>(ctx, BUF_INPUT));
+  const double t1 = wall_ms();
+  ctx->counts_hook = host_out_hook;
+  ctx->hook_user = &ho;
+  if (rc == B2M_OK) rc = b2m_meshify_device(ctx, b2m_ptr<float>(ctx, BUF_INPUT), dims, opts, res);
+  if (rc == B2M_OK && srow_x && srow_y && srow_z) rc = b2m_apply_sform_device(ctx, res, srow_x, srow_y, srow_z);
+  const double t2 = wall_ms();
+  host_out_remember(ctx, &ho, n);
+  rc = host_out_finish(ctx, &ho, rc, res->d_verts, (size_t)res->nverts, res->d_tris, (size_t)res->ntris, verts, tris);
+  if (rc != B2M_OK) return rc;
+  res->h2d_ms = (float)(t1 - t0);
+  res->d2h_ms = (float)(wall_ms() - t2);
+  return B2M_OK;
+}
+
 // z-slab path from HOST memory: this rank's planes in, this rank's mesh blocks out (malloc()'d, caller frees).
 extern "C" int b2m_meshify_slab_host(b2m_ctx *ctx, b2m_comm *comm, const float *h_slab, const int64_t gdims[3], int64_t z0,
                                      int64_t nzl, const b2m_opts *opts, void **verts, void **tris, b2m_slab_result *out) {

@@ -97,6 +97,10 @@ def load():
     L.b2m_isolevel_host.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     L.setThreshold.argtypes = [vp, C.c_int, C.c_int]
     L.setThreshold.restype = C.c_float
+    L.b2m_ingest_host.argtypes = [vp, vp, C.c_int, C.c_size_t, C.c_float, C.c_float, vp]
+    L.b2m_apply_sform_device.argtypes = [vp, C.POINTER(Result), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.b2m_meshify_raw_host.argtypes = [vp, vp, C.c_int, i64p, C.c_float, C.c_float, C.POINTER(Opts), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
     L.b2m_comm_nccl_id.argtypes = [vp]
     L.b2m_comm_create_nccl.argtypes = [C.POINTER(vp), vp, vp, C.c_int, C.c_int]
     L.b2m_comm_create_local.argtypes = [C.POINTER(vp), C.c_int]
@@ -249,6 +253,35 @@ class Engine:
         pv, pt = C.c_void_p(), C.c_void_p()
         self._chk(self.lib.b2m_meshify_host(self.ctx, vol.ctypes.data, _dims(vol.shape), C.byref(o), C.byref(pv),
                                             C.byref(pt), C.byref(r)))
+        v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(r.nverts, 3)).copy()
+        t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(r.ntris, 3)).copy()
+        _libc.free(pv)
+        _libc.free(pt)
+        return v, t, r
+
+    NIFTI_DT = {np.dtype(np.uint8): 2, np.dtype(np.int16): 4, np.dtype(np.uint16): 512, np.dtype(np.float32): 16}
+
+    def ingest(self, raw, slope=1.0, inter=0.0):
+        """raw voxels (u8 / i16 / u16 / f32 array, z,y,x) -> f32 DeviceVolume, converted on the device like load_nii()"""
+        raw = np.ascontiguousarray(raw)
+        out = DeviceVolume(self, raw.shape, self.alloc(raw.size * 4))
+        self._chk(self.lib.b2m_ingest_host(self.ctx, raw.ctypes.data, self.NIFTI_DT[raw.dtype], raw.size, float(slope),
+                                           float(inter), out.ptr))
+        return out
+
+    def meshify_raw(self, raw, iso, slope=1.0, inter=0.0, srow=None, original_mc=0, pre_smooth=True, only_largest=True,
+                    fill_bubbles=False, backend=BACKEND_LEWINER):
+        """raw voxels in, world-space mesh out: ingest + meshify + apply_sform (srow = 3 x 4 floats or None) + D2H"""
+        raw = np.ascontiguousarray(raw)
+        o = self._opts(iso, original_mc, pre_smooth, only_largest, fill_bubbles, backend)
+        r = Result()
+        pv, pt = C.c_void_p(), C.c_void_p()
+        rows = [None, None, None]
+        if srow is not None:
+            rows = [(C.c_float * 4)(*[float(x) for x in srow[k]]) for k in range(3)]
+        self._chk(self.lib.b2m_meshify_raw_host(self.ctx, raw.ctypes.data, self.NIFTI_DT[raw.dtype], _dims(raw.shape), float(slope),
+                                                float(inter), C.byref(o), rows[0], rows[1], rows[2], C.byref(pv), C.byref(pt),
+                                                C.byref(r)))
         v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(r.nverts, 3)).copy()
         t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(r.ntris, 3)).copy()
         _libc.free(pv)

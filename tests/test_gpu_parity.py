@@ -295,3 +295,44 @@ def test_isolevel_selection(eng, orc, libb2m):
     bet = np.ascontiguousarray(VOLS["bet"][0])
     iso = libb2m.setThreshold(bet.ctypes.data, bet.size, 2)
     assert iso == orc.set_threshold(bet, 2) and abs(iso - 67.729) < 1e-3   # BASELINE config 1: "default medium isolevel"
+
+
+def test_ingest_and_sform_on_device(eng, orc, libb2m):
+    """load_nii's voxel conversion (src/nii2mesh.c:155-172) and apply_sform (src/meshify.c:1021-1045) on the GPU:
+    raw u8 / i16 / u16 / f32 voxels in, world-space mesh out, equal to convert-on-host + meshify + host apply_sform"""
+    rng = np.random.default_rng(9)
+    base = VOLS["blobs2"][0]
+    srow = [[-0.7, 0.01, 0.0, 90.5], [0.02, 0.6, -0.03, -126.25], [0.0, 0.05, 0.9, -72.0]]   # negative determinant proxy: winding flips
+    for dt, slope, inter in ((np.uint8, 0.025, -3.0), (np.int16, 0.001, 0.5), (np.uint16, 0.0, 0.0), (np.float32, 1.5, -0.25)):
+        if dt == np.float32:
+            raw = base.astype(np.float32)
+        else:
+            info = np.iinfo(dt)
+            span = base.max() - base.min()
+            raw = ((base - base.min()) / span * min(info.max, 4000)).astype(dt)
+        s = np.float32(slope if slope != 0.0 else 1.0)
+        vol = (raw.astype(np.float32) * s) + np.float32(inter)          # f32 product, f32 sum
+        d = eng.ingest(raw, slope, inter)
+        try:
+            assert bits_differ(d.to_host(), vol) == 0, dt
+        finally:
+            d.free()
+        iso = float(np.float32(vol.mean()))
+        for backend in (0, 1):
+            hv, ht, _ = eng.meshify(vol, iso, 0, 1, 1, 1, backend)
+            # the reference's apply_sform on the host mesh (our meshify_host.c copy is pinned to it in test_abi)
+            v2 = np.ascontiguousarray(hv.copy())
+            t2 = np.ascontiguousarray(ht.copy())
+            libb2m.apply_sform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            libb2m.apply_sform.restype = None
+            rows = [(C.c_float * 4)(*r) for r in srow]
+            libb2m.apply_sform(t2.ctypes.data, v2.ctypes.data, len(t2), len(v2), rows[0], rows[1], rows[2])
+            gv, gt, r = eng.meshify_raw(raw, iso, slope, inter, srow, 0, 1, 1, 1, backend)
+            assert np.array_equal(gt, t2) and np.array_equal(gv.view(np.uint64), v2.view(np.uint64)), (dt, backend)
+            assert not np.array_equal(gt, ht)   # the winding really flipped
+    # without srow: plain voxel coordinates, identical to meshify()
+    raw = (np.clip(base, -2, 2) * 1000).astype(np.int16)
+    vol = raw.astype(np.float32) * np.float32(0.001)
+    hv, ht, _ = eng.meshify(vol, 0.2, 0, 1, 1, 0, 0)
+    gv, gt, _ = eng.meshify_raw(raw, 0.2, 0.001, 0.0, None, 0, 1, 1, 0, 0)
+    assert np.array_equal(gt, ht) and np.array_equal(gv.view(np.uint64), hv.view(np.uint64))
