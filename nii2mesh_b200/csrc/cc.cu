@@ -940,7 +940,10 @@ static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint
   if (M >= (1u << 30)) { b2m_set_error("seam: too many seam components"); return B2M_EARG; }
   const int mb = seam_bits(M);
   // 2. compact ids of the last own plane go up; pairs are listed by the upper rank of each seam
-  if (sl.hh) KT_LAUNCH(ctx, "seam_dense", k_seam_dense<<<pblocks, 256, 0, ctx->stream>>>(bits_own, cg, nodes, U, m, dense_send));
+  if (sl.hh) {
+    CU_TRY(cudaMemsetAsync(dense_send, 0, pw * 64, ctx->stream));  // only run-start slots are written (and read)
+    KT_LAUNCH(ctx, "seam_dense", k_seam_dense<<<pblocks, 256, 0, ctx->stream>>>(bits_own, cg, nodes, U, m, dense_send));
+  }
   B2M_TRY(b2m_comm_exchange(ctx, comm, dense_send, sl.hh ? pw * 64 : 0, dense_recv, sl.hl ? pw * 64 : 0, nullptr, 0, nullptr, 0));
   const unsigned cap_pairs = (unsigned)(pw * 96);
   B2M_TRY(b2m_reserve(ctx, BUF_SEAM2, (size_t)cap_pairs * 8 + (size_t)cap_pairs * 4 + 256));

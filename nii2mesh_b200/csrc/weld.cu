@@ -275,6 +275,7 @@ __global__ void k_w_bases(weld_geom g, weld_tables w, const uint32_t *n_dead, co
   const uint32_t e = (g.c_base + g.nv_c) - dead_below(w, g.c_base + g.nv_c, &d);
   out->new_e_off = a; out->nve_new = b - a; out->new_c_base = c; out->nvc_new = e - c;
   out->n_dead = n_dead ? *n_dead : 0; out->n_extra = n_extra ? *n_extra : 0;
+  out->pad[0] = out->pad[1] = 0;
 }
 
 // own vertices -> compacted local array [edge block | centroid block | extras (last rank)]
