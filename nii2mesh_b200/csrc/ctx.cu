@@ -235,10 +235,14 @@ static void pool_finish_locked(copy_pool *p) {
   pthread_mutex_unlock(&p->mu);
   pthread_mutex_unlock(&p->job_mu);
 }
+// a touch job started by THIS thread still owns the pool (job_mu): it must be joined before the thread posts a copy
+static thread_local bool tl_touch_pending = false;
+void b2m_touch_wait(void);
 static void par_memcpy(void *dst, const void *src, size_t n) {
   copy_pool *p = &g_pool;
   const int nt = par_threads();
   if (nt <= 1 || n <= p->slice) { memcpy(dst, src, n); return; }
+  if (tl_touch_pending) b2m_touch_wait();
   pthread_mutex_lock(&p->job_mu);
   p->dst = (char *)dst; p->src = (const char *)src; p->n = n;
   p->nslices = (long long)((n + p->slice - 1) / p->slice);
@@ -251,7 +255,7 @@ static void par_memcpy(void *dst, const void *src, size_t n) {
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
   copy_pool *p = &g_pool;
   const int nt = par_threads();
-  if (nt <= 1 || na + nb < ((size_t)64 << 20)) return 0;
+  if (nt <= 1 || na + nb < ((size_t)64 << 20) || tl_touch_pending) return 0;
   pthread_mutex_lock(&p->job_mu);
   p->src = nullptr;
   p->dst = (char *)a; p->n = na; p->dst2 = (char *)b; p->n2 = nb;
@@ -259,9 +263,14 @@ int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
   p->nslices = p->nslices1 + (long long)((nb + p->slice - 1) / p->slice);
   pool_start_locked(p, nt);
   if (p->started <= 0) { pool_work(p); pool_finish_locked(p); return 0; }
+  tl_touch_pending = true;
   return 1;
 }
-void b2m_touch_wait(void) { pool_finish_locked(&g_pool); }
+void b2m_touch_wait(void) {  // idempotent
+  if (!tl_touch_pending) return;
+  tl_touch_pending = false;
+  pool_finish_locked(&g_pool);
+}
 
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
   if (!bytes) return B2M_OK;

@@ -336,3 +336,15 @@ def test_ingest_and_sform_on_device(eng, orc, libb2m):
     hv, ht, _ = eng.meshify(vol, 0.2, 0, 1, 1, 0, 0)
     gv, gt, _ = eng.meshify_raw(raw, 0.2, 0.001, 0.0, None, 0, 1, 1, 0, 0)
     assert np.array_equal(gt, ht) and np.array_equal(gv.view(np.uint64), hv.view(np.uint64))
+
+
+def test_repeated_host_calls_large_pageable_volume(eng):
+    """two meshify() calls in a row on a pageable host volume whose mesh exceeds the pre-fault threshold (64 MiB): the
+    second call starts pre-faulting its output blocks BEFORE the pageable H2D copy, which needs the same copy pool
+    (regression test for a self-deadlock), and both give the same mesh"""
+    from nii2mesh_b200 import synth
+    vol = synth.gyroid(384)
+    a = eng.meshify(vol, 0.0, 0, 1, 1, 1, 0)
+    b = eng.meshify(vol, 0.0, 0, 1, 1, 1, 0)
+    assert a[2].nverts * 24 + a[2].ntris * 12 > (64 << 20)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
