@@ -31,16 +31,20 @@ def _stale():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: an experiment build (e.g. defines=["-DSX_Y_F2F=0"], out=HERE / "libb2m_alt.so", loaded through
+    the B2M_LIBPATH environment variable) next to the product library"""
+    alt = out is not None
+    out = Path(out) if alt else LIB
+    if not alt and not force and not _stale():
         return LIB
-    objdir = HERE / "build"
+    objdir = HERE / ("build_alt" if alt else "build")
     objdir.mkdir(exist_ok=True)
     objs = []
     procs = []
     for f in CU:
         o = objdir / (f + ".o")
-        cmd = ["nvcc", *NVCC_FLAGS, "-c", str(CSRC / f), "-o", str(o)]
+        cmd = ["nvcc", *NVCC_FLAGS, *defines, "-c", str(CSRC / f), "-o", str(o)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((f, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -52,17 +56,20 @@ def build(force=False, verbose=False):
         objs.append(str(o))
     failed = False
     for f, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {f}\n{out}\n")
+            sys.stderr.write(f"--- {f}\n{log}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("libb2m build failed")
-    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out), *objs,
                            "-lcudart_static", "-lm", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
-    print(LIB)
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    if defs:
+        print(build(force=True, verbose="--verbose" in sys.argv, defines=defs, out=HERE / "libb2m_alt.so"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -228,7 +228,7 @@ __device__ __noinline__ void mc33_select(const signed char *__restrict__ tab, co
 // (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.  Active voxels are appended to a
 // warp-private shared-memory buffer and flushed to the global list with one atomic per ~150 records.
 #define MCB_THREADS 128
-#define MCB_ZC 32
+#define MCB_ZC 8
 #define MCB_BUF 192
 
 // inside bit of one sub-volume voxel given in VOLUME coordinates that may lie one column / row / plane beyond

@@ -16,6 +16,10 @@
 #define SX_THREADS (32 * SX_WARPS)
 #define SX_SMEM (2 * SX_ROWS * SX_TX * 8)
 
+#ifndef SX_Y_F2F
+#define SX_Y_F2F 1                /* y pass rounds with F2F conversions (1) or with the FP64-adder trick (0) */
+#endif
+
 #define K0 0.45
 #define K1 0.225
 #define K2 0.05
@@ -112,14 +116,27 @@ __device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly,
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
       const int k = 2 * h + kk;
+#if SX_Y_F2F
+      // the y pass rounds through the real conversions: the f32 value is needed anyway for border planes, and this
+      // keeps the tile free of a CTA-wide "unsafe input" flag (only the x pass, warp-local, uses the adder rounding)
+      double ys;
+      if (YBORDER) {
+        ys = c[2][kk];
+        ob[k] = (float)ys;
+      } else {
+        ob[k] = (float)fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]);
+        ys = (double)ob[k];
+      }
+#else
       const double ys = YBORDER ? c[2][kk] : round_to_f32<FAST>(fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]));
+      ob[k] = (float)ys;
+#endif
       const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
       const double fin = __dadd_rn(S[k][3], q2);
       S[k][3] = __dadd_rn(S[k][2], q1);
       S[k][2] = __dadd_rn(S[k][1], q0);
       S[k][1] = __dadd_rn(S[k][0], q1);
       S[k][0] = q2;
-      ob[k] = (float)ys;
       oi[k] = (float)fin;
     }
   }
@@ -148,10 +165,7 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
                                                            int ny, int zc, unsigned int *__restrict__ mm_enc) {
   extern __shared__ double2 xs2[];  // [2][SX_ROWS][2][32]
   __shared__ float red[2][SX_WARPS];
-  __shared__ int s_bad[3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < 3) s_bad[tid] = 0;
-  __syncthreads();
   const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
   const int nz = src.gnz;
   const int z0 = src.oz0 + blockIdx.z * zc, z1 = min(z0 + zc, src.oz0 + src.onz);
@@ -170,7 +184,6 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   const int sy = y0 - 2 + warp;
   const bool rowok = sy >= 0 && sy < ny;
   const size_t rowoff = (size_t)(rowok ? sy : 0) * nx;
-  const bool haloL = lane == 0 && x0 > 0, haloR0 = lane == 31 && gx + 4 < nx, haloR1 = lane == 31 && gx + 5 < nx;
   const int oy = y0 + warp;
   const bool yborder = oy < 2 || oy >= ny - 2;
   const bool ook = yz && oy < ny && gx < nx;
@@ -178,23 +191,29 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   float *outp = out + (size_t)oy * nx + gx;  // + (z - oz0) * nxy
 
   // raw row of the plane being staged, prefetched one plane ahead
-  float raw[4], hal[2];  // hal: lane 0 = left halo pair, lane 31 = right halo pair
-  // values that are never used (rows / columns outside the volume, halo slots of inner lanes) are 1.0 so that they
+  // hal: lane 0 = left halo pair (x0-2, x0-1), lane 31 = right halo pair (gx+4, gx+5), fetched by ONE load per register
+  // (two predicated loads into the same register serialise on the first one's return: a full memory latency per plane).
+  // values that are never loaded (rows / columns outside the volume, halo slots of inner lanes) stay 1.0 so that they
   // pass the input screen; the plane pointer runs along z and is recomputed only where the source piece changes
+  float raw[4] = {1.f, 1.f, 1.f, 1.f}, hal[2] = {1.f, 1.f};
+  const int haloff = lane == 0 ? x0 - 2 : gx + 4;
+  const bool hal0 = rowok && ((lane == 0 && x0 > 0) || (lane == 31 && gx + 4 < nx));
+  const bool hal1 = rowok && ((lane == 0 && x0 > 0) || (lane == 31 && gx + 5 < nx));
   const int zb1 = src.rz0 + src.n_lo, zb2 = zb1 + src.n_main;
   const float *rowp = nullptr;
   auto fetch = [&](int zp) {
-    raw[0] = raw[1] = raw[2] = raw[3] = 1.f;
-    hal[0] = hal[1] = 1.f;
-    if (zp < ze) {
-      if (zp == zs || zp == zb1 || zp == zb2) rowp = smooth_plane(src, zp, nxy) + rowoff;
-      else rowp += nxy;
-    }
-    if (rowok && zp < ze) {
-      load_row4<VEC>(rowp, gx, nx, raw);
-      if (haloL) { hal[0] = __ldg(rowp + x0 - 2); hal[1] = __ldg(rowp + x0 - 1); }
-      if (haloR0) hal[0] = __ldg(rowp + gx + 4);
-      if (haloR1) hal[1] = __ldg(rowp + gx + 5);
+    if (zp >= ze) return;  // block-uniform; the registers keep the last plane's (screened) values
+    if (zp == zs || zp == zb1 || zp == zb2) rowp = smooth_plane(src, zp, nxy) + rowoff;
+    else rowp += nxy;
+    if (rowok) load_row4<VEC>(rowp, gx, nx, raw);
+    if (VEC) {  // nx % 4 == 0: both halo voxels exist together and the pair is 8-byte aligned
+      if (hal0) {
+        const float2 h = __ldg(reinterpret_cast<const float2 *>(rowp + haloff));
+        hal[0] = h.x; hal[1] = h.y;
+      }
+    } else {
+      if (hal0) hal[0] = __ldg(rowp + haloff);
+      if (hal1) hal[1] = __ldg(rowp + haloff + 1);
     }
   };
   fetch(zs);
@@ -223,12 +242,13 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
       if (!warp_bad) x_pass_row<true, false>(raw, hal, lane, gx, nx, buf + warp * 64);
       else x_pass_row<false, false>(raw, hal, lane, gx, nx, buf + warp * 64);
     }
-    // tile-wide "unsafe input" flag for this plane through shared memory (three slots: the slot of
-    // plane zp+2 is cleared after this barrier, one full barrier before its writers can run)
-    if (warp_bad && lane == 0) s_bad[zp % 3] = 1;
+    // tile-wide "unsafe input" flag for this plane: the barrier itself carries the OR
+#if SX_Y_F2F
+    const bool cta_bad = false;
     __syncthreads();
-    const bool cta_bad = s_bad[zp % 3] != 0;
-    if (tid == 0) s_bad[(zp + 2) % 3] = 0;
+#else
+    const bool cta_bad = __syncthreads_or(warp_bad) != 0;
+#endif
     fetch(zp + 1);  // next plane's loads fly while this plane's y/z passes run
     // ---- y pass + z pass ----
     if (yz) {

@@ -6,12 +6,13 @@ fillBubbles; it returns (verts[np,3] f64, tris[nt,3] i32) like the reference's m
 arrays.  There is no CPU fallback: constructing an Engine without a CUDA device raises.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
-LIBPATH = HERE / "libb2m.so"
+LIBPATH = Path(os.environ.get("B2M_LIBPATH") or HERE / "libb2m.so")  # B2M_LIBPATH: an experiment build (build.py -D...)
 
 BACKEND_LEWINER, BACKEND_CLASSIC = 0, 1
 STAGES = ("smooth", "range", "cc", "compose", "mc", "weld", "degen", "total")
