@@ -143,6 +143,8 @@ struct b2m_ktimer {
   cudaEvent_t e0, e1;
 };
 
+#define B2M_RING_CHUNK ((size_t)8 << 20)   /* streamed D2H: DMA granule */
+#define B2M_RING_SLOTS 12                  /* = 3 * B2M_STAGE_BYTES / B2M_RING_CHUNK */
 struct b2m_ctx {
   int device;
   b2m_scalars *h_all;      // pinned: scalar blocks of all ranks (slabs), h_all_cap entries
@@ -166,6 +168,7 @@ struct b2m_ctx {
   // host<->device staging for pageable host memory (b2m_copy_h2d / b2m_copy_d2h)
   void *stage[3];          // pinned ring buffers (B2M_STAGE_BYTES each), allocated on first use
   cudaEvent_t stage_ev[3];
+  cudaEvent_t ring_ev[B2M_RING_SLOTS];  // streamed D2H: the three buffers seen as B2M_RING_SLOTS sub-chunks
   int profile;             // record an event pair around every kernel launch
   int nkt, nkt_events;     // entries used in this call / event pairs created so far
   b2m_ktimer kt[B2M_KT_MAX];

@@ -65,6 +65,8 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
   for (int i = 0; i < c->nkt_events; i++) { cudaEventDestroy(c->kt[i].e0); cudaEventDestroy(c->kt[i].e1); }
   for (int i = 0; i < 3; i++)
     if (c->stage[i]) { cudaFreeHost(c->stage[i]); cudaEventDestroy(c->stage_ev[i]); }
+  for (int i = 0; i < B2M_RING_SLOTS; i++)
+    if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
   cudaFreeHost(c->h_scalars);
   if (c->h_all) { cudaFreeHost(c->h_all); cudaFree(c->d_all); }
   cudaStreamDestroy(c->stream);
@@ -149,6 +151,8 @@ static int stage_init(b2m_ctx *ctx) {
       CU_TRY(cudaMallocHost(&ctx->stage[i], B2M_STAGE_BYTES));
       CU_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     }
+  for (int i = 0; i < B2M_RING_SLOTS; i++)
+    if (!ctx->ring_ev[i]) CU_TRY(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
   return B2M_OK;
 }
 // multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded copy).
@@ -156,7 +160,9 @@ static int stage_init(b2m_ctx *ctx) {
 // must not depend on the host program's OpenMP settings.  Slices of 4 MiB are handed out through an atomic counter;
 // the calling thread works too.  One job at a time (callers from several host threads serialise on the pool).
 #include <pthread.h>
+#include <sched.h>
 #include <atomic>
+static inline void cpu_relax(void) { asm volatile("pause" ::: "memory"); }
 static int par_threads(void) {
   static int n = 0;
   if (!n) {
@@ -182,12 +188,28 @@ struct copy_pool {
   long long nslices = 0;
   std::atomic<long long> next{0};
   int generation = 0, running = 0, started = 0;
+  // streamed D2H job (ring != null): slice i belongs to DMA chunk i / spc and may be copied once ready > chunk;
+  // done[slot] counts the copied slices of the chunk that occupies a ring slot
+  char *const *ring = nullptr;
+  long long spc = 0;
+  std::atomic<long long> ready{0};
+  std::atomic<int> done[B2M_RING_SLOTS];
 } g_pool;
+extern "C" void b2m_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.c
 static void pool_work(copy_pool *p) {
   for (;;) {
     const long long i = p->next.fetch_add(1);
     if (i >= p->nslices) break;
-    if (p->src) {
+    if (p->ring) {
+      const long long c = i / p->spc;
+      for (int spins = 0; p->ready.load(std::memory_order_acquire) <= c; spins++) {
+        if (spins < 2000) cpu_relax();
+        else sched_yield();
+      }
+      const size_t o = (size_t)i * p->slice, oc = (size_t)(i - c * p->spc) * p->slice;
+      b2m_stream_copy(p->dst + o, p->ring[c % B2M_RING_SLOTS] + oc, p->n - o < p->slice ? p->n - o : p->slice);
+      p->done[c % B2M_RING_SLOTS].fetch_add(1, std::memory_order_release);
+    } else if (p->src) {
       const size_t o = (size_t)i * p->slice;
       memcpy(p->dst + o, p->src + o, p->n - o < p->slice ? p->n - o : p->slice);
     } else {
@@ -244,7 +266,7 @@ static void par_memcpy(void *dst, const void *src, size_t n) {
   if (nt <= 1 || n <= p->slice) { memcpy(dst, src, n); return; }
   if (tl_touch_pending) b2m_touch_wait();
   pthread_mutex_lock(&p->job_mu);
-  p->dst = (char *)dst; p->src = (const char *)src; p->n = n;
+  p->dst = (char *)dst; p->src = (const char *)src; p->n = n; p->ring = nullptr;
   p->nslices = (long long)((n + p->slice - 1) / p->slice);
   pool_start_locked(p, nt);
   pool_work(p);
@@ -257,7 +279,7 @@ int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
   const int nt = par_threads();
   if (nt <= 1 || na + nb < ((size_t)64 << 20) || tl_touch_pending) return 0;
   pthread_mutex_lock(&p->job_mu);
-  p->src = nullptr;
+  p->src = nullptr; p->ring = nullptr;
   p->dst = (char *)a; p->n = na; p->dst2 = (char *)b; p->n2 = nb;
   p->nslices1 = (long long)((na + p->slice - 1) / p->slice);
   p->nslices = p->nslices1 + (long long)((nb + p->slice - 1) / p->slice);
@@ -272,6 +294,10 @@ void b2m_touch_wait(void) {  // idempotent
   pool_finish_locked(&g_pool);
 }
 
+// Pageable destination: the DMA engine fills a ring of pinned 8 MiB chunks while the pool threads stream finished
+// chunks into the caller's block (1 MiB slices, non-temporal stores).  ONE pool job for the whole transfer: the
+// workers spin on the "chunks ready" counter instead of being woken and joined per chunk, and the calling thread
+// only waits for DMA events and re-issues ring slots whose slices have all been copied.
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
   if (!bytes) return B2M_OK;
   if (bytes < ((size_t)1 << 20) || host_is_pinned(h_dst)) {
@@ -280,20 +306,65 @@ int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     return B2M_OK;
   }
   B2M_TRY(stage_init(ctx));
-  const size_t nchunk = (bytes + B2M_STAGE_BYTES - 1) / B2M_STAGE_BYTES;
-  auto issue = [&](size_t c) -> cudaError_t {
-    const size_t o = c * B2M_STAGE_BYTES, n = bytes - o < B2M_STAGE_BYTES ? bytes - o : B2M_STAGE_BYTES;
-    cudaError_t e = cudaMemcpyAsync(ctx->stage[c % 3], (const char *)d_src + o, n, cudaMemcpyDeviceToHost, ctx->stream);
+  copy_pool *p = &g_pool;
+  char *ring[B2M_RING_SLOTS];
+  const int per_buf = (int)(B2M_STAGE_BYTES / B2M_RING_CHUNK);
+  for (int k = 0; k < B2M_RING_SLOTS; k++) ring[k] = (char *)ctx->stage[k / per_buf] + (size_t)(k % per_buf) * B2M_RING_CHUNK;
+  const long long nchunk = (long long)((bytes + B2M_RING_CHUNK - 1) / B2M_RING_CHUNK);
+  auto chunk_bytes = [&](long long c) { const size_t o = (size_t)c * B2M_RING_CHUNK; return bytes - o < B2M_RING_CHUNK ? bytes - o : B2M_RING_CHUNK; };
+  auto issue = [&](long long c) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(ring[c % B2M_RING_SLOTS], (const char *)d_src + (size_t)c * B2M_RING_CHUNK, chunk_bytes(c),
+                                    cudaMemcpyDeviceToHost, ctx->stream);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(ctx->stage_ev[c % 3], ctx->stream);
+    return cudaEventRecord(ctx->ring_ev[c % B2M_RING_SLOTS], ctx->stream);
   };
-  for (size_t c = 0; c < nchunk && c < 3; c++) CU_TRY(issue(c));
-  for (size_t c = 0; c < nchunk; c++) {
-    const size_t o = c * B2M_STAGE_BYTES, n = bytes - o < B2M_STAGE_BYTES ? bytes - o : B2M_STAGE_BYTES;
-    CU_TRY(cudaEventSynchronize(ctx->stage_ev[c % 3]));
-    par_memcpy((char *)h_dst + o, ctx->stage[c % 3], n);
-    if (c + 3 < nchunk) CU_TRY(issue(c + 3));
+  const int nt = par_threads();
+  if (tl_touch_pending) b2m_touch_wait();
+  pthread_mutex_lock(&p->job_mu);
+  p->dst = (char *)h_dst; p->src = nullptr; p->n = bytes;
+  p->nslices = (long long)((bytes + p->slice - 1) / p->slice);
+  p->ring = ring; p->spc = (long long)(B2M_RING_CHUNK / p->slice);
+  p->ready.store(0);
+  for (int k = 0; k < B2M_RING_SLOTS; k++) p->done[k].store(0);
+  long long issued = 0;
+  cudaError_t err = cudaSuccess;
+  for (; issued < nchunk && issued < B2M_RING_SLOTS && err == cudaSuccess; issued++) err = issue(issued);
+  auto slot_free = [&](long long c) {  // every slice of chunk c has left its ring slot
+    const long long need = (long long)((chunk_bytes(c) + p->slice - 1) / p->slice);
+    return p->done[c % B2M_RING_SLOTS].load(std::memory_order_acquire) >= need;
+  };
+  auto refill = [&](bool must) {
+    while (err == cudaSuccess && issued < nchunk) {
+      const long long prev = issued - B2M_RING_SLOTS;
+      if (!slot_free(prev)) {
+        if (!must) break;
+        cpu_relax();
+        continue;
+      }
+      p->done[prev % B2M_RING_SLOTS].store(0);
+      err = issue(issued++);
+      must = false;
+    }
+  };
+  pool_start_locked(p, nt);
+  const bool alone = p->started <= 0;  // no worker threads: the caller copies chunk by chunk itself
+  for (long long c = 0; c < nchunk && err == cudaSuccess; c++) {
+    if (issued <= c) refill(true);
+    if (err != cudaSuccess) break;
+    err = cudaEventSynchronize(ctx->ring_ev[c % B2M_RING_SLOTS]);
+    if (err != cudaSuccess) break;
+    p->ready.store(c + 1, std::memory_order_release);
+    if (alone) {
+      const size_t o = (size_t)c * B2M_RING_CHUNK;
+      b2m_stream_copy((char *)h_dst + o, ring[c % B2M_RING_SLOTS], chunk_bytes(c));
+      p->done[c % B2M_RING_SLOTS].store((int)p->spc);
+    }
+    refill(false);
   }
+  if (err != cudaSuccess) p->ready.store(nchunk + 1, std::memory_order_release);  // release the workers; the copy is void anyway
+  if (alone) p->next.store(p->nslices);
+  pool_finish_locked(p);  // the next job of any kind resets p->ring under job_mu
+  CU_TRY(err);
   return B2M_OK;
 }
 
