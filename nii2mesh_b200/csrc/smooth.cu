@@ -9,10 +9,15 @@
 #include "common.cuh"
 
 // ---- tile geometry ----
+// CTA = 12 warps on a 128 x 24 xy tile (28 staged rows).  Every warp owns TWO adjacent output rows (8 voxels per lane):
+// the per-plane fixed work of a warp (addressing, input screen, barrier, loop) is paid once per 8 voxels, and the
+// y pass reads 6 staged rows for 2 output rows instead of 5 for 1.  The 28 staged rows are split 2 per warp plus one
+// more for warps 0..3, which sit on the four different schedulers: the x-pass work is balanced across them.
 #define SX_TX 128                 /* tile width: 32 lanes x 4 voxels */
-#define SX_TY 20                  /* output rows per tile */
+#define SX_TY 24                  /* output rows per tile */
 #define SX_ROWS (SX_TY + 4)       /* rows staged per plane (2 + 2 halo) */
-#define SX_WARPS SX_ROWS          /* one staged row per warp; warps 0..SX_TY-1 also own one output row */
+#define SX_WARPS (SX_TY / 2)
+#define SX_XTRA (SX_ROWS - 2 * SX_WARPS)  /* staged rows beyond two per warp */
 #define SX_THREADS (32 * SX_WARPS)
 #define SX_SMEM (2 * SX_ROWS * SX_TX * 8)
 
@@ -101,51 +106,55 @@ __device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2
   dst[32 + lane] = make_double2(o[2], o[3]);
 }
 
-// y pass (1 row x 4 voxels per lane out of 5 staged rows) + z streaming accumulators
-template <bool FAST, bool YBORDER>
-__device__ __forceinline__ void yz_pass(const double2 *__restrict__ buf, int ly, int lane,
-                                        double S[4][4], float ob[4], float oi[4]) {
+// y pass (2 adjacent rows x 4 voxels per lane out of 6 staged rows) + z streaming accumulators
+// YEDGE: the tile holds rows y < 2 or y >= ny-2 (block-uniform); yb0 / yb1 say which of the two rows pass through
+template <bool FAST, bool YEDGE>
+__device__ __forceinline__ void yz_pass2(const double2 *__restrict__ buf, int r0, int lane, bool yb0, bool yb1,
+                                         double S[2][4][4], float ob[2][4], float oi[2][4]) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
-    double c[5][2];
+    double c[6][2];
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-      const double2 pj = buf[(ly + j) * 64 + h * 32 + lane];
+    for (int j = 0; j < 6; j++) {
+      const double2 pj = buf[(r0 + j) * 64 + h * 32 + lane];
       c[j][0] = pj.x; c[j][1] = pj.y;
     }
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
       const int k = 2 * h + kk;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const double f = fir5(c[r][kk], c[r + 1][kk], c[r + 2][kk], c[r + 3][kk], c[r + 4][kk]);
+        const bool yb = YEDGE && (r ? yb1 : yb0);
 #if SX_Y_F2F
-      // the y pass rounds through the real conversions: the f32 value is needed anyway for border planes, and this
-      // keeps the tile free of a CTA-wide "unsafe input" flag (only the x pass, warp-local, uses the adder rounding)
-      double ys;
-      if (YBORDER) {
-        ys = c[2][kk];
-        ob[k] = (float)ys;
-      } else {
-        ob[k] = (float)fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]);
-        ys = (double)ob[k];
-      }
+        // the y pass rounds through the real conversions: the f32 value is needed anyway for border planes, and this
+        // keeps the tile free of a CTA-wide "unsafe input" flag (only the x pass, warp-local, uses the adder rounding)
+        float yf = (float)f;
+        if (yb) yf = (float)c[r + 2][kk];
+        const double ys = (double)yf;
+        ob[r][k] = yf;
 #else
-      const double ys = YBORDER ? c[2][kk] : round_to_f32<FAST>(fir5(c[0][kk], c[1][kk], c[2][kk], c[3][kk], c[4][kk]));
-      ob[k] = (float)ys;
+        double ys = round_to_f32<FAST>(f);
+        if (yb) ys = c[r + 2][kk];
+        ob[r][k] = (float)ys;
 #endif
-      const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
-      const double fin = __dadd_rn(S[k][3], q2);
-      S[k][3] = __dadd_rn(S[k][2], q1);
-      S[k][2] = __dadd_rn(S[k][1], q0);
-      S[k][1] = __dadd_rn(S[k][0], q1);
-      S[k][0] = q2;
-      oi[k] = (float)fin;
+        const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
+        const double fin = __dadd_rn(S[r][k][3], q2);
+        S[r][k][3] = __dadd_rn(S[r][k][2], q1);
+        S[r][k][2] = __dadd_rn(S[r][k][1], q0);
+        S[r][k][1] = __dadd_rn(S[r][k][0], q1);
+        S[r][k][0] = q2;
+        oi[r][k] = (float)fin;
+      }
     }
   }
 }
 
-// One CTA (32 warps): a 128 x 28 xy tile, marching along z over [z0, z1) (+2 halo planes each side).
-//   x pass: warp w filters staged row w (gy = y0-2+w) in registers (float4 per lane, neighbours by
-//           shuffle), rounds to the f32 grid and parks the row in shared memory as doubles;
-//   y pass: warps 0..27 own output row y0+w: 4 voxels per lane from 5 staged rows in shared memory;
+// One CTA (12 warps): a 128 x 24 xy tile, marching along z over [z0, z1) (+2 halo planes each side).
+//   x pass: warp w filters staged rows 2w, 2w+1 (and 24+w for w < 4; staged row r is gy = y0-2+r) in registers
+//           (float4 per lane, neighbours by shuffle), rounds to the f32 grid and parks the rows in shared memory as
+//           doubles;
+//   y pass: warp w owns output rows y0+2w, y0+2w+1: 2 x 4 voxels per lane from 6 staged rows in shared memory;
 //   z pass: streaming accumulators - the reference's left-to-right sum
 //           ((((a*k2)+b*k1)+c*k0)+d*k1)+e*k2 is advanced by one term per arriving plane, so a
 //           column keeps 4 partial sums instead of a 5-plane ring.
@@ -160,6 +169,14 @@ __device__ __forceinline__ const float *smooth_plane(const smooth_src &s, int zg
   return s.hi + (size_t)(q - s.n_main) * nxy;
 }
 
+template <bool FAST, bool XEDGE>
+__device__ __forceinline__ void x_pass_rows(const float raw[3][4], const float hal[3][2], bool has3, int warp, int lane,
+                                            int gx, int nx, double2 *__restrict__ buf) {
+  x_pass_row<FAST, XEDGE>(raw[0], hal[0], lane, gx, nx, buf + (2 * warp) * 64);
+  x_pass_row<FAST, XEDGE>(raw[1], hal[1], lane, gx, nx, buf + (2 * warp + 1) * 64);
+  if (has3) x_pass_row<FAST, XEDGE>(raw[2], hal[2], lane, gx, nx, buf + (2 * SX_WARPS + warp) * 64);
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant__ smooth_src src, float *__restrict__ out, int nx,
                                                            int ny, int zc, unsigned int *__restrict__ mm_enc) {
@@ -172,48 +189,68 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
   const int gx = x0 + lane * 4;
   const size_t nxy = (size_t)nx * ny;
-  const bool yz = warp < SX_TY;
-  double S[4][4];
+  double S[2][4][4];
 #pragma unroll
-  for (int k = 0; k < 4; k++)
+  for (int r = 0; r < 2; r++)
 #pragma unroll
-    for (int q = 0; q < 4; q++) S[k][q] = 0.0;
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) S[r][k][q] = 0.0;
   float vmin = INFINITY, vmax = -INFINITY;
 
-  // loop-invariant addressing: the row this warp stages (gy = y0 - 2 + warp) and the output row it owns (y0 + warp)
-  const int sy = y0 - 2 + warp;
-  const bool rowok = sy >= 0 && sy < ny;
-  const size_t rowoff = (size_t)(rowok ? sy : 0) * nx;
-  const int oy = y0 + warp;
-  const bool yborder = oy < 2 || oy >= ny - 2;
-  const bool ook = yz && oy < ny && gx < nx;
+  // loop-invariant addressing.  Staged rows of this warp: slot q < 2 -> staged row 2*warp + q, slot 2 -> staged row
+  // 2*SX_WARPS + warp (warps 0..SX_XTRA-1 only); row offsets inside a plane fit 31 bits (dims <= 32767)
+  const bool has3 = warp < SX_XTRA;
+  bool rowok[3];
+  int roff[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const int sy = y0 - 2 + (q < 2 ? 2 * warp + q : 2 * SX_WARPS + warp);
+    rowok[q] = sy >= 0 && sy < ny && (q < 2 || has3);
+    roff[q] = rowok[q] ? sy * nx : 0;
+  }
+  const int oy0 = y0 + 2 * warp;  // output rows oy0, oy0 + 1
+  const bool yb0 = oy0 < 2 || oy0 >= ny - 2, yb1 = oy0 + 1 < 2 || oy0 + 1 >= ny - 2;
+  const bool ok0 = oy0 < ny && gx < nx, ok1 = oy0 + 1 < ny && gx < nx;
   const bool xedge = x0 == 0 || x0 + SX_TX > nx - 2;  // block-uniform
-  float *outp = out + (size_t)oy * nx + gx;  // + (z - oz0) * nxy
+  const bool yedge = y0 == 0 || y0 + SX_TY > ny - 2;  // block-uniform
+  float *outp = out + (size_t)oy0 * nx + gx;  // + (z - oz0) * nxy (+ nx for the second row)
 
-  // raw row of the plane being staged, prefetched one plane ahead
+  // raw rows of the plane being staged, prefetched one plane ahead
   // hal: lane 0 = left halo pair (x0-2, x0-1), lane 31 = right halo pair (gx+4, gx+5), fetched by ONE load per register
   // (two predicated loads into the same register serialise on the first one's return: a full memory latency per plane).
   // values that are never loaded (rows / columns outside the volume, halo slots of inner lanes) stay 1.0 so that they
   // pass the input screen; the plane pointer runs along z and is recomputed only where the source piece changes
-  float raw[4] = {1.f, 1.f, 1.f, 1.f}, hal[2] = {1.f, 1.f};
+  float raw[3][4], hal[3][2];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    raw[q][0] = raw[q][1] = raw[q][2] = raw[q][3] = 1.f;
+    hal[q][0] = hal[q][1] = 1.f;
+  }
   const int haloff = lane == 0 ? x0 - 2 : gx + 4;
-  const bool hal0 = rowok && ((lane == 0 && x0 > 0) || (lane == 31 && gx + 4 < nx));
-  const bool hal1 = rowok && ((lane == 0 && x0 > 0) || (lane == 31 && gx + 5 < nx));
+  const bool hal0 = (lane == 0 && x0 > 0) || (lane == 31 && gx + 4 < nx);
+  const bool hal1 = (lane == 0 && x0 > 0) || (lane == 31 && gx + 5 < nx);
   const int zb1 = src.rz0 + src.n_lo, zb2 = zb1 + src.n_main;
-  const float *rowp = nullptr;
+  const float *planep = nullptr;
   auto fetch = [&](int zp) {
     if (zp >= ze) return;  // block-uniform; the registers keep the last plane's (screened) values
-    if (zp == zs || zp == zb1 || zp == zb2) rowp = smooth_plane(src, zp, nxy) + rowoff;
-    else rowp += nxy;
-    if (rowok) load_row4<VEC>(rowp, gx, nx, raw);
-    if (VEC) {  // nx % 4 == 0: both halo voxels exist together and the pair is 8-byte aligned
-      if (hal0) {
-        const float2 h = __ldg(reinterpret_cast<const float2 *>(rowp + haloff));
-        hal[0] = h.x; hal[1] = h.y;
+    if (zp == zs || zp == zb1 || zp == zb2) planep = smooth_plane(src, zp, nxy);
+    else planep += nxy;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const float *rowp = planep + roff[q];
+      if (rowok[q]) {
+        load_row4<VEC>(rowp, gx, nx, raw[q]);
+        if (VEC) {  // nx % 4 == 0: both halo voxels exist together and the pair is 8-byte aligned
+          if (hal0) {
+            const float2 h = __ldg(reinterpret_cast<const float2 *>(rowp + haloff));
+            hal[q][0] = h.x; hal[q][1] = h.y;
+          }
+        } else {
+          if (hal0) hal[q][0] = __ldg(rowp + haloff);
+          if (hal1) hal[q][1] = __ldg(rowp + haloff + 1);
+        }
       }
-    } else {
-      if (hal0) hal[0] = __ldg(rowp + haloff);
-      if (hal1) hal[1] = __ldg(rowp + haloff + 1);
     }
   };
   fetch(zs);
@@ -222,67 +259,79 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
     double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
     // ---- x pass ---- (inputs are screened only now, not at fetch time: touching the prefetched
     // registers earlier would stall on loads that are meant to fly across the y/z passes)
-    // cheap screen first: one unsigned max over the six biased magnitudes says "all inside [2^-100, 2^100)";
+    // cheap screen first: one unsigned max over the biased magnitudes says "all inside [2^-100, 2^100)";
     // only warps that hold something else (zeros included) run the exact per-value test
     bool warp_bad = false;
     {
-      unsigned m = input_bias(raw[0]);
-      m = max(m, input_bias(raw[1])); m = max(m, input_bias(raw[2])); m = max(m, input_bias(raw[3]));
-      m = max(m, input_bias(hal[0])); m = max(m, input_bias(hal[1]));
+      unsigned m = 0u;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) m = max(m, input_bias(raw[q][k]));
+        m = max(m, input_bias(hal[q][0])); m = max(m, input_bias(hal[q][1]));
+      }
       if (__any_sync(0xffffffffu, m >= 0x64000000u)) {
-        const bool raw_bad = input_unsafe(raw[0]) | input_unsafe(raw[1]) | input_unsafe(raw[2]) | input_unsafe(raw[3]) |
-                             input_unsafe(hal[0]) | input_unsafe(hal[1]);
+        bool raw_bad = false;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) raw_bad |= input_unsafe(raw[q][k]);
+          raw_bad |= input_unsafe(hal[q][0]) | input_unsafe(hal[q][1]);
+        }
         warp_bad = __any_sync(0xffffffffu, raw_bad);
       }
     }
     if (xedge) {
-      if (!warp_bad) x_pass_row<true, true>(raw, hal, lane, gx, nx, buf + warp * 64);
-      else x_pass_row<false, true>(raw, hal, lane, gx, nx, buf + warp * 64);
+      if (!warp_bad) x_pass_rows<true, true>(raw, hal, has3, warp, lane, gx, nx, buf);
+      else x_pass_rows<false, true>(raw, hal, has3, warp, lane, gx, nx, buf);
     } else {
-      if (!warp_bad) x_pass_row<true, false>(raw, hal, lane, gx, nx, buf + warp * 64);
-      else x_pass_row<false, false>(raw, hal, lane, gx, nx, buf + warp * 64);
+      if (!warp_bad) x_pass_rows<true, false>(raw, hal, has3, warp, lane, gx, nx, buf);
+      else x_pass_rows<false, false>(raw, hal, has3, warp, lane, gx, nx, buf);
     }
-    // tile-wide "unsafe input" flag for this plane: the barrier itself carries the OR
 #if SX_Y_F2F
     const bool cta_bad = false;
     __syncthreads();
 #else
+    // tile-wide "unsafe input" flag for this plane: the barrier itself carries the OR
     const bool cta_bad = __syncthreads_or(warp_bad) != 0;
 #endif
     fetch(zp + 1);  // next plane's loads fly while this plane's y/z passes run
     // ---- y pass + z pass ----
-    if (yz) {
-      float ob[4], oi[4];
-      if (!yborder) {
-        if (!cta_bad) yz_pass<true, false>(buf, warp, lane, S, ob, oi);
-        else yz_pass<false, false>(buf, warp, lane, S, ob, oi);
+    {
+      float ob[2][4], oi[2][4];
+      if (!yedge) {
+        if (!cta_bad) yz_pass2<true, false>(buf, 2 * warp, lane, false, false, S, ob, oi);
+        else yz_pass2<false, false>(buf, 2 * warp, lane, false, false, S, ob, oi);
       } else {
-        yz_pass<false, true>(buf, warp, lane, S, ob, oi);
+        yz_pass2<false, true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
       }
       const bool zborder = zp < 2 || zp >= nz - 2;
       const int zo = zp - 2;
       const bool emit_border = zborder && zp >= z0 && zp < z1;
       const bool emit_inner = zo >= z0 && zo < z1 && zo >= 2 && zo < nz - 2;
-      if (ook) {
-        if (emit_border) {
-          float *dst = outp + zoff;
-          if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(ob[0], ob[1], ob[2], ob[3]);
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (VEC || gx + k < nx) {
-              if (!VEC) dst[k] = ob[k];
-              vmin = fminf(vmin, ob[k]); vmax = fmaxf(vmax, ob[k]);
-            }
-        }
-        if (emit_inner) {
-          float *dst = outp + (zoff - 2 * (long long)nxy);
-          if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[0], oi[1], oi[2], oi[3]);
+      for (int r = 0; r < 2; r++) {
+        if (r ? ok1 : ok0) {
+          if (emit_border) {
+            float *dst = outp + zoff + (r ? nx : 0);
+            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(ob[r][0], ob[r][1], ob[r][2], ob[r][3]);
 #pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (VEC || gx + k < nx) {
-              if (!VEC) dst[k] = oi[k];
-              vmin = fminf(vmin, oi[k]); vmax = fmaxf(vmax, oi[k]);
-            }
+            for (int k = 0; k < 4; k++)
+              if (VEC || gx + k < nx) {
+                if (!VEC) dst[k] = ob[r][k];
+                vmin = fminf(vmin, ob[r][k]); vmax = fmaxf(vmax, ob[r][k]);
+              }
+          }
+          if (emit_inner) {
+            float *dst = outp + (zoff - 2 * (long long)nxy) + (r ? nx : 0);
+            if (VEC) *reinterpret_cast<float4 *>(dst) = make_float4(oi[r][0], oi[r][1], oi[r][2], oi[r][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+              if (VEC || gx + k < nx) {
+                if (!VEC) dst[k] = oi[r][k];
+                vmin = fminf(vmin, oi[r][k]); vmax = fmaxf(vmax, oi[r][k]);
+              }
+          }
         }
       }
     }
@@ -448,13 +497,20 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
 int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
   const unsigned tx = b2m_cdiv(g.nx, SX_TX), ty = b2m_cdiv(g.ny, SX_TY);
   const int onz = src.onz;
-  // z chunk: enough CTAs to fill the machine a few times over, but >= 16 planes so that the 4 halo
-  // planes of a chunk stay a small overhead
-  int want = (int)((4 * (size_t)ctx->sm_count + (size_t)tx * ty - 1) / ((size_t)tx * ty));
-  if (want < 1) want = 1;
-  int zc = (onz + want - 1) / want;
-  if (zc < 16) zc = 16;
-  if (zc > 128) zc = 128;
+  // z chunks: one CTA per SM at a time, so the step takes ceil(CTAs / SMs) rounds of (zc + 4) planes each; take the
+  // split with the cheapest estimate (chunks >= 16 planes keep the 4 halo planes a small overhead)
+  int zc = onz;
+  {
+    const size_t tiles = (size_t)tx * ty;
+    size_t best = 0;
+    for (int k = 1; k <= 64; k++) {
+      const int c = (onz + k - 1) / k;
+      if (c < 16 && k > 1) break;
+      const size_t ctas = tiles * (size_t)((onz + c - 1) / c);
+      const size_t cost = ((ctas + ctx->sm_count - 1) / ctx->sm_count) * (size_t)(c + 4);
+      if (!best || cost < best) { best = cost; zc = c; }
+    }
+  }
   dim3 grid(tx, ty, b2m_cdiv(onz, zc));
   const bool vec = (g.nx % 4 == 0) && (((uintptr_t)src.main | (uintptr_t)src.lo | (uintptr_t)src.hi | (uintptr_t)d_out) % 16 == 0);
   static bool attr_done = false;
