@@ -14,16 +14,37 @@
 // y pass reads 6 staged rows for 2 output rows instead of 5 for 1.  The 28 staged rows are split 2 per warp plus one
 // more for warps 0..3, which sit on the four different schedulers: the x-pass work is balanced across them.
 #define SX_TX 128                 /* tile width: 32 lanes x 4 voxels */
+#ifndef SX_TY
 #define SX_TY 24                  /* output rows per tile */
+#endif
 #define SX_ROWS (SX_TY + 4)       /* rows staged per plane (2 + 2 halo) */
+#ifndef SX_STAGE_WARPS
+#define SX_STAGE_WARPS 1          /* 1: two more warps stage the last four rows (and own no output rows) instead of a third row in warps 0..3 */
+#endif
+#if SX_STAGE_WARPS
+#define SX_WARPS (SX_ROWS / 2)
+#else
 #define SX_WARPS (SX_TY / 2)
+#endif
 #define SX_XTRA (SX_ROWS - 2 * SX_WARPS)  /* staged rows beyond two per warp */
 #define SX_THREADS (32 * SX_WARPS)
-#define SX_SMEM (2 * SX_ROWS * SX_TX * 8)
+#define SX_RING 4                 /* planes of x-pass results in shared memory */
+#define SX_SMEM (SX_RING * SX_ROWS * SX_TX * 8)
 
-#ifndef SX_Y_F2F
-#define SX_Y_F2F 1                /* y pass rounds with F2F conversions (1) or with the FP64-adder trick (0) */
-#endif
+// mbarrier (shared-memory arrive/wait barrier with phases): split arrive / wait lets warps run one plane apart
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nMB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MB_DONE;\nbra MB_WAIT;\nMB_DONE:\n}" ::"r"(
+          (unsigned)__cvta_generic_to_shared(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 #define K0 0.45
 #define K1 0.225
@@ -108,7 +129,7 @@ __device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2
 
 // y pass (2 adjacent rows x 4 voxels per lane out of 6 staged rows) + z streaming accumulators
 // YEDGE: the tile holds rows y < 2 or y >= ny-2 (block-uniform); yb0 / yb1 say which of the two rows pass through
-template <bool FAST, bool YEDGE>
+template <bool YEDGE>
 __device__ __forceinline__ void yz_pass2(const double2 *__restrict__ buf, int r0, int lane, bool yb0, bool yb1,
                                          double S[2][4][4], float ob[2][4], float oi[2][4]) {
 #pragma unroll
@@ -126,18 +147,13 @@ __device__ __forceinline__ void yz_pass2(const double2 *__restrict__ buf, int r0
       for (int r = 0; r < 2; r++) {
         const double f = fir5(c[r][kk], c[r + 1][kk], c[r + 2][kk], c[r + 3][kk], c[r + 4][kk]);
         const bool yb = YEDGE && (r ? yb1 : yb0);
-#if SX_Y_F2F
         // the y pass rounds through the real conversions: the f32 value is needed anyway for border planes, and this
-        // keeps the tile free of a CTA-wide "unsafe input" flag (only the x pass, warp-local, uses the adder rounding)
+        // keeps the tile free of a CTA-wide "unsafe input" flag (only the x pass, warp-local, uses the adder rounding;
+        // measured: the adder rounding here was 4 % slower)
         float yf = (float)f;
         if (yb) yf = (float)c[r + 2][kk];
         const double ys = (double)yf;
         ob[r][k] = yf;
-#else
-        double ys = round_to_f32<FAST>(f);
-        if (yb) ys = c[r + 2][kk];
-        ob[r][k] = (float)ys;
-#endif
         const double q0 = __dmul_rn(ys, K0), q1 = __dmul_rn(ys, K1), q2 = __dmul_rn(ys, K2);
         const double fin = __dadd_rn(S[r][k][3], q2);
         S[r][k][3] = __dadd_rn(S[r][k][2], q1);
@@ -180,8 +196,9 @@ __device__ __forceinline__ void x_pass_rows(const float raw[3][4], const float h
 template <bool VEC>
 __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant__ smooth_src src, float *__restrict__ out, int nx,
                                                            int ny, int zc, unsigned int *__restrict__ mm_enc) {
-  extern __shared__ double2 xs2[];  // [2][SX_ROWS][2][32]
+  extern __shared__ double2 xs2[];  // [SX_RING][SX_ROWS][2][32]
   __shared__ float red[2][SX_WARPS];
+  __shared__ __align__(8) unsigned long long mbar[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
   const int nz = src.gnz;
@@ -253,14 +270,12 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
       }
     }
   };
-  fetch(zs);
-  long long zoff = (long long)(zs - src.oz0) * (long long)nxy;  // may start negative: only used for planes inside [oz0, oz0+onz)
-  for (int zp = zs; zp < ze; zp++, zoff += (long long)nxy) {
-    double2 *buf = xs2 + (size_t)(zp & 1) * (SX_ROWS * 64);
-    // ---- x pass ---- (inputs are screened only now, not at fetch time: touching the prefetched
-    // registers earlier would stall on loads that are meant to fly across the y/z passes)
-    // cheap screen first: one unsigned max over the biased magnitudes says "all inside [2^-100, 2^100)";
-    // only warps that hold something else (zeros included) run the exact per-value test
+  // x pass of the prefetched plane into its ring slot (inputs are screened only now, not at fetch time: touching the
+  // prefetched registers earlier would stall on loads that are meant to fly across the y/z passes).
+  // cheap screen first: one unsigned max over the biased magnitudes says "all inside [2^-100, 2^100)";
+  // only warps that hold something else (zeros included) run the exact per-value test
+  auto stage = [&](int zp) {
+    double2 *buf = xs2 + (size_t)((zp - zs) % SX_RING) * (SX_ROWS * 64);
     bool warp_bad = false;
     {
       unsigned m = 0u;
@@ -288,22 +303,35 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
       if (!warp_bad) x_pass_rows<true, false>(raw, hal, has3, warp, lane, gx, nx, buf);
       else x_pass_rows<false, false>(raw, hal, has3, warp, lane, gx, nx, buf);
     }
-#if SX_Y_F2F
-    const bool cta_bad = false;
-    __syncthreads();
-#else
-    // tile-wide "unsafe input" flag for this plane: the barrier itself carries the OR
-    const bool cta_bad = __syncthreads_or(warp_bad) != 0;
-#endif
-    fetch(zp + 1);  // next plane's loads fly while this plane's y/z passes run
+  };
+  // Plane pipeline without a CTA-wide barrier per plane: a warp stages plane zp+1, ARRIVES on that plane's mbarrier and
+  // only then waits for plane zp (staged one trip earlier by everybody) before its y/z passes - warps drift up to one
+  // plane apart instead of meeting at every plane.  Two mbarriers alternate (the previous phase of the one a warp arrives
+  // on is the one it waited for a trip ago); with four ring slots the slot being written (zp+1) was last read for plane
+  // zp-3, which every warp finished before it arrived for plane zp-1 - and that arrival has been waited for.
+  if (tid == 0) { mbar_init(&mbar[0], SX_THREADS); mbar_init(&mbar[1], SX_THREADS); }
+  fetch(zs);
+  __syncthreads();
+  stage(zs);
+  mbar_arrive(&mbar[0]);
+  fetch(zs + 1);
+  long long zoff = (long long)(zs - src.oz0) * (long long)nxy;  // may start negative: only used for planes inside [oz0, oz0+onz)
+  for (int zp = zs; zp < ze; zp++, zoff += (long long)nxy) {
+    const int i = zp - zs;
+    if (zp + 1 < ze) {  // block-uniform
+      stage(zp + 1);
+      mbar_arrive(&mbar[(i + 1) & 1]);
+      fetch(zp + 2);  // loads fly while this plane's y/z passes run
+    }
+    mbar_wait(&mbar[i & 1], (unsigned)(i >> 1) & 1u);
+    const double2 *buf = xs2 + (size_t)(i % SX_RING) * (SX_ROWS * 64);
     // ---- y pass + z pass ----
-    {
+    if (!SX_STAGE_WARPS || warp < SX_TY / 2) {
       float ob[2][4], oi[2][4];
       if (!yedge) {
-        if (!cta_bad) yz_pass2<true, false>(buf, 2 * warp, lane, false, false, S, ob, oi);
-        else yz_pass2<false, false>(buf, 2 * warp, lane, false, false, S, ob, oi);
+        yz_pass2<false>(buf, 2 * warp, lane, false, false, S, ob, oi);
       } else {
-        yz_pass2<false, true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
+        yz_pass2<true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
       }
       const bool zborder = zp < 2 || zp >= nz - 2;
       const int zo = zp - 2;
@@ -335,7 +363,6 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
         }
       }
     }
-    // the other half of the double buffer is rewritten only after the next barrier
   }
   // block reduction of the range
 #pragma unroll
