@@ -83,7 +83,8 @@ def kernel_bytes(name, n, nv, nt, nwords):
         "threshold": 4 * n + nwords * 4,         # R V + W bits
         "mc_classify": 4 * n,                    # R V (composed on the fly)
         "mc_emit": 24 * nv + 12 * nt,            # surface term S
-        "tri_remap_degen": 12 * nt + 72 * nt + 4 * nt,
+        "tri_degen": 12 * nt + nt // 4,           # R indices + W keep bits/counts (positions only for the few near-corner ones)
+        "tri_finish": 24 * nt,                   # R indices + W renumbered, compacted indices
         "cc_local": nwords * 4, "cc_border": nwords * 4, "cc_flatten": nwords * 4, "cc_best": nwords * 4,
         "cc_select": nwords * 8, "dilate_bbox": nwords * 12,
     }

@@ -305,6 +305,12 @@ int b2m_compose_materialize(b2m_ctx *ctx, const b2m_geom &g, const b2m_front_out
 // marching-cubes output of one rank, before the weld.  Vertex ids are GLOBAL (reference emission order
 // over the whole volume): own edge vertices e_off .. e_off+nv_edge, own centroid vertices
 // NVE+c_off .. NVE+c_off+nv_c; verts[] holds the own blocks back to back.
+// A triangle whose three vertices are edge vertices farther than d from the ends of their cube edges has area >= 0.3 d^2
+// (all sides >= d, every height >= d/2: two points on different cube edges are at least max(d_a, d_b) apart, and a
+// boundary point near the line through two others must be near one of them or near a corner), so with d = 1/128 it is
+// three orders of magnitude above the reference's FLT_EPSILON area threshold (src/meshify.c:122-142): only triangles
+// with a flagged or centroid vertex need the FP64 needle test and its three position gathers.
+#define B2M_NEAR_TOL 0.0078125f
 struct b2m_mesh_dev {
   double *verts;  // BUF_VERTS: [edge block | centroid block]
   int *tris;      // BUF_TRIS (global vertex ids)
@@ -312,6 +318,7 @@ struct b2m_mesh_dev {
   unsigned int NVE, NVC, NT;        // global counts
   unsigned int e_off, c_off, t_off; // global offsets of the own blocks
   unsigned int nitems;              // own weld items in BUF_CAND
+  const uint32_t *nearbits;         // one bit per own EDGE vertex (local index): within B2M_NEAR_TOL of a grid corner
   const double *halo_verts;         // next rank's first-plane vertices: ids halo0 .. halo1
   unsigned int halo0, halo1;
   const double *d_p0;               // device pointer to the weld's key origin (the reference's pts[0])

@@ -521,6 +521,7 @@ struct mc_emit_params {
   double *verts;         // own vertices: [edge block | centroid block]
   int *tris;             // own triangles (global vertex ids)
   b2m_item *items;       // weld items (vertices / soup copies near a grid corner)
+  uint32_t *nearbits;    // bit per own edge vertex: within B2M_NEAR_TOL of a grid corner (zeroed before the launch)
   unsigned int item_cap;
   unsigned int n_active;
   unsigned int e_off;    // global id of the first own edge vertex (segbits[].w already includes it)
@@ -560,6 +561,7 @@ __device__ __forceinline__ float lew_u(float c0, float c1) {
   return den != 0.0f ? __fdiv_rn(c0, den) : 0.5f;
 }
 __device__ __forceinline__ bool near_int(float f, float tol) { return fabsf(__fsub_rn(f, rintf(f))) < tol; }
+__device__ __forceinline__ void flag_near(const mc_emit_params &e, uint32_t local) { atomicOr(e.nearbits + (local >> 5), 1u << (local & 31u)); }
 __device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f - rint(f)) < tol; }
 
 __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params e) {
@@ -599,21 +601,30 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
         float px = __fadd_rn(__fadd_rn(fx, lew_u(c[0], c[1])), flo0);
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)px; o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(px, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        if (near_int(px, B2M_NEAR_TOL)) {
+          flag_near(e, vid - e.e_off);
+          if (near_int(px, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        }
         vid++;
       }
       if (ey) {
         float py = __fadd_rn(__fadd_rn(fy, lew_u(c[0], c[3])), flo1);
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)py; o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(py, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        if (near_int(py, B2M_NEAR_TOL)) {
+          flag_near(e, vid - e.e_off);
+          if (near_int(py, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        }
         vid++;
       }
       if (ez) {
         float pz = __fadd_rn(__fadd_rn(fz, lew_u(c[0], c[4])), flo2);
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)pz;
-        if (near_int(pz, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        if (near_int(pz, B2M_NEAR_TOL)) {
+          flag_near(e, vid - e.e_off);
+          if (near_int(pz, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+        }
       }
     } else {
       // classic: FP64, mu = (iso - v1)/(v2 - v1), p = p1 + mu*(p2-p1) (src/oldcubes.c:35-38) with the
@@ -630,6 +641,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
                          : __dadd_rn(gx + 1.0, __dmul_rn(__ddiv_rn(__dsub_rn(iso, v1), __dsub_rn(v0, v1)), -1.0));
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = px; o[1] = gy; o[2] = gz;
+        if (near_int_d(px, (double)B2M_NEAR_TOL)) flag_near(e, vid - e.e_off);
         vid++;
       }
       if (ey) {
@@ -640,6 +652,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
                           : __dadd_rn(gy, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = gx; o[1] = py; o[2] = gz;
+        if (near_int_d(py, (double)B2M_NEAR_TOL)) flag_near(e, vid - e.e_off);
         vid++;
       }
       if (ez) {
@@ -647,6 +660,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
         double pz = __dadd_rn(gz, __ddiv_rn(__dsub_rn(iso, v0), __dsub_rn(v1, v0)));
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
         o[0] = gx; o[1] = gy; o[2] = pz;
+        if (near_int_d(pz, (double)B2M_NEAR_TOL)) flag_near(e, vid - e.e_off);
       }
     }
   }
@@ -934,6 +948,8 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   }
   B2M_TRY(b2m_reserve(ctx, BUF_VERTS, ((size_t)tot_v + tot_c) * 24));
   B2M_TRY(b2m_reserve(ctx, BUF_TRIS, (size_t)tot_t * 12));
+  const size_t near_words = (size_t)tot_v / 32 + 1;
+  B2M_TRY(b2m_reserve(ctx, BUF_REMAP, near_words * 4));
   size_t ccap = ((size_t)tot_v + tot_c) / (p.classic ? 4 : 16) + 4096;
   mc_emit_params e;
   memset(&e, 0, sizeof(e));
@@ -944,6 +960,8 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     e.verts = b2m_ptr<double>(ctx, BUF_VERTS);
     e.tris = b2m_ptr<int>(ctx, BUF_TRIS);
     e.items = b2m_ptr<b2m_item>(ctx, BUF_CAND);
+    e.nearbits = b2m_ptr<uint32_t>(ctx, BUF_REMAP);
+    CU_TRY(cudaMemsetAsync(e.nearbits, 0, near_words * 4, ctx->stream));
     e.item_cap = (unsigned)ccap;
     e.n_active = n_active;
     e.e_off = e_off;
@@ -967,6 +985,7 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   mesh->nitems = ctx->h_scalars->n_cand;
   mesh->verts = b2m_ptr<double>(ctx, BUF_VERTS);
   mesh->tris = b2m_ptr<int>(ctx, BUF_TRIS);
+  mesh->nearbits = b2m_ptr<uint32_t>(ctx, BUF_REMAP);
   // key origin of the weld = the reference's pts[0]
   if (W == 1) {
     mesh->d_p0 = p.classic ? d_sc->pts0 : mesh->verts;

@@ -313,67 +313,142 @@ __global__ void __launch_bounds__(256) k_w_patch(unsigned n, const uint32_t *__r
   vout[3 * o] = s[0]; vout[3 * o + 1] = s[1]; vout[3 * o + 2] = s[2];
 }
 
-// remap triangle indices to the welded numbering and flag the degenerate ones (src/meshify.c:118-145)
-__global__ void __launch_bounds__(256) k_tri_remap_degen(int *__restrict__ tris, unsigned nt, const double *__restrict__ verts,
-                                                         const double *__restrict__ halo, weld_geom g, weld_tables w,
-                                                         uint32_t *__restrict__ keepbits, uint32_t *__restrict__ keepcnt,
-                                                         unsigned int *__restrict__ overflow) {
-  // keep flags leave the kernel as one bit per triangle + a count per 32 triangles (the compaction offsets come
-  // from a scan over nt/32 counts instead of nt flags)
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t keep = 0;
-  if (i < nt) {
-  int idx[3];
-  double p[3][3];
-#pragma unroll
-  for (int c = 0; c < 3; c++) {
-    const uint32_t vid = (uint32_t)tris[3 * (size_t)i + c];
-    const uint32_t id = g.classic_soup ? 3u * (g.t_off + i) + (uint32_t)c : vid;
-    const int k = find_item(w, id);
-    const double *src;
-    if (k >= 0) {
-      idx[c] = (int)__ldg(w.S_out + k);
-      src = w.S_pos + 3 * (size_t)__ldg(w.S_top + k);
-    } else {
-      bool dead;
-      idx[c] = (int)(vid - dead_below(w, vid, &dead));
-      if (vid - g.e_off < g.nv_edge) src = verts + 3 * (size_t)(vid - g.e_off);
-      else if (vid - g.c_base < g.nv_c) src = verts + 3 * (size_t)(g.nv_edge + (vid - g.c_base));
-      else if (vid - g.halo0 < g.halo1 - g.halo0) src = halo + 3 * (size_t)(vid - g.halo0);
-      else { atomicOr(overflow, 2u); src = verts; }
-    }
-    p[c][0] = src[0]; p[c][1] = src[1]; p[c][2] = src[2];
+// Triangle clean-up (src/meshify.c:113-168) in two streaming passes over the index array:
+//   k_tri_degen : keep bit per triangle (+ count per 32) - the reference's FP64 needle test, run only for the triangles
+//                 that can fail it (a vertex within B2M_NEAR_TOL of a grid corner, a centroid vertex, a vertex of the
+//                 next rank: see B2M_NEAR_TOL); the others never touch a vertex position;
+//   k_tri_finish: kept triangles -> welded vertex numbering, written at their compacted position.
+// welded index and (optionally) position of one triangle corner; slow = the vertex may own a weld item
+__device__ __forceinline__ int tri_corner(const weld_geom &g, const weld_tables &w, uint32_t vid, uint32_t soup_id, bool slow,
+                                          const double *__restrict__ verts, const double *__restrict__ halo, const double **src,
+                                          unsigned int *__restrict__ overflow) {
+  const int k = slow ? find_item(w, g.classic_soup ? soup_id : vid) : -1;
+  if (k >= 0) {
+    if (src) *src = w.S_pos + 3 * (size_t)__ldg(w.S_top + k);
+    return (int)__ldg(w.S_out + k);
   }
-  if (w.Q || w.P) { tris[3 * (size_t)i] = idx[0]; tris[3 * (size_t)i + 1] = idx[1]; tris[3 * (size_t)i + 2] = idx[2]; }
-  double l = dist_rn(p[0], p[1]), m = dist_rn(p[0], p[2]), n = dist_rn(p[1], p[2]);
-  double cc = fmin(fmin(l, m), n), aa = fmax(fmax(l, m), n);
-  double bb = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(l, m), n), aa), cc);
-  double amb = __dsub_rn(aa, bb);
-  double t1 = __dsub_rn(cc, amb);
-  keep = 1;
-  if (t1 <= 0.0) keep = 0;
-  else {
-    double prod = __dmul_rn(__dmul_rn(__dmul_rn(__dadd_rn(aa, __dadd_rn(bb, cc)), t1), __dadd_rn(cc, amb)),
-                            __dadd_rn(aa, __dsub_rn(bb, cc)));
-    double area4 = __dmul_rn(0.25, __dsqrt_rn(prod));
-    if (area4 < (double)FLT_EPSILON) keep = 0;
+  bool dead;
+  const int idx = (int)(vid - dead_below(w, vid, &dead));
+  if (src) {
+    if (vid - g.e_off < g.nv_edge) *src = verts + 3 * (size_t)(vid - g.e_off);
+    else if (vid - g.c_base < g.nv_c) *src = verts + 3 * (size_t)(g.nv_edge + (vid - g.c_base));
+    else if (vid - g.halo0 < g.halo1 - g.halo0) *src = halo + 3 * (size_t)(vid - g.halo0);
+    else { atomicOr(overflow, 2u); *src = verts; }
   }
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, keep != 0);
-  if ((threadIdx.x & 31) == 0 && i < nt) { keepbits[i >> 5] = m; keepcnt[i >> 5] = (uint32_t)__popc(m); }
+  return idx;
+}
+// may this vertex fail the needle test / own a weld item?  (own edge vertices: the flag bit; everything else: yes)
+__device__ __forceinline__ bool vert_slow(const weld_geom &g, const uint32_t *__restrict__ nearbits, uint32_t vid) {
+  const uint32_t l = vid - g.e_off;
+  if (!nearbits || l >= g.nv_edge) return true;
+  return (__ldg(nearbits + (l >> 5)) >> (l & 31u)) & 1u;
 }
 
-__global__ void __launch_bounds__(256) k_compact_tris(const int *__restrict__ tin, int *__restrict__ tout,
-                                                      const uint32_t *__restrict__ keepbits,
-                                                      const uint32_t *__restrict__ cnt_scanned, unsigned nt) {
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nt) return;
-  const uint32_t m = __ldg(keepbits + (i >> 5));
-  const unsigned bit = i & 31u;
-  if (!((m >> bit) & 1u)) return;
-  const uint32_t me = __ldg(cnt_scanned + (i >> 5)) + (uint32_t)__popc(m & ((1u << bit) - 1u));
-  size_t o = 3 * (size_t)me;
-  tout[o] = tin[3 * (size_t)i]; tout[o + 1] = tin[3 * (size_t)i + 1]; tout[o + 2] = tin[3 * (size_t)i + 2];
+// Both passes: a block of 256 threads covers 1024 consecutive triangles, thread t taking t, t+256, t+512, t+768 (twelve
+// index loads in flight per thread; a warp's ballot is the keep / slow word of 32 consecutive triangles).
+#define TRI_PER_THREAD 4
+#define TRI_PER_BLOCK (256 * TRI_PER_THREAD)
+__global__ void __launch_bounds__(256) k_tri_degen(const int *__restrict__ tris, unsigned nt, const double *__restrict__ verts,
+                                                   const double *__restrict__ halo, const uint32_t *__restrict__ nearbits,
+                                                   weld_geom g, weld_tables w, uint32_t *__restrict__ keepbits,
+                                                   uint32_t *__restrict__ keepcnt, uint32_t *__restrict__ slowbits,
+                                                   unsigned int *__restrict__ overflow) {
+  // the triangles that need the test are gathered per block so that whole warps run it (a few percent of the
+  // triangles, spread evenly: without the gather nearly every warp would walk the slow path for one or two lanes)
+  __shared__ unsigned s_n;
+  __shared__ unsigned short s_list[TRI_PER_BLOCK];
+  __shared__ unsigned char s_keep[TRI_PER_BLOCK];
+  const unsigned tid = threadIdx.x, lane = tid & 31u, b0 = blockIdx.x * TRI_PER_BLOCK;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  uint32_t v[TRI_PER_THREAD][3];
+#pragma unroll
+  for (int k = 0; k < TRI_PER_THREAD; k++) {
+    const unsigned i = b0 + k * 256 + tid;
+    const int *t = tris + 3 * (size_t)(i < nt ? i : 0);
+    v[k][0] = (uint32_t)__ldg(t); v[k][1] = (uint32_t)__ldg(t + 1); v[k][2] = (uint32_t)__ldg(t + 2);
+  }
+  unsigned slowm = 0;
+#pragma unroll
+  for (int k = 0; k < TRI_PER_THREAD; k++) {
+    const unsigned i = b0 + k * 256 + tid;
+    const bool slow = i < nt && (vert_slow(g, nearbits, v[k][0]) | vert_slow(g, nearbits, v[k][1]) | vert_slow(g, nearbits, v[k][2]));
+    const unsigned m = __ballot_sync(0xffffffffu, slow);
+    unsigned base = 0;
+    if (lane == 0 && m) base = atomicAdd(&s_n, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (slow) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * 256 + tid);
+    if (lane == 0 && i < nt) slowbits[i >> 5] = m;
+    slowm |= (slow ? 1u : 0u) << k;
+  }
+  __syncthreads();
+  const unsigned ns = s_n;
+  for (unsigned q = tid; q < ns; q += blockDim.x) {
+    const unsigned lt = s_list[q], ti = b0 + lt;
+    double p[3][3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t vid = (uint32_t)tris[3 * (size_t)ti + c];
+      const double *src;
+      tri_corner(g, w, vid, 3u * (g.t_off + ti) + (uint32_t)c, true, verts, halo, &src, overflow);
+      p[c][0] = src[0]; p[c][1] = src[1]; p[c][2] = src[2];
+    }
+    double l = dist_rn(p[0], p[1]), m = dist_rn(p[0], p[2]), n = dist_rn(p[1], p[2]);
+    double cc = fmin(fmin(l, m), n), aa = fmax(fmax(l, m), n);
+    double bb = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(l, m), n), aa), cc);
+    double amb = __dsub_rn(aa, bb);
+    double t1 = __dsub_rn(cc, amb);
+    unsigned char keep = 1;
+    if (t1 <= 0.0) keep = 0;
+    else {
+      double prod = __dmul_rn(__dmul_rn(__dmul_rn(__dadd_rn(aa, __dadd_rn(bb, cc)), t1), __dadd_rn(cc, amb)),
+                              __dadd_rn(aa, __dsub_rn(bb, cc)));
+      double area4 = __dmul_rn(0.25, __dsqrt_rn(prod));
+      if (area4 < (double)FLT_EPSILON) keep = 0;
+    }
+    s_keep[lt] = keep;
+  }
+  __syncthreads();
+  // keep flags leave the kernel as one bit per triangle + a count per 32 triangles (the compaction offsets come
+  // from a scan over nt/32 counts instead of nt flags)
+#pragma unroll
+  for (int k = 0; k < TRI_PER_THREAD; k++) {
+    const unsigned i = b0 + k * 256 + tid;
+    const bool keep = i < nt && (!((slowm >> k) & 1u) || s_keep[k * 256 + tid]);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0 && i < nt) { keepbits[i >> 5] = m; keepcnt[i >> 5] = (uint32_t)__popc(m); }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tri_finish(const int *__restrict__ tin, int *__restrict__ tout,
+                                                    const uint32_t *__restrict__ keepbits, const uint32_t *__restrict__ cnt_scanned,
+                                                    const uint32_t *__restrict__ slowbits, unsigned nt, weld_geom g, weld_tables w) {
+  const unsigned tid = threadIdx.x, bit = tid & 31u, b0 = blockIdx.x * TRI_PER_BLOCK;
+  uint32_t v[TRI_PER_THREAD][3], km[TRI_PER_THREAD], sm[TRI_PER_THREAD], base[TRI_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < TRI_PER_THREAD; k++) {
+    const unsigned i = b0 + k * 256 + tid;
+    const bool in = i < nt;
+    const int *t = tin + 3 * (size_t)(in ? i : 0);
+    v[k][0] = (uint32_t)__ldg(t); v[k][1] = (uint32_t)__ldg(t + 1); v[k][2] = (uint32_t)__ldg(t + 2);
+    km[k] = in ? __ldg(keepbits + (i >> 5)) : 0u;
+    sm[k] = in ? __ldg(slowbits + (i >> 5)) : 0u;
+    base[k] = in ? __ldg(cnt_scanned + (i >> 5)) : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < TRI_PER_THREAD; k++) {
+    if (!((km[k] >> bit) & 1u)) continue;
+    const unsigned i = b0 + k * 256 + tid;
+    const uint32_t me = base[k] + (uint32_t)__popc(km[k] & ((1u << bit) - 1u));
+    const bool slow = (sm[k] >> bit) & 1u;  // only such a triangle can hold a vertex that owns a weld item
+    int idx[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      idx[c] = (w.Q || w.P) ? tri_corner(g, w, v[k][c], 3u * (g.t_off + i) + (uint32_t)c, slow, nullptr, nullptr, nullptr, nullptr)
+                            : (int)v[k][c];
+    const size_t o = 3 * (size_t)me;
+    tout[o] = idx[0]; tout[o + 1] = idx[1]; tout[o + 2] = idx[2];
+  }
 }
 
 // workspace carving: one arena (BUF_WELD) for all the small per-item arrays
@@ -497,18 +572,18 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
   unsigned nt_out = nt;
   if (nt > 0) {
     const size_t nw32 = ((size_t)nt + 31) / 32;
-    B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, nw32 * 8 + 64));
-    uint32_t *kb = b2m_ptr<uint32_t>(ctx, BUF_FLAGS), *kc = kb + nw32;
-    KT_LAUNCH(ctx, "tri_remap_degen", k_tri_remap_degen<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, nt, verts, mesh->halo_verts, g, w, kb, kc, &d_sc->overflow));
+    B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, nw32 * 12 + 64));
+    uint32_t *kb = b2m_ptr<uint32_t>(ctx, BUF_FLAGS), *kc = kb + nw32, *ks = kc + nw32;
+    KT_LAUNCH(ctx, "tri_degen", k_tri_degen<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(tris, nt, verts, mesh->halo_verts, mesh->nearbits, g, w, kb, kc, ks, &d_sc->overflow));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, kc, kc, nw32, &d_sc->n_tri_kept));
     CU_TRY(cudaGetLastError());
     B2M_TRY(b2m_fetch_scalars(ctx));
     if (ctx->h_scalars->overflow & 2u) { b2m_set_error("weld: triangle references a vertex outside this rank's blocks"); return B2M_ECUDA; }
     nt_out = ctx->h_scalars->n_tri_kept;
-    if (nt_out != nt) {
-      B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)nt_out * 12));
+    if (nt_out != nt || w.Q || w.P) {  // something to drop or to renumber: one pass does both
+      B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)(nt_out ? nt_out : 1) * 12));
       int *t2 = b2m_ptr<int>(ctx, BUF_TRIS2);
-      KT_LAUNCH(ctx, "compact_tris", k_compact_tris<<<b2m_cdiv(nt, 256), 256, 0, ctx->stream>>>(tris, t2, kb, kc, nt));
+      KT_LAUNCH(ctx, "tri_finish", k_tri_finish<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(tris, t2, kb, kc, ks, nt, g, w));
       tris = t2;
     }
   }
