@@ -182,6 +182,16 @@ int b2m_meshify_raw_host(b2m_ctx *ctx, const void *h_raw, int datatype, const in
                          float scl_inter, const b2m_opts *opts, const float *srow_x, const float *srow_y,
                          const float *srow_z, void **verts, void **tris, b2m_result *res);
 
+/* ---- post-smooth -------------------------------------------------------------------------
+ * laplacian_smoothHC() (src/quadric.c:343-394; nii2mesh -s <iter> runs it with alpha 0.1, beta 0.5, lockEdges true,
+ * src/nii2mesh.c:331) on a mesh in vec3d / vec3i layout, vertices updated in place; bit-identical to the reference.
+ * _device: pointers into device memory (e.g. d_verts / d_tris of a b2m_result); _host: host memory.
+ * B2M_EARG when a triangle index lies outside 0..nvert-1 (the reference would read out of bounds). */
+int b2m_laplacian_hc_device(b2m_ctx *ctx, double *d_verts, const int *d_tris, int nvert, int ntri, double alpha, double beta,
+                            int iter, int lock_edges);
+int b2m_laplacian_hc_host(b2m_ctx *ctx, double *h_verts, const int *h_tris, int nvert, int ntri, double alpha, double beta,
+                          int iter, int lock_edges);
+
 /* copy the device mesh of the last b2m_meshify_device() call into caller buffers */
 int b2m_fetch_mesh(b2m_ctx *ctx, const b2m_result *res, void *h_verts, void *h_tris);
 

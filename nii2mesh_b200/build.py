@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libb2m.so"
-CU = ["ctx.cu", "scan.cu", "smooth.cu", "cc.cu", "mc.cu", "weld.cu", "pipeline.cu", "tables.cu", "comm.cu", "atlas.cu", "isolevel.cu", "io.cu"]
+CU = ["ctx.cu", "scan.cu", "smooth.cu", "cc.cu", "mc.cu", "weld.cu", "pipeline.cu", "tables.cu", "comm.cu", "atlas.cu", "isolevel.cu", "io.cu", "post.cu"]
 CC = ["meshify_host.c", "hostcopy.c"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

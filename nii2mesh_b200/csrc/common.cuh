@@ -72,6 +72,10 @@ enum {
   BUF_SEAM0,       // slabs: CC seam lists (roots, dense ids, pairs, tables) carved per use
   BUF_SEAM1,
   BUF_SEAM2,
+  BUF_POST_INC,    // post-smooth: vertex -> (triangle, corner) incidence list
+  BUF_POST_P,      // post-smooth: p / p' / b vertex arrays + border flags
+  BUF_POST_V,      // post-smooth from host memory: device copy of the vertices
+  BUF_POST_T,      //   ... and of the triangles
   BUF_COUNT
 };
 

@@ -408,7 +408,9 @@ __global__ void __launch_bounds__(MCB_THREADS) k_mc_classify(const __grid_consta
 // scan3: the packed per-segment counts (segbits[].w = nv | nt<<7 | nc<<16) -> exclusive bases
 // segbits[].w = vbase, segt[] = tbase, segc[] = cbase; totals -> sc->tot_v/tot_t/tot_c.
 #define S3_THREADS 256
+#ifndef S3_ITEMS
 #define S3_ITEMS 8
+#endif
 #define S3_TILE (S3_THREADS * S3_ITEMS)
 struct u3 { uint32_t v, t, c; };
 __device__ __forceinline__ u3 u3_add(u3 a, u3 b) { return {a.v + b.v, a.t + b.t, a.c + b.c}; }
@@ -484,8 +486,11 @@ __global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ 
   size_t base = (size_t)blockIdx.x * S3_TILE + (size_t)threadIdx.x * S3_ITEMS;
   uint32_t raw[S3_ITEMS];
   if (base + S3_ITEMS <= n && (reinterpret_cast<uintptr_t>(segcnt + base) & 15) == 0) {  // 8 consecutive counts = one 32-byte sector per thread
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(segcnt + base)), b = __ldg(reinterpret_cast<const uint4 *>(segcnt + base) + 1);
-    raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+#pragma unroll
+    for (int q = 0; q < S3_ITEMS / 4; q++) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4 *>(segcnt + base) + q);
+      raw[4 * q] = a.x; raw[4 * q + 1] = a.y; raw[4 * q + 2] = a.z; raw[4 * q + 3] = a.w;
+    }
   } else {
 #pragma unroll
     for (int i = 0; i < S3_ITEMS; i++) raw[i] = base + i < n ? __ldg(segcnt + base + i) : 0u;

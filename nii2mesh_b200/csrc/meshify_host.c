@@ -18,6 +18,7 @@
 #include "../../include/b2m.h"
 #include "../../include/meshify.h"
 #include "../../include/isolevel.h"
+#include "../../include/quadric.h"
 
 int b2m_get_default_backend(void);
 
@@ -74,6 +75,15 @@ float setThreshold(float *img, int nvox, int darkMediumBright123) {
     return NAN;
   }
   return iso;
+}
+
+/* -s <iterations> (src/quadric.c:343-394, called from src/nii2mesh.c:331 and src/obj2mesh.c:122): same prototype, the
+ * incidence list and the gathers run on the GPU */
+void laplacian_smoothHC(vec3d *verts, vec3i *tris, int nvert, int ntri, double alpha, double beta, int iter, bool lockEdges) {
+  b2m_ctx *ctx = get_ctx();
+  if (!ctx) return; /* no CUDA device: there is no CPU path */
+  if (b2m_laplacian_hc_host(ctx, (double *)verts, (const int *)tris, nvert, ntri, alpha, beta, iter, lockEdges) != B2M_OK)
+    fprintf(stderr, "laplacian_smoothHC: %s\n", b2m_last_error());
 }
 
 /* voxel -> world transform of the vertices (src/meshify.c:1021-1045).  Each coordinate is the FP64

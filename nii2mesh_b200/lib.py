@@ -102,6 +102,10 @@ def load():
     L.b2m_apply_sform_device.argtypes = [vp, C.POINTER(Result), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.b2m_meshify_raw_host.argtypes = [vp, vp, C.c_int, i64p, C.c_float, C.c_float, C.POINTER(Opts), C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(vp), C.POINTER(vp), C.POINTER(Result)]
+    L.b2m_laplacian_hc_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.b2m_laplacian_hc_device.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    L.laplacian_smoothHC.argtypes = [vp, vp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_bool]
+    L.laplacian_smoothHC.restype = None
     L.b2m_comm_nccl_id.argtypes = [vp]
     L.b2m_comm_create_nccl.argtypes = [C.POINTER(vp), vp, vp, C.c_int, C.c_int]
     L.b2m_comm_create_local.argtypes = [C.POINTER(vp), C.c_int]
@@ -245,6 +249,13 @@ class Engine:
         self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
         return v, t, r
 
+    def fetch(self, r):
+        """(verts, tris) of the device-resident mesh of a Result"""
+        v = np.empty((r.nverts, 3), np.float64)
+        t = np.empty((r.ntris, 3), np.int32)
+        self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
+        return v, t
+
     def meshify(self, vol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False,
                 backend=BACKEND_LEWINER, verbose=False):
         """host volume in, host mesh out (H2D + device pipeline + D2H), like the reference's meshify()."""
@@ -288,6 +299,20 @@ class Engine:
         _libc.free(pv)
         _libc.free(pt)
         return v, t, r
+
+    # ---- post-smooth ----
+    def laplacian_hc(self, verts, tris, iters, alpha=0.1, beta=0.5, lock_edges=True):
+        """laplacian_smoothHC() (src/quadric.c:343-394) on a host mesh; returns the smoothed vertices"""
+        v = np.ascontiguousarray(verts, dtype=np.float64).copy()
+        t = np.ascontiguousarray(tris, dtype=np.int32)
+        self._chk(self.lib.b2m_laplacian_hc_host(self.ctx, v.ctypes.data, t.ctypes.data, len(v), len(t), float(alpha), float(beta),
+                                                 int(iters), int(lock_edges)))
+        return v
+
+    def laplacian_hc_result(self, r, iters, alpha=0.1, beta=0.5, lock_edges=True):
+        """the same on the device-resident mesh of a Result (in place, before fetching it)"""
+        self._chk(self.lib.b2m_laplacian_hc_device(self.ctx, r.d_verts, r.d_tris, r.nverts, r.ntris, float(alpha), float(beta),
+                                                   int(iters), int(lock_edges)))
 
     def isolevel(self, vol_or_dvol, dark_medium_bright_123):
         """-i d / m / b: the reference's setThreshold() (src/isolevel.c:245-277); 1 = dark, 2 = medium, 3 = bright"""

@@ -174,6 +174,14 @@ class Oracle:
         n2 = self.lib.orc_degenerate(v.ctypes.data, t.ctypes.data, len(t))
         return t[:n2].copy()
 
+    def laplacian_hc(self, verts, tris, iters, alpha=0.1, beta=0.5, lock_edges=True):
+        v = np.ascontiguousarray(verts, dtype=np.float64).copy()
+        t = np.ascontiguousarray(tris, dtype=np.int32)
+        self.lib.orc_laplacian_hc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        self.lib.orc_laplacian_hc.restype = None
+        self.lib.orc_laplacian_hc(v.ctypes.data, t.ctypes.data, len(v), len(t), alpha, beta, int(iters), int(lock_edges))
+        return v
+
     def meshify(self, vol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False, backend=0):
         """returns dict(verts, tris, pre_nv, pre_nt, iso, rc); vol is not modified."""
         v = _f32(vol).copy()
@@ -270,6 +278,15 @@ class Ref:
         t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(n2, 3)).copy()
         _libc.free(pt)
         return t
+
+    def laplacian_hc(self, verts, tris, iters, alpha=0.1, beta=0.5, lock_edges=True):
+        """laplacian_smoothHC(), src/quadric.c:343-394 (what nii2mesh -s <iters> runs after meshify + apply_sform)"""
+        v = np.ascontiguousarray(verts, dtype=np.float64).copy()
+        t = np.ascontiguousarray(tris, dtype=np.int32)
+        self.lib.laplacian_smoothHC.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_bool]
+        self.lib.laplacian_smoothHC.restype = None
+        self.lib.laplacian_smoothHC(v.ctypes.data, t.ctypes.data, len(v), len(t), alpha, beta, int(iters), bool(lock_edges))
+        return v
 
     def meshify(self, vol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False,
                 return_img=False):

@@ -758,4 +758,88 @@ float orc_set_threshold(const float *img, int nvox, int darkMediumBright123) {
   return (mid / scl) + mn;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Post-smooth: Laplacian smoothing with Humphrey's classes.  src/quadric.c:343-394
+ * (laplacian_smoothHC) over src/quadric.c:315-341 (laplacian_smooth) and the border rule of
+ * src/quadric.c:186-216 (update_mesh, iteration 0).
+ * Restated as a GATHER over a vertex -> (triangle, corner) incidence list in triangle order - the
+ * order in which the reference's triangle loop adds to sum[v], so every FP64 sum rounds alike:
+ *   corner 0 of (p0,p1,p2): sum[p0] += v[p1] + v[p2];  corner 1: v[p0] + v[p2];  corner 2: v[p0] + v[p1]
+ *   new v = sum / num (num = 2 per incident corner), vertices without triangles keep their place.
+ * HC step (alpha, beta): q = p; p = L(p); b = p - (verts*alpha + q*(1-alpha)); q = L(b);
+ *   p = p - (b*beta + q*(1-beta)).  lockEdges: a vertex stays where it was when some vertex's
+ * one-ring (all corners of its incident triangles) holds it exactly once. */
+typedef struct { int *start, *ref; } orc_inc;  /* ref = tri*4 + corner, ascending per vertex */
+static orc_inc orc_incidence(const ovec3i *tris, int nvert, int ntri) {
+  orc_inc I;
+  I.start = (int *)calloc((size_t)nvert + 1, sizeof(int));
+  I.ref = (int *)malloc((size_t)(ntri ? ntri : 1) * 3 * sizeof(int));
+  for (int t = 0; t < ntri; t++) { I.start[tris[t].x + 1]++; I.start[tris[t].y + 1]++; I.start[tris[t].z + 1]++; }
+  for (int v = 0; v < nvert; v++) I.start[v + 1] += I.start[v];
+  int *fill = (int *)malloc((size_t)(nvert ? nvert : 1) * sizeof(int));
+  memcpy(fill, I.start, (size_t)nvert * sizeof(int));
+  for (int t = 0; t < ntri; t++) {
+    const int v[3] = {tris[t].x, tris[t].y, tris[t].z};
+    for (int c = 0; c < 3; c++) I.ref[fill[v[c]]++] = t * 4 + c;
+  }
+  free(fill);
+  return I;
+}
+static void orc_laplacian(const orc_inc *I, const ovec3i *tris, const ovec3d *in, ovec3d *out, int nvert) {
+  for (int v = 0; v < nvert; v++) {
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    int num = 0;
+    for (int k = I->start[v]; k < I->start[v + 1]; k++) {
+      const ovec3i *t = &tris[I->ref[k] >> 2];
+      const int c = I->ref[k] & 3;
+      const int a = c == 0 ? t->y : t->x, b = c == 2 ? t->y : t->z;
+      sx = sx + (in[a].x + in[b].x); sy = sy + (in[a].y + in[b].y); sz = sz + (in[a].z + in[b].z);
+      num += 2;
+    }
+    if (num <= 0) { out[v] = in[v]; continue; }
+    out[v].x = sx / num; out[v].y = sy / num; out[v].z = sz / num;
+  }
+}
+void orc_laplacian_hc(ovec3d *verts, const ovec3i *tris, int nvert, int ntri, double alpha, double beta, int iter, int lockEdges) {
+  const double alpha1 = 1.0 - alpha, beta1 = 1.0 - beta;
+  orc_inc I = orc_incidence(tris, nvert, ntri);
+  size_t nb = (size_t)(nvert ? nvert : 1) * sizeof(ovec3d);
+  ovec3d *p = (ovec3d *)malloc(nb), *q = (ovec3d *)malloc(nb), *b = (ovec3d *)malloc(nb), *lb = (ovec3d *)malloc(nb);
+  memcpy(p, verts, (size_t)nvert * sizeof(ovec3d));
+  for (int j = 0; j < iter; j++) {
+    memcpy(q, p, (size_t)nvert * sizeof(ovec3d));
+    orc_laplacian(&I, tris, q, p, nvert);
+    for (int i = 0; i < nvert; i++) {
+      b[i].x = p[i].x - (verts[i].x * alpha + q[i].x * alpha1);
+      b[i].y = p[i].y - (verts[i].y * alpha + q[i].y * alpha1);
+      b[i].z = p[i].z - (verts[i].z * alpha + q[i].z * alpha1);
+    }
+    orc_laplacian(&I, tris, b, lb, nvert);
+    for (int i = 0; i < nvert; i++) {
+      p[i].x = p[i].x - (b[i].x * beta + lb[i].x * beta1);
+      p[i].y = p[i].y - (b[i].y * beta + lb[i].y * beta1);
+      p[i].z = p[i].z - (b[i].z * beta + lb[i].z * beta1);
+    }
+  }
+  unsigned char *border = (unsigned char *)calloc((size_t)(nvert ? nvert : 1), 1);
+  if (lockEdges) {
+    for (int v = 0; v < nvert; v++) {
+      const int n = 3 * (I.start[v + 1] - I.start[v]);
+      for (int a = 0; a < n; a++) {  /* ids of the one-ring, corner by corner; an id seen exactly once is a border vertex */
+        const ovec3i *ta = &tris[I.ref[I.start[v] + a / 3] >> 2];
+        const int ida = a % 3 == 0 ? ta->x : (a % 3 == 1 ? ta->y : ta->z);
+        int cnt = 0;
+        for (int c = 0; c < n; c++) {
+          const ovec3i *tc = &tris[I.ref[I.start[v] + c / 3] >> 2];
+          cnt += (c % 3 == 0 ? tc->x : (c % 3 == 1 ? tc->y : tc->z)) == ida;
+        }
+        if (cnt == 1) border[ida] = 1;
+      }
+    }
+  }
+  for (int i = 0; i < nvert; i++)
+    if (!border[i]) verts[i] = p[i];
+  free(border); free(p); free(q); free(b); free(lb); free(I.start); free(I.ref);
+}
+
 void orc_free(void *p) { free(p); }

@@ -13,7 +13,7 @@ from conftest import ROOT
 
 def declared_symbols():
     syms = []
-    for h in ("b2m.h", "meshify.h"):
+    for h in ("b2m.h", "meshify.h", "isolevel.h", "quadric.h"):
         txt = (ROOT / "include" / h).read_text()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         syms += re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", txt)
@@ -22,7 +22,7 @@ def declared_symbols():
 
 def test_header_symbols_exported(libb2m):
     syms = declared_symbols()
-    assert "meshify" in syms and "b2m_meshify_device" in syms and len(syms) >= 25
+    assert "meshify" in syms and "b2m_meshify_device" in syms and "laplacian_smoothHC" in syms and len(syms) >= 25
     for s in syms:
         assert hasattr(libb2m, s), f"libb2m.so does not export {s}"
 
