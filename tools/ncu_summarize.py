@@ -31,7 +31,8 @@ def launches(path):
     h = rows[0]
     ik, iv, iu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
     seq = [(short(r[ik]), float(r[iv].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[r[iu]]) for r in rows[1:]]
-    seq = seq[len(seq) // 2:]  # second (warm) step
+    first = sys.argv[3] if len(sys.argv) > 3 else "k_smooth3"  # a step starts with the smooth: its last launch opens the warm step
+    seq = seq[max(i for i, (k, _) in enumerate(seq) if k.startswith(first)):]
     agg = OrderedDict()
     for k, ms in seq:
         a = agg.setdefault(k, [0, 0.0])
