@@ -367,7 +367,7 @@ def main():
                 libc.free(pv)
                 libc.free(pt)
                 one.last = (sr2.r.h2d_ms, sr2.r.ms[7], sr2.r.d2h_ms)
-                return (sr2.nv_edge + sr2.nv_cent + sr2.nv_extra) * 24 + sr2.ntris_local * 12
+                return int(sr2.r.d2h_bytes)  # bytes that crossed PCIe (Lewiner vertices travel as f32 and are widened on the host)
             api = ("b2m_meshify_slab_host() (include/b2m.h), one z-slab per rank: pinned host planes in, malloc'd host "
                    "mesh blocks out")
         ke = max(1, min(args.steps, 5))
@@ -385,16 +385,18 @@ def main():
             breakdown = {"h2d_ms": round(max_over_ranks(h), 2), "device_ms": round(max_over_ranks(dv), 2),
                          "d2h_ms": round(max_over_ranks(dd), 2), "note": "max over ranks, last timed call"}
         if world == 1:
-            # one untimed call through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
+            # two untimed calls through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
             r2 = lib.Result()
             pv, pt = C.c_void_p(), C.c_void_p()
             o2 = lib.Opts(ISO, 0, 1, 1, 1, 0, 0)
-            eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o2), C.byref(pv), C.byref(pt), C.byref(r2)))
-            libc.free(pv)
-            libc.free(pt)
+            for _ in range(2):  # the second call is the steady state (output blocks pre-faulted from the previous totals)
+                eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o2), C.byref(pv), C.byref(pt), C.byref(r2)))
+                libc.free(pv)
+                libc.free(pt)
             breakdown = {"h2d_ms": round(r2.h2d_ms, 2), "device_ms": round(r2.ms[7], 2), "d2h_ms": round(r2.d2h_ms, 2)}
+            d2h = int(r2.d2h_bytes)  # bytes that crossed PCIe: Lewiner vertices travel as f32 (exact) and are widened on the host
         e2e = {"value": GN / dt / 1e9, "breakdown": breakdown, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
-               "d2h_bytes_per_step": d2h, "bytes_scope": "per rank" if world > 1 else "whole job",
+               "d2h_bytes_per_step": d2h, "d2h_delivered_bytes_per_step": (nv * 24 + nt * 12) if world == 1 else None, "bytes_scope": "per rank" if world > 1 else "whole job",
                "ms_per_step": dt * 1e3, "steps": ke, "api": api}
         L.b2m_host_free(hp)
 

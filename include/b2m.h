@@ -64,6 +64,7 @@ typedef struct {
   float ms[B2M_NSTAGE];      /* CUDA-event device time per stage, ms; ms[B2M_T_TOTAL] = whole call */
   uint64_t launches;         /* kernels launched by this call */
   float h2d_ms, d2h_ms;      /* b2m_meshify_host only: wall-clock time of the host->device / device->host copies */
+  unsigned long long d2h_bytes; /* ... and the bytes the device->host copies moved over PCIe (Lewiner vertices travel as f32) */
 } b2m_result;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -199,6 +199,7 @@ int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
 #define B2M_STAGE_BYTES ((size_t)32 << 20)
 int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int b2m_copy_d2h_f32exact(b2m_ctx *ctx, double *h_dst, const double *d_src, size_t n, int *done);  // doubles that are all f32 values: 4 B each over PCIe
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb);
 void b2m_touch_wait(void);
 

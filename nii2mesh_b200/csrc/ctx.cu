@@ -192,10 +192,12 @@ struct copy_pool {
   // done[slot] counts the copied slices of the chunk that occupies a ring slot
   char *const *ring = nullptr;
   long long spc = 0;
+  int widen = 0;  // the ring holds f32 values that land in dst as f64 (slices and p->n count OUTPUT bytes)
   std::atomic<long long> ready{0};
   std::atomic<int> done[B2M_RING_SLOTS];
 } g_pool;
 extern "C" void b2m_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.c
+extern "C" void b2m_stream_widen(double *dst, const float *src, size_t n);
 static void pool_work(copy_pool *p) {
   for (;;) {
     const long long i = p->next.fetch_add(1);
@@ -206,8 +208,9 @@ static void pool_work(copy_pool *p) {
         if (spins < 2000) cpu_relax();
         else sched_yield();
       }
-      const size_t o = (size_t)i * p->slice, oc = (size_t)(i - c * p->spc) * p->slice;
-      b2m_stream_copy(p->dst + o, p->ring[c % B2M_RING_SLOTS] + oc, p->n - o < p->slice ? p->n - o : p->slice);
+      const size_t o = (size_t)i * p->slice, oc = (size_t)(i - c * p->spc) * p->slice, len = p->n - o < p->slice ? p->n - o : p->slice;
+      if (p->widen) b2m_stream_widen((double *)(p->dst + o), (const float *)(p->ring[c % B2M_RING_SLOTS] + oc / 2), len / 8);
+      else b2m_stream_copy(p->dst + o, p->ring[c % B2M_RING_SLOTS] + oc, len);
       p->done[c % B2M_RING_SLOTS].fetch_add(1, std::memory_order_release);
     } else if (p->src) {
       const size_t o = (size_t)i * p->slice;
@@ -266,7 +269,7 @@ static void par_memcpy(void *dst, const void *src, size_t n) {
   if (nt <= 1 || n <= p->slice) { memcpy(dst, src, n); return; }
   if (tl_touch_pending) b2m_touch_wait();
   pthread_mutex_lock(&p->job_mu);
-  p->dst = (char *)dst; p->src = (const char *)src; p->n = n; p->ring = nullptr;
+  p->dst = (char *)dst; p->src = (const char *)src; p->n = n; p->ring = nullptr; p->widen = 0;
   p->nslices = (long long)((n + p->slice - 1) / p->slice);
   pool_start_locked(p, nt);
   pool_work(p);
@@ -298,22 +301,26 @@ void b2m_touch_wait(void) {  // idempotent
 // chunks into the caller's block (1 MiB slices, non-temporal stores).  ONE pool job for the whole transfer: the
 // workers spin on the "chunks ready" counter instead of being woken and joined per chunk, and the calling thread
 // only waits for DMA events and re-issues ring slots whose slices have all been copied.
-int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+// widen: d_src holds bytes / 8 FLOATS that arrive in h_dst as doubles (half the PCIe bytes; the conversion rides on the
+// copy the pool threads do anyway).  `bytes`, slices and chunk sizes below count OUTPUT bytes; a ring chunk holds
+// B2M_RING_CHUNK input bytes = B2M_RING_CHUNK << widen output bytes.
+static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, int widen) {
   if (!bytes) return B2M_OK;
-  if (bytes < ((size_t)1 << 20) || host_is_pinned(h_dst)) {
+  if (!widen && (bytes < ((size_t)1 << 20) || host_is_pinned(h_dst))) {
     CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     return B2M_OK;
   }
+  const size_t CH = B2M_RING_CHUNK << widen;  // output bytes per ring chunk
   B2M_TRY(stage_init(ctx));
   copy_pool *p = &g_pool;
   char *ring[B2M_RING_SLOTS];
   const int per_buf = (int)(B2M_STAGE_BYTES / B2M_RING_CHUNK);
   for (int k = 0; k < B2M_RING_SLOTS; k++) ring[k] = (char *)ctx->stage[k / per_buf] + (size_t)(k % per_buf) * B2M_RING_CHUNK;
-  const long long nchunk = (long long)((bytes + B2M_RING_CHUNK - 1) / B2M_RING_CHUNK);
-  auto chunk_bytes = [&](long long c) { const size_t o = (size_t)c * B2M_RING_CHUNK; return bytes - o < B2M_RING_CHUNK ? bytes - o : B2M_RING_CHUNK; };
+  const long long nchunk = (long long)((bytes + CH - 1) / CH);
+  auto chunk_bytes = [&](long long c) { const size_t o = (size_t)c * CH; return bytes - o < CH ? bytes - o : CH; };
   auto issue = [&](long long c) -> cudaError_t {
-    cudaError_t e = cudaMemcpyAsync(ring[c % B2M_RING_SLOTS], (const char *)d_src + (size_t)c * B2M_RING_CHUNK, chunk_bytes(c),
+    cudaError_t e = cudaMemcpyAsync(ring[c % B2M_RING_SLOTS], (const char *)d_src + (size_t)c * B2M_RING_CHUNK, chunk_bytes(c) >> widen,
                                     cudaMemcpyDeviceToHost, ctx->stream);
     if (e != cudaSuccess) return e;
     return cudaEventRecord(ctx->ring_ev[c % B2M_RING_SLOTS], ctx->stream);
@@ -323,7 +330,7 @@ int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
   pthread_mutex_lock(&p->job_mu);
   p->dst = (char *)h_dst; p->src = nullptr; p->n = bytes;
   p->nslices = (long long)((bytes + p->slice - 1) / p->slice);
-  p->ring = ring; p->spc = (long long)(B2M_RING_CHUNK / p->slice);
+  p->ring = ring; p->spc = (long long)(CH / p->slice); p->widen = widen;
   p->ready.store(0);
   for (int k = 0; k < B2M_RING_SLOTS; k++) p->done[k].store(0);
   long long issued = 0;
@@ -355,8 +362,9 @@ int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (err != cudaSuccess) break;
     p->ready.store(c + 1, std::memory_order_release);
     if (alone) {
-      const size_t o = (size_t)c * B2M_RING_CHUNK;
-      b2m_stream_copy((char *)h_dst + o, ring[c % B2M_RING_SLOTS], chunk_bytes(c));
+      const size_t o = (size_t)c * CH;
+      if (widen) b2m_stream_widen((double *)((char *)h_dst + o), (const float *)ring[c % B2M_RING_SLOTS], chunk_bytes(c) / 8);
+      else b2m_stream_copy((char *)h_dst + o, ring[c % B2M_RING_SLOTS], chunk_bytes(c));
       p->done[c % B2M_RING_SLOTS].store((int)p->spc);
     }
     refill(false);
@@ -365,6 +373,41 @@ int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
   if (alone) p->next.store(p->nslices);
   pool_finish_locked(p);  // the next job of any kind resets p->ring under job_mu
   CU_TRY(err);
+  return B2M_OK;
+}
+int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) { return copy_d2h_impl(ctx, h_dst, d_src, bytes, 0); }
+int b2m_copy_d2h_widen(b2m_ctx *ctx, double *h_dst, const float *d_src, size_t n) { return copy_d2h_impl(ctx, h_dst, d_src, n * 8, 1); }
+
+// f64 -> f32 copy of an array whose values are all exactly representable in f32 (Lewiner vertices are exported as
+// (double)(float), src/MarchingCubes.c:1127-1129): *inexact is raised otherwise and the caller sends the doubles
+__global__ void __launch_bounds__(256) k_narrow_f64(const double *__restrict__ in, float *__restrict__ out, size_t n, unsigned int *__restrict__ inexact) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < n; i += stride) {
+    const double d = in[i];
+    const float f = (float)d;
+    bad |= !((double)f == d);  // NaN counts as inexact: its payload would not survive
+    out[i] = f;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(inexact, 1u);
+}
+// h_dst[0..n) = d_src[0..n) (doubles), moving 4 bytes per value over PCIe when every value is an f32; *done = 0 when
+// that is not the case (nothing copied: use b2m_copy_d2h)
+int b2m_copy_d2h_f32exact(b2m_ctx *ctx, double *h_dst, const double *d_src, size_t n, int *done) {
+  *done = 0;
+  if (n < ((size_t)1 << 20) || host_is_pinned(h_dst)) return B2M_OK;
+  B2M_TRY(b2m_reserve(ctx, BUF_TMP1, n * 4 + 16));
+  float *tmp = b2m_ptr<float>(ctx, BUF_TMP1);
+  unsigned int *flag = reinterpret_cast<unsigned int *>(tmp + n + (n & 1));
+  CU_TRY(cudaMemsetAsync(flag, 0, 4, ctx->stream));
+  KT_LAUNCH(ctx, "narrow_f64", k_narrow_f64<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(d_src, tmp, n, flag));
+  unsigned int h = 1;
+  CU_TRY(cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  if (h) return B2M_OK;
+  B2M_TRY(b2m_copy_d2h_widen(ctx, h_dst, tmp, n));
+  *done = 1;
   return B2M_OK;
 }
 

@@ -50,3 +50,31 @@ void b2m_stream_copy(void *dst, const void *src, size_t n) {
   else copy_nt_sse2(d, s, n);
   _mm_sfence();
 }
+
+// dst[i] = (double)src[i]: the widening half of a device-to-host copy of f32-valued doubles
+__attribute__((target("avx2"))) static void widen_avx2(double *d, const float *s, size_t n) {
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m128 a = _mm_loadu_ps(s + i), b = _mm_loadu_ps(s + i + 4), c = _mm_loadu_ps(s + i + 8), e = _mm_loadu_ps(s + i + 12);
+    _mm256_stream_pd(d + i, _mm256_cvtps_pd(a));
+    _mm256_stream_pd(d + i + 4, _mm256_cvtps_pd(b));
+    _mm256_stream_pd(d + i + 8, _mm256_cvtps_pd(c));
+    _mm256_stream_pd(d + i + 12, _mm256_cvtps_pd(e));
+  }
+  for (; i < n; i++) d[i] = (double)s[i];
+}
+static void widen_sse2(double *d, const float *s, size_t n) {
+  size_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const __m128 a = _mm_loadu_ps(s + i);
+    _mm_stream_pd(d + i, _mm_cvtps_pd(a));
+    _mm_stream_pd(d + i + 2, _mm_cvtps_pd(_mm_movehl_ps(a, a)));
+  }
+  for (; i < n; i++) d[i] = (double)s[i];
+}
+void b2m_stream_widen(double *dst, const float *src, size_t n) {
+  while (n && ((uintptr_t)dst & 31)) { *dst++ = (double)*src++; n--; }  // non-temporal stores need an aligned destination
+  if (__builtin_cpu_supports("avx2")) widen_avx2(dst, src, n);
+  else widen_sse2(dst, src, n);
+  _mm_sfence();
+}

@@ -98,6 +98,19 @@ __global__ void __launch_bounds__(PS_THREADS) k_ps_border(const int *__restrict_
   const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
   const uint32_t s = __ldg(start + v), n = 3u * (__ldg(start + v + 1) - s);
+  if (n <= 30u) {  // up to 10 incident triangles (a regular vertex has 6): the ids are read once
+    int ids[30];
+    for (uint32_t a = 0; a < n; a += 3) {
+      const int *t = tris + 3 * (size_t)(__ldg(ref + s + a / 3u) >> 2);
+      ids[a] = __ldg(t); ids[a + 1] = __ldg(t + 1); ids[a + 2] = __ldg(t + 2);
+    }
+    for (uint32_t a = 0; a < n; a++) {
+      int cnt = 0;
+      for (uint32_t c = 0; c < n; c++) cnt += ids[c] == ids[a];
+      if (cnt == 1) border[ids[a]] = 1;
+    }
+    return;
+  }
   for (uint32_t a = 0; a < n; a++) {
     const int ida = __ldg(tris + 3 * (size_t)(__ldg(ref + s + a / 3u) >> 2) + a % 3u);
     int cnt = 0;

@@ -28,7 +28,7 @@ class Result(C.Structure):
                 ("pre_nverts", C.c_int), ("pre_ntris", C.c_int), ("nmerged", C.c_int), ("ndegenerate", C.c_int),
                 ("iso_used", C.c_float), ("vmin", C.c_float), ("vmax", C.c_float), ("lo", C.c_int * 3),
                 ("hi", C.c_int * 3), ("iso_reset", C.c_int), ("ms", C.c_float * 8), ("launches", C.c_uint64),
-                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float)]
+                ("h2d_ms", C.c_float), ("d2h_ms", C.c_float), ("d2h_bytes", C.c_uint64)]
 
     def times(self):
         return {k: float(self.ms[i]) for i, k in enumerate(STAGES)}
