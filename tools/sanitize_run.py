@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """small end-to-end runs of every code path for `compute-sanitizer --tool memcheck python tools/sanitize_run.py`
-(the pytest suite is too slow under the sanitizer): single volume, 3 z-slabs, both back-ends, atlas, isolevel, raw ingest"""
+(the pytest suite is too slow under the sanitizer): single volume, 3 z-slabs, both back-ends, atlas, isolevel, raw ingest, post-smooth"""
 import sys
 from pathlib import Path
 import numpy as np
@@ -35,5 +35,9 @@ d.free()
 raw = (np.clip(vols["blobs"][0], -2, 2) * 1000).astype(np.int16)
 v, t, _ = eng.meshify_raw(raw, 0.2, 0.001, 0.0, [[1, 0, 0, 0], [0, -1, 0, 0], [0, 0, 1, 0]], 0, 1, 1, 0, 0)
 print("raw", len(v), len(t))
+v, t, _ = eng.meshify(vols["gyroid"][0], 0.0, 0, 1, 1, 0, 0)
+s = eng.laplacian_hc(v, t, 3)
+print("post-smooth", len(v), float(np.abs(s - v).max()), flush=True)
+eng.laplacian_hc(np.random.default_rng(0).normal(size=(50, 3)), np.random.default_rng(1).integers(0, 50, size=(120, 3)).astype(np.int32), 2)
 grp.close()
 print("SANITIZE_RUN_DONE")
