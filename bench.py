@@ -110,38 +110,72 @@ def slab_volume(world, n):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock / power / throttle reasons of one GPU sampled DURING the timed region: NVML in-process (nvidia_ml_py;
+    a sample every 20 ms from the first millisecond), `nvidia-smi -lms 100` as the fallback (its start-up alone can
+    outlast a short timed region on an 8-GPU box)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.stop_flag, self.nvml, self.max_mhz = index, [], None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:  # noqa: BLE001
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
     def run(self):
+        if self.nvml:
+            nv, h = self.nvml
+            while not self.stop_flag:
+                try:
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:  # noqa: BLE001
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(mask)))
+                except Exception:  # noqa: BLE001
+                    break
+                time.sleep(0.02)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                c = [x.strip() for x in line.split(",")]
+                if len(c) >= 9:
+                    mask = sum(bit for (name, bit), col in zip(self.REASONS, (8, 5, 7, 6)) if c[col].lower().startswith("active"))
+                    self.max_mhz = float(c[2])
+                    self.rows.append((float(c[1]), float(c[3]), mask))
         except Exception:  # noqa: BLE001
             pass
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 9]
+        self.join(timeout=2.0)
+        rows = list(self.rows)
         if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = set()
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        sm = sorted(r[0] for r in rows)
+        mask = 0
         for r in rows:
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
-                              ("sw_power_cap", 8)):
-                if r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+            mask |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(n for n, bit in self.REASONS if mask & bit),
+                "samples": len(rows), "power_w_max": max(r[1] for r in rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def ref_meshify_time(n, steps, warmup, threads):
