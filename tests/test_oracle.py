@@ -159,3 +159,44 @@ def test_isolevel_restatement_equals_reference(orc, ref_lewiner):
             a, b = orc.set_threshold(vol, mode), ref_lewiner.set_threshold(vol, mode)
             assert a == b or (np.isnan(a) and np.isnan(b)), (name, mode, a, b)
     assert abs(orc.set_threshold(cases.volumes()["bet"][0], 2) - 67.729) < 1e-3
+
+
+# ---- the GPU clean-up's pre-filter as a property of the reference's own output -------------
+def _removed_mask(before, after):
+    """order-preserving compaction (src/meshify.c:147-166): which rows of `before` are missing from `after`"""
+    rem = np.ones(len(before), bool)
+    j = 0
+    for i in range(len(before)):
+        if j < len(after) and np.array_equal(before[i], after[j]):
+            rem[i] = False
+            j += 1
+    assert j == len(after)
+    return rem
+
+
+@pytest.mark.parametrize("name,backend,flags", [
+    ("sphere40", cases.LEWINER, (0, 0, 0, 0)), ("sphere64", cases.LEWINER, (0, 1, 1, 0)), ("blobs", cases.LEWINER, (0, 0, 0, 0)),
+    ("blobs2", cases.LEWINER, (1, 0, 0, 0)), ("bet", cases.LEWINER, (0, 1, 1, 0)), ("gyroid160", cases.LEWINER, (0, 1, 1, 1)),
+    ("sphere40", cases.CLASSIC, (0, 0, 0, 0)), ("blobs", cases.CLASSIC, (0, 1, 1, 1))])
+def test_degenerate_triangles_touch_a_grid_corner(orc, name, backend, flags):
+    """libb2m runs the reference's needle test (src/meshify.c:113-145) only for triangles with a vertex within 1/128 of
+    a grid corner along its cube edge, or a vertex that is not an edge vertex (Lewiner centroid vertices): every triangle
+    the test removes must be such a triangle - and by a wide margin (the closest removed triangle is reported)."""
+    vol, iso = VOLS[name]
+    omc, p, l, b = flags
+    f = orc.front(vol, iso, p, l, b)
+    v, t = orc.mc(f["img"], f["lo"], f["hi"], f["iso"], omc, backend)
+    v2, t2 = orc.weld(v, t)
+    kept = orc.degenerate(v2, t2)
+    rem = _removed_mask(t2, kept)
+    frac = np.abs(v2 - np.rint(v2))                       # distance of every coordinate to the grid
+    on_grid = frac == 0.0
+    edge_vertex = on_grid.sum(axis=1) >= 2                # two integer coordinates: a vertex on a cube edge
+    free = np.where(on_grid, 0.0, frac).max(axis=1)       # its free coordinate's distance to the nearest corner
+    slow = ~edge_vertex | (free < 1.0 / 128)
+    tri_slow = slow[t2].any(axis=1)
+    assert rem.sum() == len(t2) - len(kept)
+    assert not (rem & ~tri_slow).any(), f"{(rem & ~tri_slow).sum()} removed triangles without a near-corner vertex"
+    if rem.any():
+        closest = np.where(edge_vertex[t2], free[t2], 0.0).min(axis=1)[rem].max()
+        assert closest < 1e-3, closest                    # 150x inside the 1/128 band (area >= 0.3 d^2 argument)
