@@ -163,6 +163,8 @@ static int stage_init(b2m_ctx *ctx) {
 #include <sched.h>
 #include <atomic>
 static inline void cpu_relax(void) { asm volatile("pause" ::: "memory"); }
+extern "C" void b2m_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.c
+extern "C" void b2m_stream_widen(double *dst, const float *src, size_t n);
 static int par_threads(void) {
   static int n = 0;
   if (!n) {
@@ -196,8 +198,7 @@ struct copy_pool {
   std::atomic<long long> ready{0};
   std::atomic<int> done[B2M_RING_SLOTS];
 } g_pool;
-extern "C" void b2m_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.c
-extern "C" void b2m_stream_widen(double *dst, const float *src, size_t n);
+
 static void pool_work(copy_pool *p) {
   for (;;) {
     const long long i = p->next.fetch_add(1);

@@ -113,3 +113,29 @@ def test_apply_sform_and_strip_ext(libb2m):
     b = C.create_string_buffer(b"a/b.nii.gz", 64)
     libb2m.strip_ext(b)
     assert b.value == b"a/b.nii"
+
+
+def test_host_copy_kernels(libb2m):
+    """hostcopy.c (the pool threads' non-temporal copy / f32->f64 widening of the D2H leg): every alignment and tail"""
+    libb2m.b2m_stream_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    libb2m.b2m_stream_copy.restype = None
+    libb2m.b2m_stream_widen.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    libb2m.b2m_stream_widen.restype = None
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 256, 70000, dtype=np.uint8)
+    for n in (0, 1, 31, 4095, 4096, 4097, 65536, 69999):
+        for so in (0, 1, 7):
+            for do in (0, 3, 32):
+                if so + n > len(src):
+                    continue
+                dst = np.full(n + 128, 0xAB, np.uint8)
+                libb2m.b2m_stream_copy(dst.ctypes.data + do, src.ctypes.data + so, n)
+                assert np.array_equal(dst[do:do + n], src[so:so + n]) and (dst[:do] == 0xAB).all() and (dst[do + n:] == 0xAB).all()
+    f = rng.standard_normal(5000).astype(np.float32)
+    f[:8] = [0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, 1.17549435e-38]
+    for n in (0, 1, 3, 4, 15, 16, 17, 1000, 4999):
+        for do in (0, 1, 3):
+            dst = np.full(n + 8, 7.0, np.float64)
+            libb2m.b2m_stream_widen(dst.ctypes.data + 8 * do, f.ctypes.data + 4, n)
+            assert np.array_equal(dst[do:do + n].view(np.uint64), f[1:1 + n].astype(np.float64).view(np.uint64))
+            assert (dst[:do] == 7.0).all() and (dst[do + n:] == 7.0).all()
