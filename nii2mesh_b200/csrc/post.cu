@@ -39,12 +39,32 @@ __global__ void __launch_bounds__(PS_THREADS) k_ps_fill(const int *__restrict__ 
 __global__ void __launch_bounds__(PS_THREADS) k_ps_sort(unsigned nv, const uint32_t *__restrict__ start, uint32_t *__restrict__ ref) {
   const unsigned v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nv) return;
-  const uint32_t s = start[v], e = start[v + 1];
-  for (uint32_t a = s + 1; a < e; a++) {
-    const uint32_t key = ref[a];
-    uint32_t b = a;
-    while (b > s && ref[b - 1] > key) { ref[b] = ref[b - 1]; b--; }
-    ref[b] = key;
+  const uint32_t s = start[v], e = start[v + 1], n = e - s;
+  uint32_t *a = ref + s;
+  if (n <= 32u) {  // the usual handful: insertion sort
+    for (uint32_t i = 1; i < n; i++) {
+      const uint32_t key = a[i];
+      uint32_t b = i;
+      while (b > 0 && a[b - 1] > key) { a[b] = a[b - 1]; b--; }
+      a[b] = key;
+    }
+    return;
+  }
+  // a vertex shared by very many triangles (the apex of a fan): heap sort keeps it O(n log n)
+  auto sift = [&](uint32_t root, uint32_t end) {
+    for (;;) {
+      uint32_t c = 2 * root + 1;
+      if (c >= end) return;
+      if (c + 1 < end && a[c] < a[c + 1]) c++;
+      if (a[root] >= a[c]) return;
+      const uint32_t t = a[root]; a[root] = a[c]; a[c] = t;
+      root = c;
+    }
+  };
+  for (uint32_t i = n / 2; i-- > 0;) sift(i, n);
+  for (uint32_t end = n - 1; end > 0; end--) {
+    const uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+    sift(0, end);
   }
 }
 
