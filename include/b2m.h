@@ -76,7 +76,8 @@ void b2m_set_default_backend(int backend); /* used by meshify(); overrides B2M_C
 int b2m_device_count(void);
 
 /* ---- device memory helpers (so that C or ctypes callers need no CUDA bindings) ------------- */
-int b2m_dev_alloc(void **dptr, size_t bytes);
+int b2m_dev_alloc(void **dptr, size_t bytes);  /* on the calling thread's CURRENT device */
+int b2m_ctx_alloc(b2m_ctx *ctx, void **dptr, size_t bytes);  /* on the context's device (processes that drive several GPUs) */
 int b2m_dev_free(void *dptr);
 int b2m_host_alloc(void **hptr, size_t bytes); /* pinned */
 int b2m_host_free(void *hptr);

@@ -449,6 +449,11 @@ extern "C" int b2m_dev_alloc(void **dptr, size_t bytes) {
   }
   return B2M_OK;
 }
+extern "C" int b2m_ctx_alloc(b2m_ctx *ctx, void **dptr, size_t bytes) {
+  if (!ctx) return B2M_EARG;
+  CU_TRY(cudaSetDevice(ctx->device));
+  return b2m_dev_alloc(dptr, bytes);
+}
 extern "C" int b2m_dev_free(void *dptr) {
   CU_TRY(cudaFree(dptr));
   return B2M_OK;

@@ -540,11 +540,14 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
   }
   dim3 grid(tx, ty, b2m_cdiv(onz, zc));
   const bool vec = (g.nx % 4 == 0) && (((uintptr_t)src.main | (uintptr_t)src.lo | (uintptr_t)src.hi | (uintptr_t)d_out) % 16 == 0);
-  static bool attr_done = false;
-  if (!attr_done) {
+  // more than 48 KB of dynamic shared memory: opt in once PER DEVICE (function attributes belong to the device's
+  // context; one process may drive several GPUs - local slab groups, atlas threads)
+  static bool attr_done[64] = {};
+  const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 63;
+  if (!attr_done[dv] || dv == 63) {
     CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
     CU_TRY(cudaFuncSetAttribute(k_smooth3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
-    attr_done = true;
+    attr_done[dv] = true;
   }
   if (vec)
     KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));

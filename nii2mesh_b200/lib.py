@@ -74,6 +74,7 @@ def load():
     L.b2m_set_default_backend.argtypes = [C.c_int]
     L.b2m_set_default_backend.restype = None
     L.b2m_dev_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.b2m_ctx_alloc.argtypes = [vp, C.POINTER(vp), C.c_size_t]
     L.b2m_dev_free.argtypes = [vp]
     L.b2m_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     L.b2m_host_free.argtypes = [vp]
@@ -205,7 +206,7 @@ class Engine:
     # ---- memory ----
     def alloc(self, nbytes):
         p = C.c_void_p()
-        self._chk(self.lib.b2m_dev_alloc(C.byref(p), nbytes))
+        self._chk(self.lib.b2m_ctx_alloc(self.ctx, C.byref(p), nbytes))  # on this engine's device, whatever the thread's current one
         return p
 
     def upload(self, vol):

@@ -21,3 +21,24 @@ def test_slabs_over_nccl(libb2m):
                        env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     sys.stdout.write(p.stdout[-4000:])
     assert p.returncode == 0 and "SLAB_NCCL_RESULT PASS" in p.stdout
+
+
+def test_two_devices_in_one_process(libb2m):
+    """one process driving two GPUs (local slab group over devices 0 and 1, then a plain Engine on device 1): per-device
+    state such as the opt-in to > 48 KB of dynamic shared memory must not be remembered process-wide"""
+    if libb2m.b2m_device_count() < 2:
+        pytest.skip("one GPU on this box")
+    import numpy as np
+    import cases
+    from nii2mesh_b200 import lib
+    vol, iso = cases.volumes(big=False)["gyroid96"]
+    e0 = lib.Engine(0)
+    v0, t0, _ = e0.meshify(vol, iso, 0, 1, 1, 1)
+    e1 = lib.Engine(1)
+    v1, t1, _ = e1.meshify(vol, iso, 0, 1, 1, 1)
+    assert np.array_equal(t0, t1) and np.array_equal(v0.view(np.uint64), v1.view(np.uint64))
+    grp = lib.LocalSlabGroup(2, devices=[0, 1])
+    nz = vol.shape[0]
+    gv, gt, _ = grp.meshify(vol, [0, nz // 2, nz], iso, original_mc=0, pre_smooth=1, only_largest=1, fill_bubbles=1)
+    grp.close()
+    assert np.array_equal(gt, t0) and np.array_equal(gv.view(np.uint64), v0.view(np.uint64))
