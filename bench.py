@@ -178,6 +178,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(rows), "power_w_max": max(r[1] for r in rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip() + f" ({os.cpu_count()} logical cores)"
+    except Exception:  # noqa: BLE001
+        pass
+    return f"unknown ({os.cpu_count()} logical cores)"
+
+
 def ref_meshify_time(n, steps, warmup, threads):
     """time the unmodified reference (oracle/_ref; falls back to the oracle port) on `threads` concurrent
     G<n> volumes per step (meshify() itself is single-threaded; ctypes releases the GIL)"""
@@ -230,7 +240,7 @@ def run_reference(args, rank, emit):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
                                   f"each step = {T} G{n} volumes of the same generator, one per host core (bounded sample)"},
-           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "kind": kind,
+           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "kind": kind, "cpu": cpu_model(),
                             "sample": f"{T} x G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris each; meshify() is "
                                       f"single-threaded, one volume per core"},
            "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -441,7 +451,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         sn, T = 256, host_threads()
         dt, kind, cnv, cnt = ref_meshify_time(sn, 1, 0, T)
-        cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "kind": kind,
+        cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "kind": kind, "cpu": cpu_model(),
                "sample": f"{T} x G{sn} ({sn}^3 voxels, same generator and flags) concurrently, one per host core, "
                          f"{dt:.1f} s, {cnv} verts {cnt} tris each; meshify() itself is single-threaded"}
     # known answer of the G family: the reference's PRE-weld counts are exactly cubic in the number
