@@ -227,6 +227,9 @@ __device__ __noinline__ void mc33_select(const signed char *__restrict__ tab, co
 // Per segment the kernel leaves {xbits, ybits, zbits, packed counts}; packed counts = nv | nt << 7 | nc << 16
 // (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.  Active voxels are appended to a
 // warp-private shared-memory buffer and flushed to the global list with one atomic per ~150 records.
+#ifndef MC_EMIT_EARLY
+#define MC_EMIT_EARLY 0  /* 1: emit looks the edge-vertex ids up before the vertex stores, one record load per (row, segment): parity green on the single-volume suite, 2.10 -> 2.06 ms; off until the slab suites have run with it */
+#endif
 #define MCB_THREADS 128
 #define MCB_ZC 8
 #define MCB_BUF 192
@@ -613,6 +616,64 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     c[2] = c[5] = c[6] = c[7] = c[0];
   }
   const float flo0 = (float)(p.lo0 + p.org0), flo1 = (float)(p.lo1 + p.org1), flo2 = (float)(p.lo2 + p.org2);
+#if MC_EMIT_EARLY
+  // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
+  // Looked up BEFORE the vertex stores below: behind them (and behind the `ntri == 0` exit) the segment-record loads
+  // started only after the corner values had arrived and the vertices were written - a third dependent round trip
+  // through L2 per thread.  One record load serves every edge that shares a (row, segment): <= 4 loads instead of 12.
+  uint32_t ev[13];
+  const unsigned lut = r.w;  // inside bits of the corners = the cube index the classify pass built from the inside-bit rows
+  const bool in0 = lut & 1u, in1 = (lut >> 1) & 1u, in2 = (lut >> 2) & 1u, in3 = (lut >> 3) & 1u;
+  const bool in4 = (lut >> 4) & 1u, in5 = (lut >> 5) & 1u, in6 = (lut >> 6) & 1u, in7 = (lut >> 7) & 1u;
+  if (ntri) {
+    const bool c0 = in0 != in1, c1 = in1 != in2, c2 = in3 != in2, c3 = in0 != in3, c4 = in4 != in5, c5 = in5 != in6;
+    const bool c6 = in7 != in6, c7 = in4 != in7, c8 = in0 != in4, c9 = in1 != in5, c10 = in2 != in6, c11 = in3 != in7;
+    if (((x + 1) & 31) != 0) {  // x and x+1 share their segment (31 voxels of 32): four record loads at most
+      const uint4 none = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 *sA = p.segbits + row * p.segs + (x >> 5), *sB = sA + p.segs, *sC = sA + (size_t)p.sy * p.segs, *sD = sC + p.segs;
+      const uint4 A = (c0 | c3 | c8 | c1 | c9) ? __ldg(sA) : none;
+      const uint4 B = (c2 | c11 | c10) ? __ldg(sB) : none;
+      const uint4 Cr = (c4 | c7 | c5) ? __ldg(sC) : none;
+      const uint4 D = c6 ? __ldg(sD) : none;
+      // mc_vidx on a record already loaded: vertices before voxel xx in the segment, + the x (+ y) vertex of xx itself
+      const unsigned l0 = x & 31, m0 = (1u << l0) - 1u, l1 = l0 + 1, m1 = (1u << l1) - 1u;
+      const uint32_t a0 = A.w + __popc(A.x & m0) + __popc(A.y & m0) + __popc(A.z & m0);
+      const uint32_t a1 = A.w + __popc(A.x & m1) + __popc(A.y & m1) + __popc(A.z & m1);
+      const uint32_t b0 = B.w + __popc(B.x & m0) + __popc(B.y & m0) + __popc(B.z & m0);
+      const uint32_t b1 = B.w + __popc(B.x & m1) + __popc(B.y & m1) + __popc(B.z & m1);
+      const uint32_t q0 = Cr.w + __popc(Cr.x & m0) + __popc(Cr.y & m0) + __popc(Cr.z & m0);
+      const uint32_t q1 = Cr.w + __popc(Cr.x & m1) + __popc(Cr.y & m1) + __popc(Cr.z & m1);
+      const uint32_t d0 = D.w + __popc(D.x & m0) + __popc(D.y & m0) + __popc(D.z & m0);
+      ev[0] = c0 ? a0 : 0xffffffffu;
+      ev[1] = c1 ? a1 + ((A.x >> l1) & 1u) : 0xffffffffu;
+      ev[2] = c2 ? b0 : 0xffffffffu;
+      ev[3] = c3 ? a0 + ((A.x >> l0) & 1u) : 0xffffffffu;
+      ev[4] = c4 ? q0 : 0xffffffffu;
+      ev[5] = c5 ? q1 + ((Cr.x >> l1) & 1u) : 0xffffffffu;
+      ev[6] = c6 ? d0 : 0xffffffffu;
+      ev[7] = c7 ? q0 + ((Cr.x >> l0) & 1u) : 0xffffffffu;
+      ev[8] = c8 ? a0 + ((A.x >> l0) & 1u) + ((A.y >> l0) & 1u) : 0xffffffffu;
+      ev[9] = c9 ? a1 + ((A.x >> l1) & 1u) + ((A.y >> l1) & 1u) : 0xffffffffu;
+      ev[10] = c10 ? b1 + ((B.x >> l1) & 1u) + ((B.y >> l1) & 1u) : 0xffffffffu;
+      ev[11] = c11 ? b0 + ((B.x >> l0) & 1u) + ((B.y >> l0) & 1u) : 0xffffffffu;
+    } else {  // x+1 opens the next segment of its row: one lookup per edge
+      const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
+      ev[0] = c0 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
+      ev[1] = c1 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
+      ev[2] = c2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
+      ev[3] = c3 ? mc_vidx(p, row, x, 1) : 0xffffffffu;
+      ev[4] = c4 ? mc_vidx(p, rowZ, x, 0) : 0xffffffffu;
+      ev[5] = c5 ? mc_vidx(p, rowZ, x + 1, 1) : 0xffffffffu;
+      ev[6] = c6 ? mc_vidx(p, rowYZ, x, 0) : 0xffffffffu;
+      ev[7] = c7 ? mc_vidx(p, rowZ, x, 1) : 0xffffffffu;
+      ev[8] = c8 ? mc_vidx(p, row, x, 2) : 0xffffffffu;
+      ev[9] = c9 ? mc_vidx(p, row, x + 1, 2) : 0xffffffffu;
+      ev[10] = c10 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
+      ev[11] = c11 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
+    }
+    ev[12] = 0xffffffffu;
+  }
+#endif
   // ---- own edge vertices ----
   if (ex | ey | ez) {
     uint32_t vid = __ldg(&p.segbits[sidx].w) + (uint32_t)pv;
@@ -686,6 +747,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     }
   }
   if (!ntri) return;
+#if !MC_EMIT_EARLY
   // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
   const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
   uint32_t ev[13];
@@ -706,6 +768,7 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
   ev[10] = in2 != in6 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
   ev[11] = in3 != in7 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
   ev[12] = 0xffffffffu;
+#endif
   if (hasc) {
     // centroid of the cube's existing edge vertices, summed in edge-code order in f32 local
     // coordinates, divided by the f32 count (src/MarchingCubes.c:1042-1071); then + lo in f32.
