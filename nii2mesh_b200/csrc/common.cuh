@@ -147,6 +147,7 @@ struct b2m_ktimer {
   cudaEvent_t e0, e1;
 };
 
+#define B2M_PEND_MAX 16
 #define B2M_RING_CHUNK ((size_t)8 << 20)   /* streamed D2H: DMA granule */
 #define B2M_RING_SLOTS 12                  /* = 3 * B2M_STAGE_BYTES / B2M_RING_CHUNK */
 struct b2m_ctx {
@@ -173,6 +174,12 @@ struct b2m_ctx {
   void *stage[3];          // pinned ring buffers (B2M_STAGE_BYTES each), allocated on first use
   cudaEvent_t stage_ev[3];
   cudaEvent_t ring_ev[B2M_RING_SLOTS];  // streamed D2H: the three buffers seen as B2M_RING_SLOTS sub-chunks
+  // H2D overlapped with the smooth (B2M_H2D_OVERLAP=1, experimental): the volume arrives in z-chunks on copy_stream;
+  // pend_zend[k] raw planes are on the device once pend_ev[k] has fired.  Consumed (and cleared) by b2m_front_run
+  cudaStream_t copy_stream;
+  cudaEvent_t pend_ev[B2M_PEND_MAX + 1];  // [B2M_PEND_MAX] = start of the transfer
+  int pend_zend[B2M_PEND_MAX];
+  int pend_n, pend_last;   // chunks not yet consumed / index of the last chunk of the transfer
   int profile;             // record an event pair around every kernel launch
   int nkt, nkt_events;     // entries used in this call / event pairs created so far
   b2m_ktimer kt[B2M_KT_MAX];
@@ -199,6 +206,10 @@ int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
 #define B2M_STAGE_BYTES ((size_t)32 << 20)
 int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+bool b2m_host_is_pinned(const void *p);
+// start an asynchronous z-chunked H2D of a pinned volume; b2m_front_run waits chunk by chunk (ctx->pend_*)
+int b2m_h2d_chunked_begin(b2m_ctx *ctx, float *d_dst, const float *h_src, size_t nxy, int nz);
+int b2m_h2d_chunked_ms(b2m_ctx *ctx, float *ms);  // duration of the transfer started by the call above
 int b2m_copy_d2h_f32exact(b2m_ctx *ctx, double *h_dst, const double *d_src, size_t n, int *done);  // doubles that are all f32 values: 4 B each over PCIe
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb);
 void b2m_touch_wait(void);

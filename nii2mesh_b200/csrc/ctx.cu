@@ -67,6 +67,12 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
     if (c->stage[i]) { cudaFreeHost(c->stage[i]); cudaEventDestroy(c->stage_ev[i]); }
   for (int i = 0; i < B2M_RING_SLOTS; i++)
     if (c->ring_ev[i]) cudaEventDestroy(c->ring_ev[i]);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i <= B2M_PEND_MAX; i++)
+      if (c->pend_ev[i]) cudaEventDestroy(c->pend_ev[i]);
+    cudaStreamDestroy(c->copy_stream);
+  }
   cudaFreeHost(c->h_scalars);
   if (c->h_all) { cudaFreeHost(c->h_all); cudaFree(c->d_all); }
   cudaStreamDestroy(c->stream);
@@ -409,6 +415,40 @@ int b2m_copy_d2h_f32exact(b2m_ctx *ctx, double *h_dst, const double *d_src, size
   if (h) return B2M_OK;
   B2M_TRY(b2m_copy_d2h_widen(ctx, h_dst, tmp, n));
   *done = 1;
+  return B2M_OK;
+}
+
+bool b2m_host_is_pinned(const void *p) { return host_is_pinned(p); }
+
+// Experimental (B2M_H2D_OVERLAP=1): the pinned volume goes up in <= B2M_PEND_MAX z-chunks on a second stream, one event
+// per chunk, so that the smooth of the planes that have arrived runs under the rest of the transfer.
+int b2m_h2d_chunked_begin(b2m_ctx *ctx, float *d_dst, const float *h_src, size_t nxy, int nz) {
+  if (!ctx->copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i <= B2M_PEND_MAX; i++) CU_TRY(cudaEventCreate(&ctx->pend_ev[i]));
+  }
+  int k = (int)(((size_t)nz * nxy * 4 + ((size_t)512 << 20) - 1) / ((size_t)512 << 20));  // ~512 MiB per chunk
+  if (k < 2) k = 2;
+  if (k > B2M_PEND_MAX) k = B2M_PEND_MAX;
+  if (k > nz / 8) k = nz / 8 > 0 ? nz / 8 : 1;
+  CU_TRY(cudaEventRecord(ctx->pend_ev[B2M_PEND_MAX], ctx->copy_stream));
+  int z = 0;
+  for (int i = 0; i < k; i++) {
+    const int z1 = (int)(((long long)nz * (i + 1)) / k);
+    CU_TRY(cudaMemcpyAsync(d_dst + (size_t)z * nxy, h_src + (size_t)z * nxy, (size_t)(z1 - z) * nxy * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU_TRY(cudaEventRecord(ctx->pend_ev[i], ctx->copy_stream));
+    ctx->pend_zend[i] = z1;
+    z = z1;
+  }
+  ctx->pend_n = k;
+  ctx->pend_last = k - 1;
+  return B2M_OK;
+}
+int b2m_h2d_chunked_ms(b2m_ctx *ctx, float *ms) {
+  *ms = 0.f;
+  if (!ctx->copy_stream) return B2M_OK;
+  CU_TRY(cudaEventSynchronize(ctx->pend_ev[ctx->pend_last]));
+  CU_TRY(cudaEventElapsedTime(ms, ctx->pend_ev[B2M_PEND_MAX], ctx->pend_ev[ctx->pend_last]));
   return B2M_OK;
 }
 

@@ -103,10 +103,31 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
                                 d_img, sl.hl ? 3 * nxy * 4 : 0, hhi, nh * nxy * 4));
       src.lo = hlo; src.n_lo = nl; src.hi = hhi; src.n_hi = nh; src.rz0 = sl.z0 - nl;
     }
-    B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));  // range reduction fused (halo planes are other ranks' planes: harmless)
+    if (!slabs && ctx->pend_n > 0) {
+      // the volume is still arriving in z-chunks (b2m_h2d_chunked_begin): smooth the output planes whose raw planes
+      // (z-2 .. z+2) are on the device, chunk by chunk, under the rest of the transfer
+      int zdone = 0;
+      for (int k = 0; k < ctx->pend_n; k++) {
+        CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->pend_ev[k], 0));
+        const int avail = ctx->pend_zend[k];
+        const int zend = avail >= sl.gnz ? sl.gnz : avail - 2;
+        if (zend > zdone) {
+          src.oz0 = zdone; src.onz = zend - zdone;
+          B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)zdone * nxy, g, d_sc));
+          zdone = zend;
+        }
+      }
+      ctx->pend_n = 0;
+    } else {
+      B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));  // range reduction fused (halo planes are other ranks' planes: harmless)
+    }
     fo->S = S;
     B2M_TRY(stage_end(ctx, B2M_T_SMOOTH));
   } else {
+    if (ctx->pend_n > 0) {  // no smooth to overlap with: wait for the whole volume
+      CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->pend_ev[ctx->pend_n - 1], 0));
+      ctx->pend_n = 0;
+    }
     B2M_TRY(stage_begin(ctx, B2M_T_RANGE));
     if (!slabs) {
       fo->S = d_img;
@@ -376,16 +397,25 @@ extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t 
   memset(&ho, 0, sizeof(ho));
   host_out_early(ctx, &ho, n);
   const double t0 = wall_ms();
-  int rc = b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_img, n * 4);
+  // experimental: B2M_H2D_OVERLAP=1 sends a pinned volume up in z-chunks on a second stream and lets the smooth follow it
+  static const bool want_overlap = getenv("B2M_H2D_OVERLAP") && atoi(getenv("B2M_H2D_OVERLAP")) > 0;
+  const bool overlap = want_overlap && opts->pre_smooth && dims[0] >= 5 && dims[1] >= 5 && dims[2] >= 64 && b2m_host_is_pinned(h_img);
+  int rc = overlap ? b2m_h2d_chunked_begin(ctx, b2m_ptr<float>(ctx, BUF_INPUT), h_img, (size_t)dims[0] * dims[1], (int)dims[2])
+                   : b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_img, n * 4);
   const double t1 = wall_ms();
   ctx->counts_hook = host_out_hook;
   ctx->hook_user = &ho;
   if (rc == B2M_OK) rc = b2m_meshify_device(ctx, b2m_ptr<float>(ctx, BUF_INPUT), dims, opts, res);
+  if (overlap) {  // whatever happened, the transfer must have drained before the buffers are reused
+    ctx->pend_n = 0;
+    cudaStreamSynchronize(ctx->copy_stream);
+  }
   const double t2 = wall_ms();
   host_out_remember(ctx, &ho, n);
   rc = host_out_finish(ctx, &ho, rc, res->d_verts, (size_t)res->nverts, res->d_tris, (size_t)res->ntris, verts, tris);
   if (rc != B2M_OK) return rc;
   res->h2d_ms = (float)(t1 - t0);
+  if (overlap) b2m_h2d_chunked_ms(ctx, &res->h2d_ms);  // the transfer's own duration; ms[] (device) includes waiting for it
   res->d2h_ms = (float)(wall_ms() - t2);
   res->d2h_bytes = ho.pcie_bytes;
   if (opts->verbose) printf("host copies: H2D %.1f ms, D2H %.1f ms\n", res->h2d_ms, res->d2h_ms);
