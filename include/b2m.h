@@ -85,6 +85,13 @@ int b2m_h2d(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
 int b2m_d2h(b2m_ctx *ctx, void *dst, const void *src, size_t bytes);
 int b2m_sync(b2m_ctx *ctx);
 int b2m_flush_l2(b2m_ctx *ctx); /* writes a 256 MiB scratch buffer (benchmark hygiene) */
+/* Host threads of the copy pool that moves pageable host memory to / from the pinned staging buffers (the caller
+ * included).  Default: B2M_COPY_THREADS, else (cores the process may run on) / LOCAL_WORLD_SIZE (as exported by torchrun:
+ * the ranks that share this node share its cores), at most 16.  b2m_set_copy_threads(n) must precede the first bulk copy
+ * of the process (returns B2M_FAIL afterwards); n = 0 restores the default rule. */
+int b2m_set_copy_threads(int n);
+int b2m_get_copy_threads(void);
+int b2m_pool_selftest(size_t bytes, int callers); /* the pool alone, no GPU: concurrent callers with a barrier between them */
 /* d_out[z][y][x] = d_tile[(z+z_offset) % tz][y % ty][x % tx]: periodic replication of a small device
  * tile into a (slab of a) large volume without a host copy (synthetic G1024 / G2048 inputs). */
 int b2m_tile_volume(b2m_ctx *ctx, const float *d_tile, const int64_t tile_dims[3], float *d_out,

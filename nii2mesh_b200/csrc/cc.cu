@@ -28,7 +28,28 @@ struct cc_geom {
   long long nwords;
   int zface_lo, zface_hi;  // plane 0 / plane nz-1 of the labelled region is a face of the whole volume (slabs)
 };
-#define CC_SENT 0xffffffffu /* slabs: parent of a seam root that belongs to the selected (largest) component */
+// Run slots stay below 2^31 (a slab holds at most 2^27 bit words = 2^32 voxels), so a parent field with bit 31 set is
+// never a slot: it marks a seam root (slabs) - transiently CC_TAG | ticket while the seams are being resolved, and
+// CC_SENT once the root is known to belong to the selected (largest) component.
+#define CC_TAG 0x80000000u
+#define CC_PENDING 0xfffffffeu /* a thread is turning this root into a seam root */
+#define CC_SENT 0xffffffffu
+// A node's second word is (voxel count << 1) | face flag, the count modulo 2^31; wraps are recorded in the carry table of
+// the scalar block (components of >= 2^31 voxels: at most two per slab).
+__device__ __forceinline__ void cc_carry_add(b2m_scalars *sc, uint32_t root) {
+  for (int i = 0; i < 4; i++) {
+    const unsigned old = atomicCAS(&sc->carry_slot[i], 0u, root + 1u);
+    if (old == 0u || old == root + 1u) { atomicAdd(&sc->carry_hi[i], 1u); return; }
+  }
+  atomicOr(&sc->overflow, 32u);
+}
+__device__ __forceinline__ unsigned long long cc_count(const b2m_scalars *sc, uint32_t root, uint32_t y) {
+  unsigned long long c = y >> 1;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    if (__ldcg(&sc->carry_slot[i]) == root + 1u) c += (unsigned long long)__ldcg(&sc->carry_hi[i]) << 31;
+  return c;
+}
 
 // Union-find nodes.  A run's slot id is  word*16 + (ordinal of the run inside its word)  - ordered like the
 // raster order of the runs' first voxels - but the nodes are STORED with every word's first run in a dense
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     uint32_t stat = 0;
     if (r == me) {
       const uint32_t pe = par[me];
-      stat = (pe & 0x7fffu) | ((pe & 0x8000u) << 16);
+      stat = ((pe & 0x7fffu) << 1) | ((pe >> 15) & 1u);
       const unsigned li = atomicAdd(&s_n, 1u);
       if (li < CT_LIST) s_list[li] = gparent;
       else {  // more tile roots than the staging list holds (noise): straight to the global list
@@ -341,21 +362,24 @@ __global__ void __launch_bounds__(CT_WORDS, 1536 / CT_WORDS) k_cc_border(const u
   }
 }
 
-__device__ __forceinline__ void flush_stats(const cc_nodes &nodes, uint32_t root, uint32_t cnt, uint32_t flag) {
+__device__ __forceinline__ void flush_stats(const cc_nodes &nodes, b2m_scalars *sc, uint32_t root, uint32_t cnt, uint32_t flag) {
   // warp-aggregated: lanes holding the same root combine before touching memory
   unsigned peers = __match_any_sync(__activemask(), root);
   uint32_t tot = __reduce_add_sync(peers, cnt);
   uint32_t fl = __reduce_or_sync(peers, flag);
   if ((unsigned)(__ffs(peers) - 1) == (threadIdx.x & 31u) && root != 0xffffffffu) {
-    if (tot) atomicAdd(&nodes[root].y, tot);
-    if (fl) atomicOr(&nodes[root].y, 0x80000000u);
+    if (tot) {
+      const uint32_t old = atomicAdd(&nodes[root].y, tot << 1);
+      if ((old >> 1) + tot >= 0x80000000u) cc_carry_add(sc, root);  // the 31-bit count wrapped
+    }
+    if (fl) atomicOr(&nodes[root].y, 1u);
   }
 }
 
 // every tile root that lost its root status in k_cc_border hands the count / face flag of its local
 // component to its final root and is pointed straight at it (runs then reach the final root in two hops).
 __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
-                                                    const uint32_t *__restrict__ rlist, unsigned rcap) {
+                                                    const uint32_t *__restrict__ rlist, unsigned rcap, b2m_scalars *sc) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long nround = (g.nwords + 31) / 32 * 32;  // whole warps iterate together
@@ -370,20 +394,20 @@ __global__ void __launch_bounds__(256) k_cc_flatten(const uint32_t *__restrict__
       starts &= starts - 1;
       const uint32_t slot = run_slot((uint32_t)word, wv, s);
       const uint2 nd = nodes[slot];
-      if ((nd.y & 0x7fffffffu) && nd.x != slot) {  // a tile root (it owns a count) that is no longer a root
+      if ((nd.y >> 1) && nd.x != slot) {  // a tile root (it owns a count) that is no longer a root
         root = uf_find(nodes, slot);
         atomicMin(&nodes[slot].x, root);
-        cnt = nd.y & 0x7fffffffu;
-        flag = nd.y >> 31;
+        cnt = nd.y >> 1;
+        flag = nd.y & 1u;
       }
     }
-    if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
+    if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, sc, root, cnt, flag);
   }
   }
 }
 
 // list variants: one thread per tile root (k_cc_local's list); they do nothing when the list overflowed
-__global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restrict__ rlist, unsigned rcap, cc_nodes nodes) {
+__global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restrict__ rlist, unsigned rcap, cc_nodes nodes, b2m_scalars *sc) {
   const unsigned n = rlist[0];
   if (n > rcap) return;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -394,14 +418,18 @@ __global__ void __launch_bounds__(256) k_cc_flatten_list(const uint32_t *__restr
     if (nd.x != slot) {
       root = uf_find(nodes, slot);
       atomicMin(&nodes[slot].x, root);
-      cnt = nd.y & 0x7fffffffu;
-      flag = nd.y >> 31;
+      cnt = nd.y >> 1;
+      flag = nd.y & 1u;
     }
   }
-  if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, root, cnt, flag);
+  if (__any_sync(0xffffffffu, root != 0xffffffffu)) flush_stats(nodes, sc, root, cnt, flag);
+}
+// key of a component = (voxels << 31) | (2^31-1 - root slot): the largest wins, among equals the smallest slot
+__device__ __forceinline__ unsigned long long cc_best_key(const b2m_scalars *sc, uint32_t slot, uint32_t y) {
+  return (cc_count(sc, slot, y) << 31) | (unsigned long long)(0x7fffffffu - slot);
 }
 __global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict__ rlist, unsigned rcap, cc_nodes nodes,
-                                                      unsigned long long *best, unsigned int *nroots) {
+                                                      unsigned long long *best, unsigned int *nroots, const b2m_scalars *sc) {
   const unsigned n = rlist[0];
   if (n > rcap) return;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,7 +440,7 @@ __global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict
     const uint2 nd = nodes[slot];
     if (nd.x == slot) {
       cnt = 1;
-      key = ((unsigned long long)(nd.y & 0x7fffffffu) << 32) | (unsigned long long)(0xffffffffu - slot);
+      key = cc_best_key(sc, slot, nd.y);
     }
   }
 #pragma unroll
@@ -431,18 +459,19 @@ __global__ void __launch_bounds__(256) k_cc_best_list(const uint32_t *__restrict
 __device__ __forceinline__ uint32_t cc_final_root(const cc_nodes &nodes, uint32_t slot) {
   uint32_t p = nodes[slot].x;
   while (p != slot) {
-    if (p == CC_SENT) return CC_SENT;
+    if (p & CC_TAG) return p;  // a seam root: its ticket, CC_PENDING or CC_SENT
     slot = p;
     p = nodes[slot].x;
   }
   return slot;
 }
 
-// number of components and the largest one: key = (size << 32) | ~rootslot, so that among equal
+// number of components and the largest one: key = (size << 31) | (2^31-1 - rootslot), so that among equal
 // sizes the smallest slot (earliest first voxel in raster order) wins, as src/bwlabel.c:462-466.
 __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bits, long long nwords,
                                                  cc_nodes nodes, unsigned long long *best,
-                                                 unsigned int *nroots, const uint32_t *__restrict__ rlist, unsigned rcap) {
+                                                 unsigned int *nroots, const uint32_t *__restrict__ rlist, unsigned rcap,
+                                                 const b2m_scalars *sc) {
   if (rlist[0] <= rcap) return;  // the list variant does the work
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned long long key = 0;
@@ -457,7 +486,7 @@ __global__ void __launch_bounds__(256) k_cc_best(const uint32_t *__restrict__ bi
     uint2 nd = nodes[slot];
     if (nd.x == slot) {
       cnt++;
-      unsigned long long k = ((unsigned long long)(nd.y & 0x7fffffffu) << 32) | (unsigned long long)(0xffffffffu - slot);
+      unsigned long long k = cc_best_key(sc, slot, nd.y);
       key = k > key ? k : key;
     }
   }
@@ -493,7 +522,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
   if (mode == 0) {
     uint32_t bestslot;
     bool have;
-    if (sel == -2) { bestslot = 0xffffffffu - (uint32_t)(*best & 0xffffffffull); have = *best != 0ull; }
+    if (sel == -2) { bestslot = 0x7fffffffu - (uint32_t)(*best & 0x7fffffffull); have = *best != 0ull; }
     else { bestslot = sel >= 0 ? (uint32_t)sel : 0xfffffffeu; have = true; }
     uint32_t rest = wv;
     while (rest && have) {
@@ -514,7 +543,7 @@ __global__ void __launch_bounds__(256) k_cc_select(const uint32_t *__restrict__ 
         uint32_t rm = bits_range(s, e);
         rest &= ~rm;
         uint32_t root = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
-        if (!(nodes[root].y >> 31)) res |= rm;
+        if (!(nodes[root].y & 1u)) res |= rm;
       }
     }
   }
@@ -675,13 +704,14 @@ static unsigned cc_list_cap(const cc_geom &cg) {
 
 // labelling + number of components (*nroots) + largest component (*best, optional)
 static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_nodes nodes, int conn, unsigned long long *best,
-                    unsigned int *nroots) {
+                    unsigned int *nroots, b2m_scalars *d_sc) {
   unsigned blocks = b2m_cdiv(cg.nwords, 256);
   dim3 tiles(b2m_cdiv(cg.w, CT_W), b2m_cdiv(cg.ny, CT_Y), b2m_cdiv(cg.nz, CT_Z));
   const unsigned rcap = cc_list_cap(cg);
   B2M_TRY(b2m_reserve(ctx, BUF_CCLIST, ((size_t)rcap + 1) * 4));
   uint32_t *rlist = b2m_ptr<uint32_t>(ctx, BUF_CCLIST);
   CU_TRY(cudaMemsetAsync(rlist, 0, 4, ctx->stream));
+  CU_TRY(cudaMemsetAsync(d_sc->carry_slot, 0, 32, ctx->stream));  // carry_slot[4] + carry_hi[4]
   if (conn >= 18) {
     KT_LAUNCH(ctx, "cc_local", k_cc_local<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
     KT_LAUNCH(ctx, "cc_border", k_cc_border<18><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
@@ -690,11 +720,11 @@ static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_no
     KT_LAUNCH(ctx, "cc_border", k_cc_border<6><<<tiles, CT_WORDS, 0, ctx->stream>>>(bits, cg, nodes));
   }
   const unsigned lblocks = rcap ? b2m_cdiv(rcap, 256) : 1u;
-  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes));
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes, d_sc));
   const unsigned sblocks = min(blocks, (unsigned)ctx->sm_count * 8u);  // grid-stride: these exit at once in the common case
-  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<sblocks, 256, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap));
-  KT_LAUNCH(ctx, "cc_best", k_cc_best_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes, best, nroots));
-  KT_LAUNCH(ctx, "cc_best", k_cc_best<<<sblocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes, best, nroots, rlist, rcap));
+  KT_LAUNCH(ctx, "cc_flatten", k_cc_flatten<<<sblocks, 256, 0, ctx->stream>>>(bits, cg, nodes, rlist, rcap, d_sc));
+  KT_LAUNCH(ctx, "cc_best", k_cc_best_list<<<lblocks, 256, 0, ctx->stream>>>(rlist, rcap, nodes, best, nroots, d_sc));
+  KT_LAUNCH(ctx, "cc_best", k_cc_best<<<sblocks, 256, 0, ctx->stream>>>(bits, cg.nwords, nodes, best, nroots, rlist, rcap, d_sc));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }
@@ -702,13 +732,283 @@ static int cc_label(b2m_ctx *ctx, const uint32_t *bits, const cc_geom &cg, cc_no
 // ================================================================================================
 // Slabs: merging the components of neighbouring z-slabs.
 // Every rank labels its own planes with local run slots.  The local roots that reach a seam plane
-// ("seam roots") get compact ids (rank offset + index in the rank's sorted unique list); the upper
-// rank of every seam lists the adjacent (lower root, upper root) pairs, the de-duplicated pair lists
-// and the per-root (slot, count|face flag) entries of all ranks are all-gathered, and every rank
-// resolves the same small union-find (union by minimum id = earliest first voxel in raster order,
-// because ids are ordered by (rank, slot)).  Global sizes / face flags come back into the local
-// forest through the seam roots only; everything else stays slab-local.
+// ("seam roots") get compact ids, the upper rank of every seam lists the adjacent (lower root, upper root)
+// pairs, pairs and per-root (slot, size, face flag) entries of all ranks are all-gathered, and every rank
+// resolves the same small union-find.  Global sizes / face flags come back into the local forest through
+// the seam roots only; everything else stays slab-local.
+//
+// FAST path (default): no sort, no host round trip until the resolution is complete.
+//   k_seam_tag       every root that reaches a boundary plane takes a ticket (first come) and is TAGGED: its parent
+//                    field becomes CC_TAG | ticket, so the runs of its component resolve to the ticket in O(1);
+//                    its entry {slot, flag, size} goes into this rank's block
+//   k_seam_dense     tickets of the runs of the last own plane -> dense plane, sent to the rank above
+//   k_seam_pairs_f   upper rank: (ticket below, own ticket) pairs, de-duplicated per thread and per CTA
+//   all-gather       ONE fixed-size block per rank {header, entries[ent_cap], pairs[pair_cap]}; ids are
+//                    rank * ent_cap + ticket, so no offsets have to be agreed on
+//   k_seamf_*        replicated union-find over all tickets; component size / face flag / first voxel
+//                    (min (rank, slot) = earliest voxel in raster order: src/bwlabel.c:462-466's tie-break)
+//   one host sync    sizes, component counts, overflow flags; then k_seamf_apply untags the roots (bubbles: + the
+//                    global face flag; largest: CC_SENT on the roots of the winning component)
+// A rank whose tickets or pairs exceed the block capacity (noise volumes) raises `overflow`; every rank sees it in
+// the gathered headers, all untag and take the SLOW path: sorted unique root lists, variable-length all-gathers
+// (the round-1 design, five host round trips).  B2M_SEAM_SLOW=1 forces it, B2M_SEAM_ENT_CAP / _PAIR_CAP shrink the
+// block (tests).
 // ================================================================================================
+struct seam_ent {
+  uint32_t slot;            // local root slot (0xffffffff: unused ticket)
+  uint32_t flag;            // the local component touches a face of the volume
+  unsigned long long cnt;   // its voxels
+};
+struct seam_hdr {
+  unsigned int m, npairs, overflow, pad[13];
+};
+static_assert(sizeof(seam_hdr) == 64 && sizeof(seam_ent) == 16, "seam block layout");
+struct seam_blk {  // view of one rank's block
+  seam_hdr *hdr;
+  seam_ent *ent;
+  uint64_t *pairs;
+};
+__host__ __device__ static inline size_t seam_blk_bytes(unsigned ent_cap, unsigned pair_cap) {
+  return sizeof(seam_hdr) + (size_t)ent_cap * sizeof(seam_ent) + (size_t)pair_cap * 8;
+}
+__host__ __device__ static inline seam_blk seam_blk_at(char *base, int rank, unsigned ent_cap, unsigned pair_cap) {
+  char *p = base + (size_t)rank * seam_blk_bytes(ent_cap, pair_cap);
+  seam_blk b;
+  b.hdr = reinterpret_cast<seam_hdr *>(p);
+  b.ent = reinterpret_cast<seam_ent *>(p + sizeof(seam_hdr));
+  b.pairs = reinterpret_cast<uint64_t *>(p + sizeof(seam_hdr) + (size_t)ent_cap * sizeof(seam_ent));
+  return b;
+}
+
+__global__ void __launch_bounds__(256) k_seam_tag(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes, int do_first, int do_last,
+                                                  seam_blk blk, unsigned ent_cap, const b2m_scalars *sc) {
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const int which = blockIdx.y;
+  if (which == 0 ? !do_first : (!do_last || (g.nz == 1 && do_first))) return;
+  const long long word = (which == 0 ? 0 : (long long)(g.nz - 1) * pw) + t;
+  const uint32_t wv = __ldg(bits + word);
+  uint32_t starts = wv & ~(wv << 1);
+  while (starts) {
+    const int s = __ffs(starts) - 1;
+    starts &= starts - 1;
+    const uint32_t r = cc_final_root(nodes, run_slot((uint32_t)word, wv, s));
+    if (r & CC_TAG) continue;  // tagged already, or another thread is at it
+    if (atomicCAS(&nodes[r].x, r, CC_PENDING) != r) continue;
+    const unsigned tk = atomicAdd(&blk.hdr->m, 1u);
+    if (tk < ent_cap) {
+      const uint32_t y = nodes[r].y;
+      seam_ent e;
+      e.slot = r; e.flag = y & 1u; e.cnt = cc_count(sc, r, y);
+      blk.ent[tk] = e;
+      __threadfence();
+      atomicExch(&nodes[r].x, CC_TAG | tk);
+    } else {
+      atomicExch(&nodes[r].x, r);
+      atomicOr(&blk.hdr->overflow, 1u);
+    }
+  }
+}
+// ticket of the (tagged) root of a run; 0xffffffff when the root carries no ticket (capacity overflow)
+__device__ __forceinline__ uint32_t seam_ticket(const cc_nodes &nodes, uint32_t slot) {
+  const uint32_t r = cc_final_root(nodes, slot);
+  return ((r & CC_TAG) && r < CC_PENDING) ? (r & ~CC_TAG) : 0xffffffffu;
+}
+__global__ void __launch_bounds__(256) k_seam_dense_f(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes, uint32_t *__restrict__ dense) {
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const long long word = (long long)(g.nz - 1) * pw + t;
+  const uint32_t wv = __ldg(bits + word);
+  uint32_t starts = wv & ~(wv << 1);
+  while (starts) {
+    const int s = __ffs(starts) - 1;
+    starts &= starts - 1;
+    dense[(size_t)t * 16 + (s >> 1)] = seam_ticket(nodes, run_slot((uint32_t)word, wv, s));
+  }
+}
+// neighbour runs of run [s,e] (mask rm) of word (xw, y) in the plane `below`: face + (18-connectivity) the four edge
+// neighbours of that plane; emit(neighbour word x, neighbour row, start bit of the neighbour run)
+template <int CONN, class Emit>
+__device__ __forceinline__ void seam_visit_below(const uint32_t *__restrict__ below, const cc_geom &g, int xw, int y, uint32_t rm, int s, int e,
+                                                 Emit emit) {
+  auto row = [&](int dy, bool wide) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= g.ny) return;
+    const uint32_t *r = below + (size_t)yy * g.w;
+    const uint32_t nw = __ldg(r + xw);
+    uint32_t msk = rm;
+    if (wide) msk |= (rm << 1) | (rm >> 1);
+    uint32_t tt = nw & msk;
+    while (tt) {
+      const int b = __ffs(tt) - 1;
+      const int st = run_start(nw, b);
+      const int en = run_end(nw, st);
+      emit(xw, yy, st);
+      tt &= ~bits_range(st, en);
+    }
+    if (wide) {
+      if (s == 0 && xw > 0) {
+        const uint32_t pv = __ldg(r + xw - 1);
+        if (pv >> 31) emit(xw - 1, yy, run_start(pv, 31));
+      }
+      if (e == 31 && xw + 1 < g.w) {
+        const uint32_t nv = __ldg(r + xw + 1);
+        if (nv & 1u) emit(xw + 1, yy, 0);
+      }
+    }
+  };
+  row(0, CONN >= 18);
+  if (CONN >= 18) { row(-1, false); row(1, false); }
+}
+#define SEAM_CACHE 256
+template <int CONN>
+__global__ void __launch_bounds__(256) k_seam_pairs_f(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ below, cc_geom g,
+                                                      cc_nodes nodes, const uint32_t *__restrict__ dense_below, unsigned id_me,
+                                                      unsigned id_below, seam_blk blk, unsigned pair_cap) {
+  __shared__ unsigned long long cache[SEAM_CACHE];
+  cache[threadIdx.x] = ~0ull;
+  __syncthreads();
+  const long long pw = (long long)g.ny * g.w;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pw) return;
+  const int y = (int)(t / g.w), xw = (int)(t - (long long)y * g.w);
+  const uint32_t wv = __ldg(bits + t);
+  uint64_t last = ~0ull;
+  for (uint32_t rest = wv; rest;) {
+    const int s = __ffs(rest) - 1;
+    const int e = run_end(wv, s);
+    const uint32_t rm = bits_range(s, e);
+    rest &= ~rm;
+    const uint32_t tk = seam_ticket(nodes, run_slot((uint32_t)t, wv, s));
+    if (tk == 0xffffffffu) continue;  // overflow: the slow path takes over
+    const uint64_t me = (uint64_t)(id_me + tk);
+    seam_visit_below<CONN>(below, g, xw, y, rm, s, e, [&](int nxw, int ny_, int st) {
+      const uint32_t tb = __ldg(dense_below + ((size_t)ny_ * g.w + nxw) * 16 + (st >> 1));
+      if (tb == 0xffffffffu) return;
+      const uint64_t key = ((uint64_t)(id_below + tb) << 32) | me;
+      if (key == last) return;
+      last = key;
+      const unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 56);
+      if (atomicExch(&cache[h], key) == key) return;  // this CTA has just listed the pair
+      const unsigned pos = atomicAdd(&blk.hdr->npairs, 1u);
+      if (pos < pair_cap) blk.pairs[pos] = key; else atomicOr(&blk.hdr->overflow, 2u);
+    });
+  }
+}
+
+__device__ __forceinline__ uint32_t uf32_find(uint32_t *par, uint32_t a) {
+  uint32_t p = __ldcg(par + a);
+  while (p != a) {
+    const uint32_t gp = __ldcg(par + p);
+    if (gp != p) atomicMin(par + a, gp);
+    a = p;
+    p = gp;
+  }
+  return a;
+}
+__device__ __forceinline__ void uf32_union(uint32_t *par, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = uf32_find(par, a);
+    b = uf32_find(par, b);
+    if (a == b) return;
+    if (a < b) { const uint32_t t = a; a = b; b = t; }
+    const uint32_t old = atomicMin(par + a, b);
+    if (old == a) return;
+    a = old;
+  }
+}
+// replicated resolution over the gathered blocks (ids: rank * ent_cap + ticket)
+struct seamf_arrays {
+  char *blocks;                 // world blocks
+  uint32_t *par;                // [world * ent_cap]
+  unsigned long long *gcnt;     // component size, at the root id
+  unsigned long long *gprio;    // min (rank << 32 | slot) of the component, at the root id
+  uint32_t *gflag;              // component touches a face
+  int world;
+  unsigned ent_cap, pair_cap;
+};
+__global__ void __launch_bounds__(256) k_seamf_init(seamf_arrays a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)a.world * a.ent_cap) return;
+  a.par[i] = i; a.gcnt[i] = 0ull; a.gprio[i] = ~0ull; a.gflag[i] = 0u;
+}
+__global__ void __launch_bounds__(256) k_seamf_union(seamf_arrays a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)a.world * a.pair_cap) return;
+  const int r = (int)(i / a.pair_cap);
+  const unsigned j = i - (unsigned)r * a.pair_cap;
+  const seam_blk b = seam_blk_at(a.blocks, r, a.ent_cap, a.pair_cap);
+  if (j >= min(b.hdr->npairs, a.pair_cap)) return;
+  const uint64_t key = b.pairs[j];
+  uf32_union(a.par, (uint32_t)(key >> 32), (uint32_t)(key & 0xffffffffull));
+}
+__global__ void __launch_bounds__(256) k_seamf_stats(seamf_arrays a) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)a.world * a.ent_cap) return;
+  const int r = (int)(i / a.ent_cap);
+  const unsigned t = i - (unsigned)r * a.ent_cap;
+  const seam_blk b = seam_blk_at(a.blocks, r, a.ent_cap, a.pair_cap);
+  if (t >= min(b.hdr->m, a.ent_cap)) return;
+  const seam_ent e = b.ent[t];
+  const uint32_t root = uf32_find(a.par, i);  // unions are complete (previous kernel): this is the final root
+  if (root != i) atomicMin(a.par + i, root);
+  atomicAdd(a.gcnt + root, e.cnt);
+  if (e.flag) atomicOr(a.gflag + root, 1u);
+  atomicMin(a.gprio + root, ((unsigned long long)r << 32) | e.slot);
+}
+// one CTA: number of seam roots / components among them, the largest component (size, then earliest first voxel),
+// and whether any rank overflowed its block
+__global__ void __launch_bounds__(1024) k_seamf_best(seamf_arrays a, b2m_scalars *sc) {
+  __shared__ unsigned long long s_size, s_prio;
+  __shared__ unsigned s_m, s_k, s_over;
+  if (threadIdx.x == 0) { s_size = 0ull; s_prio = ~0ull; s_m = 0u; s_k = 0u; s_over = 0u; }
+  __syncthreads();
+  const unsigned n = (unsigned)a.world * a.ent_cap;
+  unsigned long long mx = 0ull;
+  unsigned m = 0, k = 0;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = (int)(i / a.ent_cap);
+    const seam_blk b = seam_blk_at(a.blocks, r, a.ent_cap, a.pair_cap);
+    if (i - (unsigned)r * a.ent_cap >= min(b.hdr->m, a.ent_cap)) continue;
+    m++;
+    if (a.par[i] == i) { k++; const unsigned long long c = a.gcnt[i]; mx = c > mx ? c : mx; }
+  }
+  if (mx) atomicMax(&s_size, mx);
+  if (m) atomicAdd(&s_m, m);
+  if (k) atomicAdd(&s_k, k);
+  if (threadIdx.x < (unsigned)a.world && seam_blk_at(a.blocks, threadIdx.x, a.ent_cap, a.pair_cap).hdr->overflow) atomicOr(&s_over, 1u);
+  __syncthreads();
+  const unsigned long long best = s_size;
+  unsigned long long pr = ~0ull;
+  if (best)
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+      const int r = (int)(i / a.ent_cap);
+      const seam_blk b = seam_blk_at(a.blocks, r, a.ent_cap, a.pair_cap);
+      if (i - (unsigned)r * a.ent_cap >= min(b.hdr->m, a.ent_cap)) continue;
+      if (a.par[i] == i && a.gcnt[i] == best) { const unsigned long long p = a.gprio[i]; pr = p < pr ? p : pr; }
+    }
+  if (pr != ~0ull) atomicMin(&s_prio, pr);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sc->seam_n = s_m; sc->seam_roots = s_k; sc->best_seam = best; sc->best_seam_prio = s_prio;
+    if (s_over) atomicOr(&sc->overflow, 64u);
+  }
+}
+// mode 2: untag only; mode 1: untag + the component's global face flag; mode 0: untag, CC_SENT on the roots of the
+// component whose first voxel is gstar_prio
+__global__ void __launch_bounds__(256) k_seamf_apply(seamf_arrays a, int me, cc_nodes nodes, int mode, unsigned long long gstar_prio) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const seam_blk b = seam_blk_at(a.blocks, me, a.ent_cap, a.pair_cap);
+  if (i >= min(b.hdr->m, a.ent_cap)) return;
+  const uint32_t slot = b.ent[i].slot;
+  const uint32_t root = mode == 2 ? 0u : a.par[(unsigned)me * a.ent_cap + i];
+  if (mode == 1 && a.gflag[root]) atomicOr(&nodes[slot].y, 1u);
+  nodes[slot].x = (mode == 0 && a.gprio[root] == gstar_prio) ? CC_SENT : slot;
+}
+
+// ---- slow path kernels (sorted unique lists) ----
 __global__ void __launch_bounds__(256) k_seam_collect(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                       int do_first, int do_last, uint64_t *__restrict__ list, unsigned cap,
                                                       unsigned int *__restrict__ count, unsigned int *__restrict__ overflow) {
@@ -765,7 +1065,6 @@ __global__ void __launch_bounds__(256) k_seam_dense(const uint32_t *__restrict__
   }
 }
 // upper rank of a seam: every run of the first own plane against the runs of the plane below
-// (18-connectivity: face + the four edge neighbours in that plane; 6-connectivity: face only)
 template <int CONN>
 __global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ below, cc_geom g,
                                                     cc_nodes nodes, const uint32_t *__restrict__ U, unsigned m,
@@ -785,77 +1084,34 @@ __global__ void __launch_bounds__(256) k_seam_pairs(const uint32_t *__restrict__
     rest &= ~rm;
     const uint32_t root = cc_final_root(nodes, run_slot((uint32_t)t, wv, s));
     const uint64_t me = (uint64_t)(off_me + seam_lower_bound(U, m, root));
-    auto emit = [&](int nxw, int ny_, int st) {
+    seam_visit_below<CONN>(below, g, xw, y, rm, s, e, [&](int nxw, int ny_, int st) {
       const uint64_t nb = (uint64_t)(off_below + __ldg(dense_below + ((size_t)ny_ * g.w + nxw) * 16 + (st >> 1)));
       const uint64_t key = (nb << mb) | me;
       if (key == last) return;
       last = key;
       const unsigned pos = atomicAdd(count, 1u);
       if (pos < cap) pairs[pos] = key; else atomicOr(overflow, 8u);
-    };
-    auto row = [&](int dy, bool wide) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= g.ny) return;
-      const uint32_t *r = below + (size_t)yy * g.w;
-      const uint32_t nw = __ldg(r + xw);
-      uint32_t msk = rm;
-      if (wide) msk |= (rm << 1) | (rm >> 1);
-      uint32_t tt = nw & msk;
-      while (tt) {
-        const int b = __ffs(tt) - 1;
-        const int st = run_start(nw, b);
-        const int en = run_end(nw, st);
-        emit(xw, yy, st);
-        tt &= ~bits_range(st, en);
-      }
-      if (wide) {
-        if (s == 0 && xw > 0) {
-          const uint32_t pv = __ldg(r + xw - 1);
-          if (pv >> 31) emit(xw - 1, yy, run_start(pv, 31));
-        }
-        if (e == 31 && xw + 1 < g.w) {
-          const uint32_t nv = __ldg(r + xw + 1);
-          if (nv & 1u) emit(xw + 1, yy, 0);
-        }
-      }
-    };
-    row(0, CONN >= 18);
-    if (CONN >= 18) { row(-1, false); row(1, false); }
+    });
   }
 }
-// per own seam root: (local slot, count | face flag)
-__global__ void __launch_bounds__(256) k_seam_entries(const uint32_t *__restrict__ U, unsigned m, cc_nodes nodes,
-                                                      uint2 *__restrict__ ent) {
+// per own seam root: {local slot, face flag, voxels}
+__global__ void __launch_bounds__(256) k_seam_entries(const uint32_t *__restrict__ U, unsigned m, cc_nodes nodes, const b2m_scalars *sc,
+                                                      seam_ent *__restrict__ ent) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) ent[i] = make_uint2(U[i], nodes[U[i]].y);
+  if (i >= m) return;
+  const uint32_t y = nodes[U[i]].y;
+  seam_ent e;
+  e.slot = U[i]; e.flag = y & 1u; e.cnt = cc_count(sc, U[i], y);
+  ent[i] = e;
 }
 __global__ void __launch_bounds__(256) k_seam_iota(uint32_t *__restrict__ par, unsigned n) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) par[i] = i;
 }
-__device__ __forceinline__ uint32_t uf32_find(uint32_t *par, uint32_t a) {
-  uint32_t p = __ldcg(par + a);
-  while (p != a) {
-    const uint32_t gp = __ldcg(par + p);
-    if (gp != p) atomicMin(par + a, gp);
-    a = p;
-    p = gp;
-  }
-  return a;
-}
 __global__ void __launch_bounds__(256) k_seam_union(const uint64_t *__restrict__ pairs, unsigned n, int mb, uint32_t *par) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  uint32_t a = (uint32_t)(pairs[i] >> mb), b = (uint32_t)(pairs[i] & ((1ull << mb) - 1ull));
-  for (;;) {
-    a = uf32_find(par, a);
-    b = uf32_find(par, b);
-    if (a == b) return;
-    if (a < b) { const uint32_t t = a; a = b; b = t; }
-    const uint32_t old = atomicMin(par + a, b);
-    if (old == a) return;
-    a = old;
-  }
+  uf32_union(par, (uint32_t)(pairs[i] >> mb), (uint32_t)(pairs[i] & ((1ull << mb) - 1ull)));
 }
 __global__ void __launch_bounds__(256) k_seam_flatten(uint32_t *par, unsigned n) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -863,14 +1119,13 @@ __global__ void __launch_bounds__(256) k_seam_flatten(uint32_t *par, unsigned n)
   const uint32_t r = uf32_find(par, i);
   if (r != i) atomicMin(par + i, r);
 }
-__global__ void __launch_bounds__(256) k_seam_stats(unsigned n, const uint32_t *__restrict__ par, const uint2 *__restrict__ ent,
+__global__ void __launch_bounds__(256) k_seam_stats(unsigned n, const uint32_t *__restrict__ par, const seam_ent *__restrict__ ent,
                                                     unsigned long long *__restrict__ gcnt, uint32_t *__restrict__ gflag) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t r = par[i];
-  const uint32_t st = ent[i].y;
-  atomicAdd(gcnt + r, (unsigned long long)(st & 0x7fffffffu));
-  if (st >> 31) atomicOr(gflag + r, 1u);
+  atomicAdd(gcnt + r, ent[i].cnt);
+  if (ent[i].flag) atomicOr(gflag + r, 1u);
 }
 __global__ void __launch_bounds__(256) k_seam_best(unsigned n, const uint32_t *__restrict__ par, const unsigned long long *__restrict__ gcnt,
                                                    unsigned long long *__restrict__ best, unsigned int *__restrict__ nroots) {
@@ -885,14 +1140,22 @@ __global__ void __launch_bounds__(256) k_seam_apply(unsigned m, unsigned off, co
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const uint32_t r = par[off + i];
-  if (mode == 1) { if (gflag[r]) atomicOr(&nodes[U[i]].y, 0x80000000u); }
+  if (mode == 1) { if (gflag[r]) atomicOr(&nodes[U[i]].y, 1u); }
   else if ((long long)r == gstar) nodes[U[i]].x = CC_SENT;
 }
 
+__global__ void k_clear_bits(unsigned int *p, unsigned int bits) { atomicAnd(p, ~bits); }
+
 struct seam_result {
-  unsigned M, K;                 // seam roots over all ranks, components among them
-  unsigned long long best;      // (size << 30) | (2^30-1 - id) of the largest seam component (0: none)
+  int fast;                     // which path produced it
+  unsigned M, K;                // seam roots over all ranks, components among them
+  unsigned long long best_size; // voxels of the largest seam component (0: none)
   int best_rank; unsigned best_slot;  // first voxel of that component: (rank, local slot)
+  // fast path
+  seamf_arrays fa;
+  unsigned long long best_prio;
+  // slow path
+  long long gstar;              // id of the largest seam component
   unsigned m, off;              // own seam roots and their id offset
   const uint32_t *U, *par, *gflag;
 };
@@ -902,15 +1165,91 @@ static int seam_bits(unsigned long long n) {
   while ((1ull << b) < n) b++;
   return b;
 }
+static unsigned seam_env_cap(const char *name, unsigned dflt) {
+  const char *e = getenv(name);
+  if (!e) return dflt;
+  const long v = atol(e);
+  return v >= 1 && v <= (1 << 20) ? (unsigned)v : dflt;
+}
 
 // labelled `bits_own` (own planes, geometry cg) -> seam resolution.  `below` = the neighbour's last plane
-// (EXT plane 0) when this rank has a lower neighbour.
-static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
-                    const cc_geom &cg, cc_nodes nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
+// (EXT plane 0) when this rank has a lower neighbour.  Returns 1 in *overflowed when some rank's block was too small
+// (the roots are untagged again; nothing else has changed).
+static int cc_seams_fast(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
+                         const cc_geom &cg, cc_nodes nodes, int conn, b2m_scalars *d_sc, seam_result *sr, int *overflowed) {
+  const int W = sl.world, me = sl.rank;
+  const size_t pw = (size_t)cg.ny * cg.w;
+  const unsigned pblocks = b2m_cdiv(pw, 256);
+  const unsigned ent_cap = seam_env_cap("B2M_SEAM_ENT_CAP", 8192), pair_cap = seam_env_cap("B2M_SEAM_PAIR_CAP", 32768);
+  const size_t bb = seam_blk_bytes(ent_cap, pair_cap);
+  const size_t M = (size_t)W * ent_cap;
+  memset(sr, 0, sizeof(*sr));
+  sr->fast = 1;
+  *overflowed = 0;
+  size_t o = 0;
+  auto carve = [&](size_t bytes) { const size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return at; };
+  const size_t o_blk = carve(bb * W), o_par = carve(M * 4), o_cnt = carve(M * 8), o_prio = carve(M * 8), o_flag = carve(M * 4);
+  const size_t o_ds = carve(pw * 64), o_dr = carve(pw * 64);
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAMF, o));
+  char *base = b2m_ptr<char>(ctx, BUF_SEAMF);
+  seamf_arrays fa;
+  fa.blocks = base + o_blk; fa.par = reinterpret_cast<uint32_t *>(base + o_par);
+  fa.gcnt = reinterpret_cast<unsigned long long *>(base + o_cnt); fa.gprio = reinterpret_cast<unsigned long long *>(base + o_prio);
+  fa.gflag = reinterpret_cast<uint32_t *>(base + o_flag);
+  fa.world = W; fa.ent_cap = ent_cap; fa.pair_cap = pair_cap;
+  uint32_t *dense_send = reinterpret_cast<uint32_t *>(base + o_ds), *dense_recv = reinterpret_cast<uint32_t *>(base + o_dr);
+  const seam_blk mine = seam_blk_at(fa.blocks, me, ent_cap, pair_cap);
+  CU_TRY(cudaMemsetAsync(mine.hdr, 0, sizeof(seam_hdr), ctx->stream));
+  KT_LAUNCH(ctx, "seam_tag", k_seam_tag<<<dim3(pblocks, 2), 256, 0, ctx->stream>>>(bits_own, cg, nodes, sl.hl, sl.hh, mine, ent_cap, d_sc));
+  if (sl.hh) KT_LAUNCH(ctx, "seam_dense", k_seam_dense_f<<<pblocks, 256, 0, ctx->stream>>>(bits_own, cg, nodes, dense_send));  // only run-start slots are written (and read)
+  B2M_TRY(b2m_comm_exchange(ctx, comm, dense_send, sl.hh ? pw * 64 : 0, dense_recv, sl.hl ? pw * 64 : 0, nullptr, 0, nullptr, 0));
+  if (sl.hl) {
+    if (conn >= 18)
+      KT_LAUNCH(ctx, "seam_pairs", k_seam_pairs_f<18><<<pblocks, 256, 0, ctx->stream>>>(bits_own, below, cg, nodes, dense_recv, (unsigned)me * ent_cap, (unsigned)(me - 1) * ent_cap, mine, pair_cap));
+    else
+      KT_LAUNCH(ctx, "seam_pairs", k_seam_pairs_f<6><<<pblocks, 256, 0, ctx->stream>>>(bits_own, below, cg, nodes, dense_recv, (unsigned)me * ent_cap, (unsigned)(me - 1) * ent_cap, mine, pair_cap));
+  }
+  B2M_TRY(b2m_comm_allgather_inplace(ctx, comm, fa.blocks, bb));
+  KT_LAUNCH(ctx, "seam_uf", k_seamf_init<<<b2m_cdiv(M, 256), 256, 0, ctx->stream>>>(fa));
+  KT_LAUNCH(ctx, "seam_uf", k_seamf_union<<<b2m_cdiv((size_t)W * pair_cap, 256), 256, 0, ctx->stream>>>(fa));
+  KT_LAUNCH(ctx, "seam_stats", k_seamf_stats<<<b2m_cdiv(M, 256), 256, 0, ctx->stream>>>(fa));
+  KT_LAUNCH(ctx, "seam_stats", k_seamf_best<<<1, 1024, 0, ctx->stream>>>(fa, d_sc));
+  CU_TRY(cudaGetLastError());
+  B2M_TRY(b2m_sync_scalars(ctx, comm));  // the one host round trip of the fast path (also carries nroots / best of the local labelling)
+  bool over = false;
+  for (int r = 0; r < W; r++) over |= (b2m_sc(ctx, comm, r)->overflow & 64u) != 0;  // every rank computed it from the same headers
+  sr->fa = fa;
+  if (over) {
+    KT_LAUNCH(ctx, "seam_apply", k_seamf_apply<<<b2m_cdiv(ent_cap, 256), 256, 0, ctx->stream>>>(fa, me, nodes, 2, 0ull));
+    k_clear_bits<<<1, 1, 0, ctx->stream>>>(&d_sc->overflow, 64u);
+    *overflowed = 1;
+    return B2M_OK;
+  }
+  const b2m_scalars *h = ctx->h_scalars;
+  sr->M = h->seam_n; sr->K = h->seam_roots;
+  sr->best_size = h->best_seam; sr->best_prio = h->best_seam_prio;
+  sr->best_rank = (int)(h->best_seam_prio >> 32); sr->best_slot = (unsigned)(h->best_seam_prio & 0xffffffffull);
+  return B2M_OK;
+}
+// give the global result back to the local forest (and untag): mode 1 face flags, mode 0 CC_SENT on the winner (win: the
+// seam component won the largest-cluster contest), mode 2 nothing
+static int cc_seams_apply(b2m_ctx *ctx, const b2m_slab &sl, cc_nodes nodes, const seam_result *sr, int mode, bool win) {
+  if (sr->fast) {
+    KT_LAUNCH(ctx, "seam_apply", k_seamf_apply<<<b2m_cdiv(sr->fa.ent_cap, 256), 256, 0, ctx->stream>>>(sr->fa, sl.rank, nodes, mode == 0 && !win ? 2 : mode, sr->best_prio));
+  } else if (sr->m && (mode == 1 || (mode == 0 && win))) {
+    KT_LAUNCH(ctx, "seam_apply", k_seam_apply<<<b2m_cdiv(sr->m, 256), 256, 0, ctx->stream>>>(sr->m, sr->off, sr->U, sr->par, sr->gflag, nodes, mode, sr->gstar));
+  }
+  CU_TRY(cudaGetLastError());
+  return B2M_OK;
+}
+
+static int cc_seams_slow(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
+                         const cc_geom &cg, cc_nodes nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
   const int W = sl.world, me = sl.rank;
   const size_t pw = (size_t)cg.ny * cg.w;
   const unsigned pblocks = b2m_cdiv(pw, 256);
   memset(sr, 0, sizeof(*sr));
+  sr->gstar = -1;
   // 1. roots of the runs on the own boundary planes -> sorted unique list U
   const unsigned cap_runs = (unsigned)(2 * pw * 16);
   B2M_TRY(b2m_reserve(ctx, BUF_SEAM0, (size_t)cap_runs * 8 + (size_t)cap_runs * 4 + 256));
@@ -964,9 +1303,9 @@ static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint
   if (np_raw > cap_pairs) { b2m_set_error("seam: pair list overflow"); return B2M_ECUDA; }
   // the unique pairs and the own entries go to BUF_SEAM0 (the root list is no longer needed)
   const size_t up_bytes = ((size_t)np_raw * 8 + 255) & ~(size_t)255;
-  B2M_TRY(b2m_reserve(ctx, BUF_SEAM0, up_bytes + (size_t)m * 8 + 256));
+  B2M_TRY(b2m_reserve(ctx, BUF_SEAM0, up_bytes + (size_t)m * sizeof(seam_ent) + 256));
   uint64_t *upairs = b2m_ptr<uint64_t>(ctx, BUF_SEAM0);
-  uint2 *ent_own = reinterpret_cast<uint2 *>(b2m_ptr<char>(ctx, BUF_SEAM0) + up_bytes);
+  seam_ent *ent_own = reinterpret_cast<seam_ent *>(b2m_ptr<char>(ctx, BUF_SEAM0) + up_bytes);
   if (np_raw > 0) {
     B2M_TRY(b2m_sort_u64(ctx, pairs, np_raw, 2 * mb));
     KT_LAUNCH(ctx, "seam_unique", k_seam_unique_flags<<<b2m_cdiv(np_raw, 256), 256, 0, ctx->stream>>>(pairs, np_raw, pflag));
@@ -980,21 +1319,21 @@ static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint
   for (int r = 0; r < W; r++) {
     const unsigned npr = b2m_sc(ctx, comm, r)->seam_n;
     pbytes[r] = (size_t)npr * 8;
-    ebytes[r] = (size_t)(offs[r + 1] - offs[r]) * 8;
+    ebytes[r] = (size_t)(offs[r + 1] - offs[r]) * sizeof(seam_ent);
     Ptot += npr;
   }
   // 3. replicated resolution.  BUF_SEAM2 is re-carved: all pairs | all entries | parent | gcnt | gflag
-  size_t need = (size_t)Ptot * 8 + (size_t)M * (8 + 4 + 8 + 4) + 2048;
+  size_t need = (size_t)Ptot * 8 + (size_t)M * (sizeof(seam_ent) + 4 + 8 + 4) + 2048;
   B2M_TRY(b2m_reserve(ctx, BUF_SEAM2, need));
   char *base = b2m_ptr<char>(ctx, BUF_SEAM2);
   size_t o = 0;
   auto take = [&](size_t bytes) { char *q = base + o; o = (o + bytes + 255) & ~(size_t)255; return q; };
   uint64_t *all_pairs = reinterpret_cast<uint64_t *>(take((size_t)Ptot * 8));
-  uint2 *all_ent = reinterpret_cast<uint2 *>(take((size_t)M * 8));
+  seam_ent *all_ent = reinterpret_cast<seam_ent *>(take((size_t)M * sizeof(seam_ent)));
   uint32_t *par = reinterpret_cast<uint32_t *>(take((size_t)M * 4));
   unsigned long long *gcnt = reinterpret_cast<unsigned long long *>(take((size_t)M * 8));
   uint32_t *gflag = reinterpret_cast<uint32_t *>(take((size_t)M * 4));
-  if (m) KT_LAUNCH(ctx, "seam_entries", k_seam_entries<<<b2m_cdiv(m, 256), 256, 0, ctx->stream>>>(U, m, nodes, ent_own));
+  if (m) KT_LAUNCH(ctx, "seam_entries", k_seam_entries<<<b2m_cdiv(m, 256), 256, 0, ctx->stream>>>(U, m, nodes, d_sc, ent_own));
   B2M_TRY(b2m_comm_allgatherv(ctx, comm, upairs, all_pairs, pbytes));
   B2M_TRY(b2m_comm_allgatherv(ctx, comm, ent_own, all_ent, ebytes));
   const unsigned mblocks = b2m_cdiv(M, 256);
@@ -1010,19 +1349,34 @@ static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint
   CU_TRY(cudaGetLastError());
   B2M_TRY(b2m_fetch_scalars(ctx));
   sr->K = ctx->h_scalars->seam_roots;
-  sr->best = ctx->h_scalars->best_seam;
   sr->par = par; sr->gflag = gflag;
-  if (sr->best) {
-    const unsigned id = 0x3fffffffu - (unsigned)(sr->best & 0x3fffffffull);
-    uint2 e;
-    CU_TRY(cudaMemcpyAsync(&e, all_ent + id, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  const unsigned long long best = ctx->h_scalars->best_seam;
+  if (best) {
+    const unsigned id = 0x3fffffffu - (unsigned)(best & 0x3fffffffull);
+    seam_ent e;
+    CU_TRY(cudaMemcpyAsync(&e, all_ent + id, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     int r = 0;
     while (r + 1 < W && offs[r + 1] <= id) r++;
+    sr->best_size = best >> 30;
     sr->best_rank = r;
-    sr->best_slot = e.x;
+    sr->best_slot = e.slot;
+    sr->gstar = (long long)id;
   }
   return B2M_OK;
+}
+
+static int cc_seams(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const uint32_t *bits_own, const uint32_t *below,
+                    const cc_geom &cg, cc_nodes nodes, int conn, b2m_scalars *d_sc, seam_result *sr) {
+  static const bool force_slow = getenv("B2M_SEAM_SLOW") && atoi(getenv("B2M_SEAM_SLOW")) > 0;
+  if (!force_slow) {
+    int over = 0;
+    B2M_TRY(cc_seams_fast(ctx, comm, sl, bits_own, below, cg, nodes, conn, d_sc, sr, &over));
+    if (!over) return B2M_OK;
+  }
+  // the slow path needs the scalars of the local labelling on the host as well (nroots / best): its first
+  // b2m_sync_scalars brings them
+  return cc_seams_slow(ctx, comm, sl, bits_own, below, cg, nodes, conn, d_sc, sr);
 }
 
 // CC part of the front: fills fo->fill / fo->keep and the raw bright bbox in d_sc->lo/hi.
@@ -1036,6 +1390,9 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   unsigned blocks = b2m_cdiv(own_words, 256);
   const bool cc = o->only_largest || o->fill_bubbles;
   const bool slabs = sl.world > 1;
+  // bwlabelCore() refuses volumes narrower than 2 voxels in x or y (src/bwlabel.c:434-437: it prints a message and
+  // leaves the mask as thresholded), so -b finds no bubbles and -l keeps every bright voxel
+  const bool refused = g.nx < 2 || g.ny < 2;
   B2M_TRY(b2m_reserve(ctx, BUF_FG, wbytes));
   uint32_t *fg = b2m_ptr<uint32_t>(ctx, BUF_FG);
   uint32_t *bg = nullptr;
@@ -1052,9 +1409,9 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
   const uint32_t *bright = fg;
   cc_nodes nodes = {nullptr, (uint32_t)own_words};
   const size_t own_off = (size_t)sl.hl * pw;                   // first own word in an EXT bit buffer
-  if (cc) {
-    if ((unsigned long long)own_words * 16ull > 0xffffffffull || (unsigned long long)own_words * 32ull > 0x7fffffffull) {
-      b2m_set_error("slab too large for 32-bit run slots / 31-bit component sizes (%lld words)", own_words);
+  if (cc && !refused) {
+    if ((unsigned long long)own_words > (1ull << 27)) {  // run slots = word * 16 + run stay below 2^31 (bit 31 tags seam roots)
+      b2m_set_error("slab of more than 2^27 bit words (2^32 voxels): %lld words", own_words);
       return B2M_EARG;
     }
     B2M_TRY(b2m_reserve(ctx, BUF_NODES, (size_t)own_words * 16 * sizeof(uint2)));
@@ -1066,10 +1423,10 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     return b2m_comm_exchange(ctx, comm, ext + own_off + (size_t)(sl.nzl - 1) * pw, sl.hh ? pw * 4 : 0, ext, sl.hl ? pw * 4 : 0,
                              ext + own_off, sl.hl ? pw * 4 : 0, ext + own_off + (size_t)sl.nzl * pw, sl.hh ? pw * 4 : 0);
   };
-  if (o->fill_bubbles) {
+  if (o->fill_bubbles && !refused) {
     B2M_TRY(b2m_reserve(ctx, BUF_FILL, wbytes));
     uint32_t *fill = b2m_ptr<uint32_t>(ctx, BUF_FILL);
-    B2M_TRY(cc_label(ctx, bg + own_off, cg, nodes, 6, nullptr, &d_sc->nroots_bg));
+    B2M_TRY(cc_label(ctx, bg + own_off, cg, nodes, 6, nullptr, &d_sc->nroots_bg, d_sc));
     long long nroots_ovr = -1;
     if (slabs) {
       seam_result sr;
@@ -1077,7 +1434,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
       unsigned long long tot = 0;
       for (int r = 0; r < sl.world; r++) tot += b2m_sc(ctx, comm, r)->nroots_bg;
       nroots_ovr = (long long)(tot - (sr.M - sr.K));
-      if (sr.m) KT_LAUNCH(ctx, "seam_apply", k_seam_apply<<<b2m_cdiv(sr.m, 256), 256, 0, ctx->stream>>>(sr.m, sr.off, sr.U, sr.par, sr.gflag, nodes, 1, -1));
+      B2M_TRY(cc_seams_apply(ctx, sl, nodes, &sr, 1, false));
     }
     KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bg + own_off, own_words, nodes, 1, nullptr, &d_sc->nroots_bg, fg + own_off, fill + own_off, -2, nroots_ovr));
     B2M_TRY(halo_bits(fill));
@@ -1090,7 +1447,9 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     B2M_TRY(b2m_reserve(ctx, BUF_KEEP, wbytes));
     largest = b2m_ptr<uint32_t>(ctx, BUF_LARGEST);
     keep = b2m_ptr<uint32_t>(ctx, BUF_KEEP);
-    B2M_TRY(cc_label(ctx, bright + own_off, cg, nodes, 18, &d_sc->best_fg, &d_sc->nroots_fg));
+    if (refused) CU_TRY(cudaMemcpyAsync(largest, bright, wbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    else {
+    B2M_TRY(cc_label(ctx, bright + own_off, cg, nodes, 18, &d_sc->best_fg, &d_sc->nroots_fg, d_sc));
     long long sel = -2;
     if (slabs) {
       seam_result sr;
@@ -1100,24 +1459,24 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
       for (int r = 0; r < sl.world; r++) {
         const unsigned long long k = b2m_sc(ctx, comm, r)->best_fg;
         if (!k) continue;
-        const unsigned long long sz = k >> 32;
-        const unsigned slot = 0xffffffffu - (unsigned)(k & 0xffffffffull);
+        const unsigned long long sz = k >> 31;
+        const unsigned slot = 0x7fffffffu - (unsigned)(k & 0x7fffffffull);
         if (sz > bsize) { bsize = sz; brank = r; bslot = slot; }
       }
-      long long gstar = -1;
-      if (sr.best) {
-        const unsigned long long sz = sr.best >> 30;
+      bool win = false;
+      if (sr.best_size) {
+        const unsigned long long sz = sr.best_size;
         if (sz > bsize || (sz == bsize && (sr.best_rank < brank || (sr.best_rank == brank && sr.best_slot <= bslot)))) {
-          gstar = (long long)(0x3fffffffu - (unsigned)(sr.best & 0x3fffffffull));
+          win = true;
           brank = -1;
         }
       }
       sel = (brank == sl.rank) ? (long long)bslot : -1;
-      if (gstar >= 0 && sr.m)
-        KT_LAUNCH(ctx, "seam_apply", k_seam_apply<<<b2m_cdiv(sr.m, 256), 256, 0, ctx->stream>>>(sr.m, sr.off, sr.U, sr.par, sr.gflag, nodes, 0, gstar));
+      B2M_TRY(cc_seams_apply(ctx, sl, nodes, &sr, 0, win));
     }
     KT_LAUNCH(ctx, "cc_select", k_cc_select<<<blocks, 256, 0, ctx->stream>>>(bright + own_off, own_words, nodes, 0, &d_sc->best_fg, nullptr, nullptr, largest + own_off, sel, -1));
     B2M_TRY(halo_bits(largest));
+    }
     fo->keep = keep;
   }
   {

@@ -13,9 +13,15 @@
 //          cudaMemcpyAsync (peer copies when the devices differ).  This is what the parity tests use
 //          to run 2..4 slabs on a single GPU, and it is a valid single-process multi-GPU mode.
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
 #include <pthread.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -28,10 +34,35 @@ struct local_group {
   int refs;
 };
 
+// Host decision points (b2m_sync_scalars) of ranks that share a node go through a POSIX shared-memory segment instead
+// of an NCCL all-gather + D2H: every rank copies its own 256-byte block to the host and publishes it in the segment,
+// then reads the other ranks' blocks - a few microseconds instead of the ~60-80 us of a small NCCL collective followed
+// by a copy and a stream synchronisation, ~10 times per slab step.  Blocks are double-buffered by the parity of the
+// sequence number (a rank cannot be two syncs ahead of a rank that is still reading).  The segment also carries the
+// `poison` flag with which a rank that failed releases its peers (they abort the NCCL communicator and return an error
+// instead of waiting for ever).
+struct shm_slot {
+  std::atomic<unsigned long long> seq;
+  char pad[56];
+  b2m_scalars blk[2];
+};
+struct shm_seg {
+  std::atomic<unsigned int> poison;
+  std::atomic<unsigned int> attached;
+  std::atomic<unsigned int> magic;
+  char pad[52];
+  shm_slot r[1];  // [world]
+};
+#define SHM_MAGIC 0xb2b2b200u
+
 struct b2m_comm {
   int rank, world, kind;  // kind 0 = NCCL, 1 = local
   ncclComm_t nccl;
   local_group *grp;
+  shm_seg *seg;           // NCCL ranks of one node: host-side exchange of the scalar blocks (null: NCCL all-gather)
+  size_t seg_bytes;
+  unsigned long long seq;
+  int aborted;
 };
 
 // ---- NCCL through dlopen -------------------------------------------------------------------------
@@ -40,6 +71,7 @@ static struct {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *);
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
   ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*CommAbort)(ncclComm_t);
   ncclResult_t (*GroupStart)(void);
   ncclResult_t (*GroupEnd)(void);
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
@@ -58,7 +90,7 @@ static int nccl_load(void) {
 #define SYM(field, name)                                                        \
   *(void **)(&N.field) = dlsym(h, name);                                        \
   if (!N.field) { b2m_set_error("libnccl: symbol %s missing", name); return B2M_ECUDA; }
-  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy") SYM(CommAbort, "ncclCommAbort")
   SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
   SYM(AllGather, "ncclAllGather") SYM(Broadcast, "ncclBroadcast") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
@@ -74,6 +106,7 @@ static int nccl_load(void) {
     }                                                                                       \
   } while (0)
 
+static int shm_attach(b2m_comm *c, b2m_ctx *ctx, const void *id128);
 int b2m_comm_rank(const b2m_comm *c) { return c ? c->rank : 0; }
 int b2m_comm_world(const b2m_comm *c) { return c ? c->world : 1; }
 
@@ -99,12 +132,97 @@ static int grp_barrier(local_group *g) {
   if (bad) { b2m_set_error("local comm: barrier aborted (another rank failed or timed out)"); return B2M_ECUDA; }
   return B2M_OK;
 }
+// A rank that fails for a reason of its own (out of memory, a capacity overflow) must not leave its peers inside a
+// collective.  Local groups: the abort flag of the barrier.  NCCL: the poison flag of the shared segment, which every
+// host wait of the peers polls (b2m_comm_stream_wait, the sequence wait of b2m_sync_scalars), then ncclCommAbort so that
+// operations already enqueued on the stream are released.  The communicator is unusable afterwards.
+static void nccl_abort(b2m_comm *c) {
+  if (c->aborted) return;
+  c->aborted = 1;
+  if (c->seg) c->seg->poison.store(1u, std::memory_order_release);
+  if (c->nccl && N.CommAbort) { N.CommAbort(c->nccl); c->nccl = nullptr; }
+}
 void b2m_comm_abort(b2m_comm *c) {
-  if (!c || c->kind != 1) return;
+  if (!c) return;
+  if (c->kind == 0) { nccl_abort(c); return; }
   pthread_mutex_lock(&c->grp->mu);
   c->grp->abort = 1;
   pthread_cond_broadcast(&c->grp->cv);
   pthread_mutex_unlock(&c->grp->mu);
+}
+
+
+// ---- the node-local host segment of an NCCL communicator ----------------------------------------------
+static unsigned long long fnv64(const void *p, size_t n, unsigned long long h) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+__global__ void k_comm_all_equal(const unsigned long long *v, int n, int *out) {
+  int same = 1;
+  for (int i = 1; i < n; i++) same &= v[i] == v[0];
+  *out = same;
+}
+// All ranks decide together (one NCCL all-gather of a host fingerprint, once per communicator) whether they share a
+// node; if so rank 0 creates the segment (name derived from the NCCL id), the others map it, and the name is removed
+// again once everybody is attached.  B2M_SCALARS_NCCL=1 keeps the NCCL transport (tests run both).
+static int shm_attach(b2m_comm *c, b2m_ctx *ctx, const void *id128) {
+  const char *force = getenv("B2M_SCALARS_NCCL");
+  char host[256] = "";
+  gethostname(host, sizeof(host) - 1);
+  unsigned long long fp = fnv64(host, strlen(host), 1469598103934665603ull);
+  {
+    char boot[64] = "";
+    FILE *f = fopen("/proc/sys/kernel/random/boot_id", "r");
+    if (f) { if (fgets(boot, sizeof(boot), f)) fp = fnv64(boot, strlen(boot), fp); fclose(f); }
+  }
+  if (force && atoi(force) > 0) fp = fnv64(&c->rank, sizeof(int), fp);  // pretend every rank sits on another node
+  unsigned long long *d_fp = nullptr;
+  int *d_same = nullptr, same = 0;
+  CU_TRY(cudaMalloc(&d_fp, (size_t)(c->world + 1) * 8 + 8));
+  d_same = reinterpret_cast<int *>(d_fp + c->world + 1);
+  CU_TRY(cudaMemcpyAsync(d_fp + c->world, &fp, 8, cudaMemcpyHostToDevice, ctx->stream));
+  NC_TRY(N.AllGather(d_fp + c->world, d_fp, 8, ncclUint8, c->nccl, ctx->stream));
+  k_comm_all_equal<<<1, 1, 0, ctx->stream>>>(d_fp, c->world, d_same);
+  CU_TRY(cudaMemcpyAsync(&same, d_same, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  CU_TRY(cudaFree(d_fp));
+  if (!same) return B2M_OK;  // several nodes: the scalar blocks travel by NCCL
+  char name[64];
+  snprintf(name, sizeof(name), "/b2m_%016llx", fnv64(id128, 128, 1469598103934665603ull));
+  const size_t bytes = sizeof(shm_seg) + (size_t)(c->world - 1) * sizeof(shm_slot);
+  int fd = -1;
+  if (c->rank == 0) {
+    shm_unlink(name);
+    fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) { b2m_set_error("shm_open(%s) failed", name); if (fd >= 0) close(fd); return B2M_ECUDA; }
+  } else {
+    for (int tries = 0; tries < 60000 && fd < 0; tries++) {  // <= 60 s
+      fd = shm_open(name, O_RDWR, 0600);
+      struct stat st;
+      if (fd >= 0 && (fstat(fd, &st) != 0 || (size_t)st.st_size < bytes)) { close(fd); fd = -1; }
+      if (fd < 0) usleep(1000);
+    }
+    if (fd < 0) { b2m_set_error("rank %d: cannot open the host segment %s", c->rank, name); return B2M_ECUDA; }
+  }
+  void *m = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) { b2m_set_error("mmap of the host segment failed"); return B2M_ECUDA; }
+  shm_seg *seg = (shm_seg *)m;
+  if (c->rank == 0) seg->magic.store(SHM_MAGIC, std::memory_order_release);  // a fresh segment is zero-filled
+  else
+    for (int tries = 0; seg->magic.load(std::memory_order_acquire) != SHM_MAGIC; tries++) {
+      if (tries > 60000) { munmap(m, bytes); b2m_set_error("host segment never initialised"); return B2M_ECUDA; }
+      usleep(1000);
+    }
+  seg->attached.fetch_add(1u, std::memory_order_acq_rel);
+  for (int tries = 0; seg->attached.load(std::memory_order_acquire) < (unsigned)c->world; tries++) {
+    if (tries > 60000) { munmap(m, bytes); b2m_set_error("host segment: not every rank attached"); return B2M_ECUDA; }
+    usleep(1000);
+  }
+  if (c->rank == 0) shm_unlink(name);
+  c->seg = seg; c->seg_bytes = bytes;
+  return B2M_OK;
 }
 
 // ---- public constructors ---------------------------------------------------------------------------
@@ -128,6 +246,8 @@ extern "C" int b2m_comm_create_nccl(b2m_comm **out, b2m_ctx *ctx, const void *id
   c->rank = rank; c->world = world; c->kind = 0;
   ncclResult_t r = N.CommInitRank(&c->nccl, world, id, rank);
   if (r != ncclSuccess) { b2m_set_error("ncclCommInitRank: %s", N.GetErrorString(r)); free(c); return B2M_ECUDA; }
+  int rc = world > 1 ? shm_attach(c, ctx, id128) : B2M_OK;
+  if (rc != B2M_OK) { N.CommDestroy(c->nccl); free(c); return rc; }
   *out = c;
   return B2M_OK;
 }
@@ -147,8 +267,10 @@ extern "C" int b2m_comm_create_local(b2m_comm **out, int world) {
 }
 extern "C" void b2m_comm_destroy(b2m_comm *c) {
   if (!c) return;
-  if (c->kind == 0) { if (c->nccl) N.CommDestroy(c->nccl); }
-  else {
+  if (c->kind == 0) {
+    if (c->nccl) N.CommDestroy(c->nccl);
+    if (c->seg) munmap(c->seg, c->seg_bytes);
+  } else {
     pthread_mutex_lock(&c->grp->mu);
     const int left = --c->grp->refs;
     pthread_mutex_unlock(&c->grp->mu);
@@ -165,17 +287,28 @@ extern "C" int b2m_comm_reset(b2m_comm *c) {  // clears the abort flag of a loca
 }
 
 // ---- primitives --------------------------------------------------------------------------------------
+// can the exchange run on a stream of its own, next to kernels of the ctx stream?  (NCCL: yes; local groups publish
+// pointers between host barriers and always use the ctx stream)
+bool b2m_comm_async_capable(const b2m_comm *c) { return c && c->world > 1 && c->kind == 0; }
+
 int b2m_comm_exchange(b2m_ctx *ctx, b2m_comm *c, const void *d_send_up, size_t send_up_bytes, void *d_recv_lo,
                       size_t recv_lo_bytes, const void *d_send_dn, size_t send_dn_bytes, void *d_recv_hi,
                       size_t recv_hi_bytes) {
+  return b2m_comm_exchange_on(ctx, c, ctx->stream, d_send_up, send_up_bytes, d_recv_lo, recv_lo_bytes, d_send_dn, send_dn_bytes,
+                              d_recv_hi, recv_hi_bytes);
+}
+int b2m_comm_exchange_on(b2m_ctx *ctx, b2m_comm *c, cudaStream_t st, const void *d_send_up, size_t send_up_bytes, void *d_recv_lo,
+                         size_t recv_lo_bytes, const void *d_send_dn, size_t send_dn_bytes, void *d_recv_hi,
+                         size_t recv_hi_bytes) {
   if (!c || c->world == 1) return B2M_OK;
   const bool has_lo = c->rank > 0, has_hi = c->rank + 1 < c->world;
   if (c->kind == 0) {
+    if (c->aborted) { b2m_set_error("nccl comm: aborted after a rank failed"); return B2M_ECUDA; }
     NC_TRY(N.GroupStart());
-    if (has_hi && send_up_bytes) NC_TRY(N.Send(d_send_up, send_up_bytes, ncclUint8, c->rank + 1, c->nccl, ctx->stream));
-    if (has_lo && recv_lo_bytes) NC_TRY(N.Recv(d_recv_lo, recv_lo_bytes, ncclUint8, c->rank - 1, c->nccl, ctx->stream));
-    if (has_lo && send_dn_bytes) NC_TRY(N.Send(d_send_dn, send_dn_bytes, ncclUint8, c->rank - 1, c->nccl, ctx->stream));
-    if (has_hi && recv_hi_bytes) NC_TRY(N.Recv(d_recv_hi, recv_hi_bytes, ncclUint8, c->rank + 1, c->nccl, ctx->stream));
+    if (has_hi && send_up_bytes) NC_TRY(N.Send(d_send_up, send_up_bytes, ncclUint8, c->rank + 1, c->nccl, st));
+    if (has_lo && recv_lo_bytes) NC_TRY(N.Recv(d_recv_lo, recv_lo_bytes, ncclUint8, c->rank - 1, c->nccl, st));
+    if (has_lo && send_dn_bytes) NC_TRY(N.Send(d_send_dn, send_dn_bytes, ncclUint8, c->rank - 1, c->nccl, st));
+    if (has_hi && recv_hi_bytes) NC_TRY(N.Recv(d_recv_hi, recv_hi_bytes, ncclUint8, c->rank + 1, c->nccl, st));
     NC_TRY(N.GroupEnd());
     return B2M_OK;
   }
@@ -191,6 +324,37 @@ int b2m_comm_exchange(b2m_ctx *ctx, b2m_comm *c, const void *d_send_up, size_t s
   return B2M_OK;
 }
 
+// all list lengths are multiples of 8 bytes (pairs, entries, items)
+struct gather_segs { int world; size_t stride; size_t off[65]; };
+__global__ void __launch_bounds__(256) k_gather_pack(const char *__restrict__ scratch, char *__restrict__ out, gather_segs gs) {
+  const size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t o = u * 8;
+  if (o >= gs.off[gs.world]) return;
+  int r = 0;
+  while (o >= gs.off[r + 1]) r++;
+  *reinterpret_cast<unsigned long long *>(out + o) =
+      *reinterpret_cast<const unsigned long long *>(scratch + (size_t)r * gs.stride + (o - gs.off[r]));
+}
+// fixed-size all-gather: every rank's `bytes` bytes at d_buf + rank * bytes, in place
+int b2m_comm_allgather_inplace(b2m_ctx *ctx, b2m_comm *c, void *d_buf, size_t bytes) {
+  const int W = b2m_comm_world(c), me = b2m_comm_rank(c);
+  if (W == 1) return B2M_OK;
+  if (c->kind == 0) {
+    if (c->aborted) { b2m_set_error("nccl comm: aborted after a rank failed"); return B2M_ECUDA; }
+    NC_TRY(N.AllGather((char *)d_buf + (size_t)me * bytes, d_buf, bytes, ncclUint8, c->nccl, ctx->stream));
+    return B2M_OK;
+  }
+  local_group *g = c->grp;
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  g->pub[me][0] = (char *)d_buf + (size_t)me * bytes;
+  B2M_TRY(grp_barrier(g));
+  for (int r = 0; r < W; r++)
+    if (r != me) CU_TRY(cudaMemcpyAsync((char *)d_buf + (size_t)r * bytes, g->pub[r][0], bytes, cudaMemcpyDefault, ctx->stream));
+  CU_TRY(cudaStreamSynchronize(ctx->stream));
+  B2M_TRY(grp_barrier(g));
+  return B2M_OK;
+}
+
 int b2m_comm_allgatherv(b2m_ctx *ctx, b2m_comm *c, const void *d_send, void *d_recv, const size_t *bytes) {
   const int W = b2m_comm_world(c), me = b2m_comm_rank(c);
   size_t off[65];
@@ -201,12 +365,23 @@ int b2m_comm_allgatherv(b2m_ctx *ctx, b2m_comm *c, const void *d_send, void *d_r
     return B2M_OK;
   }
   if (c->kind == 0) {
-    NC_TRY(N.GroupStart());
-    for (int r = 0; r < W; r++) {
-      if (!bytes[r]) continue;
-      NC_TRY(N.Broadcast(r == me ? d_send : nullptr, (char *)d_recv + off[r], bytes[r], ncclUint8, r, c->nccl, ctx->stream));
-    }
-    NC_TRY(N.GroupEnd());
+    // ONE ncclAllGather of equal-sized (padded to the longest list) segments into a scratch buffer, then one kernel
+    // that packs the segments back to back (W grouped broadcasts were W times the latency)
+    if (c->aborted) { b2m_set_error("nccl comm: aborted after a rank failed"); return B2M_ECUDA; }
+    size_t mx = 0;
+    for (int r = 0; r < W; r++) mx = bytes[r] > mx ? bytes[r] : mx;
+    if (mx == 0) return B2M_OK;
+    mx = (mx + 15) & ~(size_t)15;
+    B2M_TRY(b2m_reserve(ctx, BUF_GATHER, mx * W));
+    char *scratch = b2m_ptr<char>(ctx, BUF_GATHER);
+    if (bytes[me]) CU_TRY(cudaMemcpyAsync(scratch + (size_t)me * mx, d_send, bytes[me], cudaMemcpyDeviceToDevice, ctx->stream));
+    NC_TRY(N.AllGather(scratch + (size_t)me * mx, scratch, mx, ncclUint8, c->nccl, ctx->stream));
+    gather_segs gs;
+    gs.world = W; gs.stride = mx;
+    for (int r = 0; r <= W; r++) gs.off[r] = off[r];
+    const size_t units = (off[W] + 7) / 8;
+    KT_LAUNCH(ctx, "gather_pack", k_gather_pack<<<b2m_cdiv(units, 256), 256, 0, ctx->stream>>>(scratch, (char *)d_recv, gs));
+    CU_TRY(cudaGetLastError());
     return B2M_OK;
   }
   local_group *g = c->grp;
@@ -220,6 +395,22 @@ int b2m_comm_allgatherv(b2m_ctx *ctx, b2m_comm *c, const void *d_send, void *d_r
   return B2M_OK;
 }
 
+// wait for the ctx stream from the host; in an NCCL group this polls the poison flag so that a failed peer cannot
+// leave this rank inside a collective that will never complete
+int b2m_comm_stream_wait(b2m_ctx *ctx, b2m_comm *c) {
+  if (!c || c->kind != 0 || !c->seg) { CU_TRY(cudaStreamSynchronize(ctx->stream)); return B2M_OK; }
+  for (unsigned spins = 0;; spins++) {
+    const cudaError_t e = cudaStreamQuery(ctx->stream);
+    if (e == cudaSuccess) return B2M_OK;
+    if (e != cudaErrorNotReady) { b2m_set_error("stream: %s", cudaGetErrorString(e)); return B2M_ECUDA; }
+    if ((spins & 63u) == 63u && c->seg->poison.load(std::memory_order_acquire)) {
+      nccl_abort(c);
+      b2m_set_error("nccl comm: another rank failed");
+      return B2M_ECUDA;
+    }
+  }
+}
+
 // the scalar blocks of all ranks -> pinned host (ctx->h_all[r]); also refreshes ctx->h_scalars
 int b2m_sync_scalars(b2m_ctx *ctx, b2m_comm *c) {
   const int W = b2m_comm_world(c);
@@ -231,7 +422,34 @@ int b2m_sync_scalars(b2m_ctx *ctx, b2m_comm *c) {
     ctx->h_all_cap = W;
   }
   const void *mine = ctx->buf[BUF_SCALARS].p;
+  if (c->kind == 0 && c->seg) {
+    if (c->aborted) { b2m_set_error("nccl comm: aborted after a rank failed"); return B2M_ECUDA; }
+    CU_TRY(cudaMemcpyAsync(ctx->h_scalars, mine, sizeof(b2m_scalars), cudaMemcpyDeviceToHost, ctx->stream));
+    B2M_TRY(b2m_comm_stream_wait(ctx, c));
+    const unsigned long long s = ++c->seq;
+    shm_slot *me = &c->seg->r[c->rank];
+    memcpy(&me->blk[s & 1], ctx->h_scalars, sizeof(b2m_scalars));
+    me->seq.store(s, std::memory_order_release);
+    struct timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < W; r++) {
+      shm_slot *o = &c->seg->r[r];
+      for (unsigned spins = 0; o->seq.load(std::memory_order_acquire) < s; spins++) {
+        if (spins < 4096) { asm volatile("pause" ::: "memory"); continue; }
+        if (c->seg->poison.load(std::memory_order_acquire)) { nccl_abort(c); b2m_set_error("nccl comm: another rank failed"); return B2M_ECUDA; }
+        sched_yield();
+        if ((spins & 0xffffu) == 0) {
+          struct timespec t1;
+          clock_gettime(CLOCK_MONOTONIC, &t1);
+          if (t1.tv_sec - t0.tv_sec > 180) { nccl_abort(c); b2m_set_error("nccl comm: rank %d did not reach sync %llu", r, s); return B2M_ECUDA; }
+        }
+      }
+      memcpy(&ctx->h_all[r], &o->blk[s & 1], sizeof(b2m_scalars));
+    }
+    return B2M_OK;
+  }
   if (c->kind == 0) {
+    if (c->aborted) { b2m_set_error("nccl comm: aborted after a rank failed"); return B2M_ECUDA; }
     NC_TRY(N.AllGather(mine, ctx->d_all, sizeof(b2m_scalars), ncclUint8, c->nccl, ctx->stream));
   } else {
     size_t bytes[64];

@@ -72,6 +72,8 @@ enum {
   BUF_SEAM0,       // slabs: CC seam lists (roots, dense ids, pairs, tables) carved per use
   BUF_SEAM1,
   BUF_SEAM2,
+  BUF_SEAMF,       // slabs: fast seam path (gathered blocks, replicated union-find, dense ticket planes)
+  BUF_GATHER,      // slabs: padded segments of a variable-length all-gather
   BUF_POST_INC,    // post-smooth: vertex -> (triangle, corner) incidence list
   BUF_POST_P,      // post-smooth: p / p' / b vertex arrays + border flags
   BUF_POST_V,      // post-smooth from host memory: device copy of the vertices
@@ -103,8 +105,15 @@ struct b2m_scalars {
   unsigned long long first_cube;         // min (row << 16 | x) over active cubes (classic pts[0])
   double pts0[3];                        // classic: first soup vertex (the weld's key origin)
   double v0[3];                          // slabs: this rank's first vertex (Lewiner key origin = global vertex 0)
-  unsigned long long best_seam;          // slabs: (size << 30) | (2^30-1 - seam id) of the largest seam component
-  unsigned int pad[24];
+  unsigned long long best_seam;          // slabs: largest seam component - slow path (size << 30) | (2^30-1 - seam id), fast path its size
+  unsigned long long best_seam_prio;     // slabs, fast path: (rank << 32 | run slot) of that component's first voxel
+  // connected components of >= 2^31 voxels: a node's count field holds 31 bits; every wrap is recorded here
+  // (at most two such components fit a slab of <= 2^32 voxels).  Reset before each labelling.
+  unsigned int carry_slot[4];            // root slot + 1 (0: free)
+  unsigned int carry_hi[4];              // wraps = units of 2^31 voxels
+  // weld bases of this rank (k_w_bases), read with the last host sync of the call instead of a sync of their own
+  unsigned int wb_new_e_off, wb_nve_new, wb_new_c_base, wb_nvc_new, wb_n_dead, wb_n_extra;
+  unsigned int pad[8];
 };
 static_assert(sizeof(b2m_scalars) == 256, "b2m_scalars is exchanged as one 256-byte block");
 
@@ -136,6 +145,11 @@ b2m_scalars *b2m_sc(b2m_ctx *ctx, b2m_comm *c, int rank);  // host copy of rank'
 int b2m_comm_exchange(b2m_ctx *ctx, b2m_comm *c, const void *d_send_up, size_t send_up_bytes, void *d_recv_lo,
                       size_t recv_lo_bytes, const void *d_send_dn, size_t send_dn_bytes, void *d_recv_hi,
                       size_t recv_hi_bytes);
+int b2m_comm_exchange_on(b2m_ctx *ctx, b2m_comm *c, cudaStream_t st, const void *d_send_up, size_t send_up_bytes, void *d_recv_lo,
+                         size_t recv_lo_bytes, const void *d_send_dn, size_t send_dn_bytes, void *d_recv_hi, size_t recv_hi_bytes);
+bool b2m_comm_async_capable(const b2m_comm *c);
+int b2m_comm_stream_wait(b2m_ctx *ctx, b2m_comm *c);  // host wait for the ctx stream that a failed peer can interrupt
+int b2m_comm_allgather_inplace(b2m_ctx *ctx, b2m_comm *c, void *d_buf, size_t bytes);  // rank r's block at d_buf + r * bytes
 // d_recv = concatenation over ranks of their d_send (bytes[r] each); every rank passes the same bytes[]
 int b2m_comm_allgatherv(b2m_ctx *ctx, b2m_comm *c, const void *d_send, void *d_recv, const size_t *bytes);
 int b2m_comm_gather_items(b2m_ctx *ctx, b2m_comm *c, unsigned n_local, b2m_item **items, unsigned *n);
@@ -168,6 +182,7 @@ struct b2m_ctx {
   b2m_scalars *h_scalars;  // pinned mirror
   uint64_t launches;
   int tables_ready;
+  int smooth_attr_done;    // the > 48 KB dynamic shared memory opt-in of the smooth kernel was made through this ctx
   int sm_count;
   unsigned ev_mask;        // which stage event pairs were recorded in the current call
   // host<->device staging for pageable host memory (b2m_copy_h2d / b2m_copy_d2h)
@@ -180,6 +195,8 @@ struct b2m_ctx {
   cudaEvent_t pend_ev[B2M_PEND_MAX + 1];  // [B2M_PEND_MAX] = start of the transfer
   int pend_zend[B2M_PEND_MAX];
   int pend_n, pend_last;   // chunks not yet consumed / index of the last chunk of the transfer
+  cudaStream_t aux_stream; // slabs: halo exchanges that run next to kernels of `stream` (high priority, created on demand)
+  cudaEvent_t aux_ev[2];
   int profile;             // record an event pair around every kernel launch
   int nkt, nkt_events;     // entries used in this call / event pairs created so far
   b2m_ktimer kt[B2M_KT_MAX];
@@ -200,6 +217,7 @@ template <typename T>
 static inline T *b2m_ptr(b2m_ctx *ctx, int which) {
   return reinterpret_cast<T *>(ctx->buf[which].p);
 }
+int b2m_aux_stream(b2m_ctx *ctx);     // creates ctx->aux_stream / aux_ev on first use
 int b2m_fetch_scalars(b2m_ctx *ctx);  // D2H of the scalar block + stream sync
 // bulk copies between device memory and ANY host memory (pinned: one DMA; pageable: pipelined through
 // pinned ring buffers with a multi-threaded host memcpy); synchronous on return
@@ -346,10 +364,12 @@ struct b2m_weld_out {
   unsigned int nv_local, nve_local, nvc_local, nx_local, nt_local;
   unsigned int v_edge_off, v_c_off;  // global welded index of the first own edge / centroid vertex
   unsigned int nv_global, n_dead, n_extra;
+  unsigned int n_items;  // weld items the run worked on (all ranks')
 };
 int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o,
                const b2m_front_out *fo, b2m_mesh_dev *mesh);
-int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items, b2m_weld_out *wo);
+int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items, b2m_weld_out *wo);   // enqueue only
+int b2m_weld_finish(b2m_ctx *ctx, b2m_comm *comm, const b2m_mesh_dev *mesh, b2m_weld_out *wo);        // after b2m_sync_scalars
 
 // generic primitives (scan.cu)
 int b2m_exclusive_scan_u32(b2m_ctx *ctx, const uint32_t *d_in, uint32_t *d_out, size_t n, uint32_t *d_total);

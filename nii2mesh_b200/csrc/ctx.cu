@@ -73,6 +73,11 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
       if (c->pend_ev[i]) cudaEventDestroy(c->pend_ev[i]);
     cudaStreamDestroy(c->copy_stream);
   }
+  if (c->aux_stream) {
+    cudaStreamSynchronize(c->aux_stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(c->aux_ev[i]);
+    cudaStreamDestroy(c->aux_stream);
+  }
   cudaFreeHost(c->h_scalars);
   if (c->h_all) { cudaFreeHost(c->h_all); cudaFree(c->d_all); }
   cudaStreamDestroy(c->stream);
@@ -163,32 +168,73 @@ static int stage_init(b2m_ctx *ctx) {
 }
 // multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded copy).
 // A small persistent pthread pool, not OpenMP: launchers such as torchrun export OMP_NUM_THREADS=1, and the copy
-// must not depend on the host program's OpenMP settings.  Slices of 4 MiB are handed out through an atomic counter;
-// the calling thread works too.  One job at a time (callers from several host threads serialise on the pool).
+// must not depend on the host program's OpenMP settings.  Slices of 1 MiB are handed out through an atomic counter;
+// the calling thread works too.  One job at a time: a job OWNS the pool (`busy`) from pool_acquire() to
+// pool_release(); ownership is a flag under a mutex, not a held mutex, so that a fire-and-forget job (the page
+// pre-fault of the output blocks) gives the pool back by itself when its last slice is done - no caller code runs
+// while the pool is owned on its behalf (several ranks of ONE process - local slab groups - share this pool and meet
+// in barriers in between).
+// Pool size: B2M_COPY_THREADS / b2m_set_copy_threads(), else (cores this process may run on) / (ranks on this node:
+// LOCAL_WORLD_SIZE as exported by torchrun), at most 16: eight ranks with sixteen threads each on a 32-core box spend
+// their time taking the cores from each other (SCALE_r01: D2H 34 ms at N=1, 271 ms at N=8).
+// Workers never spin: they sleep on a futex until the DMA chunk they need has landed.
+#include <linux/futex.h>
 #include <pthread.h>
 #include <sched.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
 #include <atomic>
 static inline void cpu_relax(void) { asm volatile("pause" ::: "memory"); }
+static inline void futex_wait(std::atomic<int> *addr, int seen) {
+  syscall(SYS_futex, reinterpret_cast<int *>(addr), FUTEX_WAIT_PRIVATE, seen, nullptr, nullptr, 0);
+}
+static inline void futex_wake_all(std::atomic<int> *addr) {
+  syscall(SYS_futex, reinterpret_cast<int *>(addr), FUTEX_WAKE_PRIVATE, 0x7fffffff, nullptr, nullptr, 0);
+}
 extern "C" void b2m_stream_copy(void *dst, const void *src, size_t n);  // hostcopy.c
 extern "C" void b2m_stream_widen(double *dst, const float *src, size_t n);
+static int g_copy_threads_req = 0;
+static int g_copy_threads = 0;  // fixed at the first bulk copy
+static int host_cores(void) {
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0) return c; }
+  const long c = sysconf(_SC_NPROCESSORS_ONLN);
+  return c > 0 ? (int)c : 1;
+}
 static int par_threads(void) {
-  static int n = 0;
-  if (!n) {
-    long c = sysconf(_SC_NPROCESSORS_ONLN);
-    const char *e = getenv("B2M_COPY_THREADS");
-    n = e ? atoi(e) : (int)(c > 16 ? 16 : c);
-    if (n < 1) n = 1;
-    if (n > 64) n = 64;
+  if (g_copy_threads) return g_copy_threads;
+  int n = g_copy_threads_req;
+  if (n <= 0) { const char *e = getenv("B2M_COPY_THREADS"); if (e) n = atoi(e); }
+  if (n <= 0) {
+    int local_world = 1;
+    const char *lw = getenv("B2M_LOCAL_WORLD");
+    if (!lw) lw = getenv("LOCAL_WORLD_SIZE");
+    if (lw && atoi(lw) > 0) local_world = atoi(lw);
+    n = host_cores() / local_world;
+    if (n > 16) n = 16;
   }
+  if (n < 1) n = 1;
+  if (n > 64) n = 64;
+  g_copy_threads = n;
   return n;
 }
+// threads of the host copy pool (the caller included); 0 = the default rule above.  Takes effect if called before the
+// first bulk copy of the process.
+extern "C" int b2m_set_copy_threads(int n) {
+  if (n < 0 || n > 64) return B2M_EARG;
+  g_copy_threads_req = n;
+  return g_copy_threads ? B2M_FAIL : B2M_OK;
+}
+extern "C" int b2m_get_copy_threads(void) { return par_threads(); }
 namespace {
 struct copy_pool {
-  pthread_mutex_t job_mu = PTHREAD_MUTEX_INITIALIZER;   // one job at a time
   pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-  pthread_cond_t cv_go = PTHREAD_COND_INITIALIZER, cv_done = PTHREAD_COND_INITIALIZER;
+  pthread_cond_t cv_go = PTHREAD_COND_INITIALIZER, cv_done = PTHREAD_COND_INITIALIZER, cv_free = PTHREAD_COND_INITIALIZER;
+  bool busy = false;           // a job owns the pool
+  bool auto_release = false;   // ... and gives it back itself when its last worker is done (touch jobs)
+  unsigned long long seq = 0, seq_done = 0;  // jobs started / auto-release jobs finished (ordered: one job at a time)
   char *dst = nullptr;
-  const char *src = nullptr;   // null: "touch" job - fault the pages of dst (and of dst2) in, one write per page
+  const char *src = nullptr;   // null: "touch" job - fault the pages of dst (and of dst2) in
   char *dst2 = nullptr;
   size_t n2 = 0;
   long long nslices1 = 0;
@@ -201,19 +247,33 @@ struct copy_pool {
   char *const *ring = nullptr;
   long long spc = 0;
   int widen = 0;  // the ring holds f32 values that land in dst as f64 (slices and p->n count OUTPUT bytes)
-  std::atomic<long long> ready{0};
+  std::atomic<int> ready{0};
   std::atomic<int> done[B2M_RING_SLOTS];
 } g_pool;
 
+static void touch_range(char *base, size_t len) {
+#ifdef MADV_POPULATE_WRITE
+  // one system call populates the page tables of the whole slice (Linux >= 5.14): no trap per page
+  const uintptr_t a = (uintptr_t)base & ~(uintptr_t)4095, e = ((uintptr_t)base + len + 4095) & ~(uintptr_t)4095;
+  static std::atomic<int> populate_ok{1};
+  if (populate_ok.load(std::memory_order_relaxed)) {
+    if (madvise((void *)a, e - a, MADV_POPULATE_WRITE) == 0) return;
+    populate_ok.store(0, std::memory_order_relaxed);
+  }
+#endif
+  for (size_t q = 0; q < len; q += 4096) ((volatile char *)base)[q] = 0;
+}
 static void pool_work(copy_pool *p) {
   for (;;) {
     const long long i = p->next.fetch_add(1);
     if (i >= p->nslices) break;
     if (p->ring) {
       const long long c = i / p->spc;
-      for (int spins = 0; p->ready.load(std::memory_order_acquire) <= c; spins++) {
-        if (spins < 2000) cpu_relax();
-        else sched_yield();
+      for (int spins = 0;; spins++) {
+        const int r = p->ready.load(std::memory_order_acquire);
+        if (r > c) break;
+        if (spins < 64) cpu_relax();
+        else futex_wait(&p->ready, r);  // returns at once if ready moved on in the meantime
       }
       const size_t o = (size_t)i * p->slice, oc = (size_t)(i - c * p->spc) * p->slice, len = p->n - o < p->slice ? p->n - o : p->slice;
       if (p->widen) b2m_stream_widen((double *)(p->dst + o), (const float *)(p->ring[c % B2M_RING_SLOTS] + oc / 2), len / 8);
@@ -226,8 +286,7 @@ static void pool_work(copy_pool *p) {
       char *base = i < p->nslices1 ? p->dst : p->dst2;
       const size_t tot = i < p->nslices1 ? p->n : p->n2;
       const size_t o = (size_t)(i < p->nslices1 ? i : i - p->nslices1) * p->slice;
-      const size_t len = tot - o < p->slice ? tot - o : p->slice;
-      for (size_t q = 0; q < len; q += 4096) ((volatile char *)base)[o + q] = 0;
+      touch_range(base + o, tot - o < p->slice ? tot - o : p->slice);
     }
   }
 }
@@ -241,19 +300,37 @@ static void *pool_main(void *arg) {
     pthread_mutex_unlock(&p->mu);
     pool_work(p);
     pthread_mutex_lock(&p->mu);
-    if (--p->running == 0) pthread_cond_signal(&p->cv_done);
+    if (--p->running == 0) {
+      if (p->auto_release) {  // a fire-and-forget job: the last worker hands the pool back
+        p->auto_release = false;
+        p->busy = false;
+        p->seq_done = p->seq;
+        pthread_cond_broadcast(&p->cv_free);
+      }
+      pthread_cond_broadcast(&p->cv_done);
+    }
   }
   return nullptr;
 }
 }  // namespace
-static void pool_start_locked(copy_pool *p, int nt) {  // job_mu held, job fields set
-  if (!p->started) {
-    for (int i = 0; i < nt - 1; i++) {
-      pthread_t t;
-      if (pthread_create(&t, nullptr, pool_main, p) == 0) { pthread_detach(t); p->started++; }
-    }
-    if (!p->started) p->started = -1;  // no workers: the caller works alone
+static void pool_acquire(copy_pool *p) {
+  pthread_mutex_lock(&p->mu);
+  while (p->busy) pthread_cond_wait(&p->cv_free, &p->mu);
+  p->busy = true;
+  p->auto_release = false;
+  p->seq++;
+  pthread_mutex_unlock(&p->mu);
+}
+static void pool_ensure_threads(copy_pool *p, int nt) {  // pool owned
+  if (p->started) return;
+  for (int i = 0; i < nt - 1; i++) {
+    pthread_t t;
+    if (pthread_create(&t, nullptr, pool_main, p) == 0) { pthread_detach(t); p->started++; }
   }
+  if (!p->started) p->started = -1;  // no workers: the caller works alone
+}
+static void pool_start(copy_pool *p, int nt) {  // pool owned, job fields set
+  pool_ensure_threads(p, nt);
   p->next.store(0);
   pthread_mutex_lock(&p->mu);
   p->running = p->started > 0 ? p->started : 0;
@@ -261,47 +338,93 @@ static void pool_start_locked(copy_pool *p, int nt) {  // job_mu held, job field
   pthread_cond_broadcast(&p->cv_go);
   pthread_mutex_unlock(&p->mu);
 }
-static void pool_finish_locked(copy_pool *p) {
+static void pool_finish(copy_pool *p) {  // wait for the workers of the job this thread started, then give the pool back
   pthread_mutex_lock(&p->mu);
   while (p->running > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+  p->busy = false;
+  pthread_cond_broadcast(&p->cv_free);
   pthread_mutex_unlock(&p->mu);
-  pthread_mutex_unlock(&p->job_mu);
 }
-// a touch job started by THIS thread still owns the pool (job_mu): it must be joined before the thread posts a copy
-static thread_local bool tl_touch_pending = false;
-void b2m_touch_wait(void);
 static void par_memcpy(void *dst, const void *src, size_t n) {
   copy_pool *p = &g_pool;
   const int nt = par_threads();
   if (nt <= 1 || n <= p->slice) { memcpy(dst, src, n); return; }
-  if (tl_touch_pending) b2m_touch_wait();
-  pthread_mutex_lock(&p->job_mu);
+  pool_acquire(p);
   p->dst = (char *)dst; p->src = (const char *)src; p->n = n; p->ring = nullptr; p->widen = 0;
   p->nslices = (long long)((n + p->slice - 1) / p->slice);
-  pool_start_locked(p, nt);
+  pool_start(p, nt);
   pool_work(p);
-  pool_finish_locked(p);
+  pool_finish(p);
 }
 // fault in the pages of two fresh host blocks on the pool threads while the caller does something else (the GPU
-// pipeline); b2m_touch_wait() must follow before the next bulk copy.  Returns 0 if nothing was started.
+// pipeline).  Fire and forget: the pool is released by its own last worker, so nobody else's copy ever waits for
+// code of the caller; b2m_touch_wait() only waits for THIS thread's last touch job.  Returns 0 if nothing was started.
+static thread_local unsigned long long tl_touch_seq = 0;
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
   copy_pool *p = &g_pool;
   const int nt = par_threads();
-  if (nt <= 1 || na + nb < ((size_t)64 << 20) || tl_touch_pending) return 0;
-  pthread_mutex_lock(&p->job_mu);
+  if (nt <= 1 || na + nb < ((size_t)64 << 20)) return 0;
+  pool_acquire(p);
   p->src = nullptr; p->ring = nullptr;
   p->dst = (char *)a; p->n = na; p->dst2 = (char *)b; p->n2 = nb;
   p->nslices1 = (long long)((na + p->slice - 1) / p->slice);
   p->nslices = p->nslices1 + (long long)((nb + p->slice - 1) / p->slice);
-  pool_start_locked(p, nt);
-  if (p->started <= 0) { pool_work(p); pool_finish_locked(p); return 0; }
-  tl_touch_pending = true;
+  pool_ensure_threads(p, nt);
+  if (p->started <= 0) { pool_start(p, nt); pool_work(p); pool_finish(p); return 0; }
+  pthread_mutex_lock(&p->mu);
+  p->auto_release = true;
+  tl_touch_seq = p->seq;
+  pthread_mutex_unlock(&p->mu);
+  pool_start(p, nt);
   return 1;
 }
 void b2m_touch_wait(void) {  // idempotent
-  if (!tl_touch_pending) return;
-  tl_touch_pending = false;
-  pool_finish_locked(&g_pool);
+  if (!tl_touch_seq) return;
+  copy_pool *p = &g_pool;
+  pthread_mutex_lock(&p->mu);
+  while (p->seq_done < tl_touch_seq) pthread_cond_wait(&p->cv_done, &p->mu);
+  pthread_mutex_unlock(&p->mu);
+  tl_touch_seq = 0;
+}
+
+// Self test of the pool without a GPU (tests/test_abi.py): `callers` host threads - the ranks of a single-process slab
+// group - each start a fire-and-forget pre-fault of two fresh blocks, meet in a barrier (the collective pipeline), copy
+// `bytes` through the pool and join their pre-fault.  With a pool that stayed locked until the pre-fault's owner came
+// back for it, the second caller never reached the barrier.  Returns 0 when every copy is exact.
+namespace {
+struct selftest_arg { pthread_barrier_t *bar; size_t bytes; int bad; };
+void *selftest_main(void *a_) {
+  selftest_arg *a = (selftest_arg *)a_;
+  const size_t n = a->bytes;
+  char *src = (char *)malloc(n), *dst = (char *)malloc(n), *t1 = (char *)malloc(n), *t2 = (char *)malloc(n);
+  a->bad = !src || !dst || !t1 || !t2;
+  if (!a->bad) {
+    for (size_t i = 0; i < n; i += 997) src[i] = (char)(i * 31u);
+    b2m_touch_async(t1, n, t2, n);
+    pthread_barrier_wait(a->bar);
+    par_memcpy(dst, src, n);
+    pthread_barrier_wait(a->bar);
+    b2m_touch_wait();
+    for (size_t i = 0; i < n; i += 997) a->bad |= dst[i] != (char)(i * 31u);
+  } else {
+    pthread_barrier_wait(a->bar);
+    pthread_barrier_wait(a->bar);
+  }
+  free(src); free(dst); free(t1); free(t2);
+  return nullptr;
+}
+}  // namespace
+extern "C" int b2m_pool_selftest(size_t bytes, int callers) {
+  if (callers < 1 || callers > 16 || bytes < 4096) return B2M_EARG;
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, (unsigned)callers);
+  selftest_arg args[16];
+  pthread_t th[16];
+  for (int i = 0; i < callers; i++) { args[i].bar = &bar; args[i].bytes = bytes; args[i].bad = 0; pthread_create(&th[i], nullptr, selftest_main, &args[i]); }
+  int bad = 0;
+  for (int i = 0; i < callers; i++) { pthread_join(th[i], nullptr); bad |= args[i].bad; }
+  pthread_barrier_destroy(&bar);
+  return bad ? B2M_FAIL : B2M_OK;
 }
 
 // Pageable destination: the DMA engine fills a ring of pinned 8 MiB chunks while the pool threads stream finished
@@ -333,8 +456,7 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
     return cudaEventRecord(ctx->ring_ev[c % B2M_RING_SLOTS], ctx->stream);
   };
   const int nt = par_threads();
-  if (tl_touch_pending) b2m_touch_wait();
-  pthread_mutex_lock(&p->job_mu);
+  pool_acquire(p);
   p->dst = (char *)h_dst; p->src = nullptr; p->n = bytes;
   p->nslices = (long long)((bytes + p->slice - 1) / p->slice);
   p->ring = ring; p->spc = (long long)(CH / p->slice); p->widen = widen;
@@ -360,14 +482,15 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
       must = false;
     }
   };
-  pool_start_locked(p, nt);
+  pool_start(p, nt);
   const bool alone = p->started <= 0;  // no worker threads: the caller copies chunk by chunk itself
   for (long long c = 0; c < nchunk && err == cudaSuccess; c++) {
     if (issued <= c) refill(true);
     if (err != cudaSuccess) break;
     err = cudaEventSynchronize(ctx->ring_ev[c % B2M_RING_SLOTS]);
     if (err != cudaSuccess) break;
-    p->ready.store(c + 1, std::memory_order_release);
+    p->ready.store((int)(c + 1), std::memory_order_release);
+    futex_wake_all(&p->ready);
     if (alone) {
       const size_t o = (size_t)c * CH;
       if (widen) b2m_stream_widen((double *)((char *)h_dst + o), (const float *)ring[c % B2M_RING_SLOTS], chunk_bytes(c) / 8);
@@ -376,9 +499,9 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
     }
     refill(false);
   }
-  if (err != cudaSuccess) p->ready.store(nchunk + 1, std::memory_order_release);  // release the workers; the copy is void anyway
+  if (err != cudaSuccess) { p->ready.store(0x7ffffff0, std::memory_order_release); futex_wake_all(&p->ready); }  // release the workers; the copy is void anyway
   if (alone) p->next.store(p->nslices);
-  pool_finish_locked(p);  // the next job of any kind resets p->ring under job_mu
+  pool_finish(p);  // the next job of any kind resets p->ring while it owns the pool
   CU_TRY(err);
   return B2M_OK;
 }
@@ -469,6 +592,15 @@ int b2m_copy_h2d(b2m_ctx *ctx, void *d_dst, const void *h_src, size_t bytes) {
     CU_TRY(cudaEventRecord(ctx->stage_ev[c % 3], ctx->stream));
   }
   CU_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2M_OK;
+}
+
+int b2m_aux_stream(b2m_ctx *ctx) {
+  if (ctx->aux_stream) return B2M_OK;
+  int lo = 0, hi = 0;
+  CU_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = the numerically smallest = highest priority
+  CU_TRY(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, hi));
+  for (int i = 0; i < 2; i++) CU_TRY(cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming));
   return B2M_OK;
 }
 

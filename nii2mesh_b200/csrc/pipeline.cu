@@ -92,6 +92,7 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
     src.main = d_img; src.n_main = sl.nzl; src.rz0 = sl.z0; src.gnz = sl.gnz;
     src.lo = src.hi = d_img;
     src.oz0 = sl.ez0; src.onz = sl.nze;
+    bool halo_async = false;
     if (slabs) {
       // 3 raw planes from each neighbour: the halo plane of S is recomputed here bit-for-bit (2 for the
       // z taps of that plane + the plane itself)
@@ -99,8 +100,19 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
       B2M_TRY(b2m_reserve(ctx, BUF_HALO_LO, 3 * nxy * 4));
       B2M_TRY(b2m_reserve(ctx, BUF_HALO_HI, 3 * nxy * 4));
       float *hlo = b2m_ptr<float>(ctx, BUF_HALO_LO), *hhi = b2m_ptr<float>(ctx, BUF_HALO_HI);
-      B2M_TRY(b2m_comm_exchange(ctx, comm, d_img + (size_t)(sl.nzl - 3) * nxy, sl.hh ? 3 * nxy * 4 : 0, hlo, nl * nxy * 4,
-                                d_img, sl.hl ? 3 * nxy * 4 : 0, hhi, nh * nxy * 4));
+      // NCCL: the exchange runs on a stream of its own while the ctx stream smooths the planes that need own raw
+      // planes only; the few planes next to the seams follow once the halo has arrived
+      halo_async = b2m_comm_async_capable(comm) && sl.nzl >= 16;
+      cudaStream_t xs = ctx->stream;
+      if (halo_async) {
+        B2M_TRY(b2m_aux_stream(ctx));
+        xs = ctx->aux_stream;
+        CU_TRY(cudaEventRecord(ctx->aux_ev[0], ctx->stream));  // whatever produced d_img / last read the halo buffers
+        CU_TRY(cudaStreamWaitEvent(xs, ctx->aux_ev[0], 0));
+      }
+      B2M_TRY(b2m_comm_exchange_on(ctx, comm, xs, d_img + (size_t)(sl.nzl - 3) * nxy, sl.hh ? 3 * nxy * 4 : 0, hlo, nl * nxy * 4,
+                                   d_img, sl.hl ? 3 * nxy * 4 : 0, hhi, nh * nxy * 4));
+      if (halo_async) CU_TRY(cudaEventRecord(ctx->aux_ev[1], xs));
       src.lo = hlo; src.n_lo = nl; src.hi = hhi; src.n_hi = nh; src.rz0 = sl.z0 - nl;
     }
     if (!slabs && ctx->pend_n > 0) {
@@ -118,6 +130,20 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
         }
       }
       ctx->pend_n = 0;
+    } else if (halo_async) {
+      // output planes [ia, ib) read own raw planes only (z-2 .. z+2 inside [z0, z0+nzl), or clipped by the volume)
+      const int ia = sl.hl ? sl.z0 + 2 : sl.ez0, ib = sl.hh ? sl.z0 + sl.nzl - 2 : sl.ez0 + sl.nze;
+      src.oz0 = ia; src.onz = ib - ia;
+      B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)(ia - sl.ez0) * nxy, g, d_sc));
+      CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
+      if (sl.hl) {
+        src.oz0 = sl.ez0; src.onz = ia - sl.ez0;
+        B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));
+      }
+      if (sl.hh) {
+        src.oz0 = ib; src.onz = sl.ez0 + sl.nze - ib;
+        B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)(ib - sl.ez0) * nxy, g, d_sc));
+      }
     } else {
       B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));  // range reduction fused (halo planes are other ranks' planes: harmless)
     }
@@ -232,19 +258,16 @@ static int meshify_slab_impl(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, c
   }
   B2M_TRY(b2m_weld_run(ctx, comm, &mesh, 0, wo));
   ctx->ev_mask |= (1u << B2M_T_WELD) | (1u << B2M_T_DEGEN);
-  // global triangle count / offsets
+  B2M_TRY(stage_end(ctx, B2M_T_TOTAL));
+  // the last host round trip of the call: weld bases, surviving triangles (of every rank), consistency flags
+  B2M_TRY(b2m_sync_scalars(ctx, comm));
+  B2M_TRY(b2m_weld_finish(ctx, comm, &mesh, wo));
   unsigned long long NTk = 0;
   unsigned t_off_new = 0;
-  if (sl.world > 1) {
-    B2M_TRY(b2m_sync_scalars(ctx, comm));
-    for (int r = 0; r < sl.world; r++) {
-      if (r == sl.rank) t_off_new = (unsigned)NTk;
-      NTk += b2m_sc(ctx, comm, r)->n_tri_kept;
-    }
-  } else {
-    NTk = wo->nt_local;
+  for (int r = 0; r < sl.world; r++) {
+    if (r == sl.rank) t_off_new = (unsigned)NTk;
+    NTk += b2m_sc(ctx, comm, r)->n_tri_kept;
   }
-  B2M_TRY(stage_end(ctx, B2M_T_TOTAL));
   B2M_TRY(collect_times(ctx, res));
   res->nverts = (int)wo->nv_global;
   res->ntris = (int)NTk;
@@ -252,7 +275,6 @@ static int meshify_slab_impl(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, c
   res->ndegenerate = (int)(mesh.NT - NTk);
   res->d_verts = wo->verts;
   res->d_tris = wo->tris;
-  wo->n_extra = wo->n_extra;
   ctx->slab_t_off = t_off_new;
   if (o->verbose && talk) {
     if (wo->n_dead) printf("vertex welding %d -> %d: %ld ms\n", res->pre_nverts, res->nverts, lroundf(res->ms[B2M_T_WELD]));
@@ -292,8 +314,10 @@ extern "C" int b2m_meshify_slab(b2m_ctx *ctx, b2m_comm *comm, const float *d_sla
     rc = B2M_EARG;
   }
   if (rc == B2M_OK && W > 1 && nzl < 4) { b2m_set_error("slabs need at least 4 planes each"); rc = B2M_EARG; }
-  if (rc == B2M_OK && (unsigned long long)gdims[0] * gdims[1] * (nzl + 2) > 0x7fffffffull) {
-    b2m_set_error("slab of more than 2^31-1 voxels");
+  // a slab holds at most 2^32 voxels (2^27 bit words: run slots stay below 2^31), the whole volume whatever the ranks
+  // can hold; mesh counts are checked against the int counts of the API where they are known (b2m_mc_run)
+  if (rc == B2M_OK && ((unsigned long long)((gdims[0] + 31) / 32) * gdims[1] * nzl > (1ull << 27))) {
+    b2m_set_error("slab of more than 2^27 bit words (2^32 voxels)");
     rc = B2M_EARG;
   }
   if (rc != B2M_OK) { b2m_comm_abort(comm); return rc; }
@@ -397,9 +421,10 @@ extern "C" int b2m_meshify_host(b2m_ctx *ctx, const float *h_img, const int64_t 
   memset(&ho, 0, sizeof(ho));
   host_out_early(ctx, &ho, n);
   const double t0 = wall_ms();
-  // experimental: B2M_H2D_OVERLAP=1 sends a pinned volume up in z-chunks on a second stream and lets the smooth follow it
-  static const bool want_overlap = getenv("B2M_H2D_OVERLAP") && atoi(getenv("B2M_H2D_OVERLAP")) > 0;
-  const bool overlap = want_overlap && opts->pre_smooth && dims[0] >= 5 && dims[1] >= 5 && dims[2] >= 64 && b2m_host_is_pinned(h_img);
+  // a pinned volume goes up in z-chunks on a second stream and the smooth follows it (B2M_H2D_OVERLAP=0: one plain copy)
+  static const bool want_overlap = !(getenv("B2M_H2D_OVERLAP") && atoi(getenv("B2M_H2D_OVERLAP")) == 0);
+  const bool overlap = want_overlap && opts->pre_smooth && dims[0] >= 5 && dims[1] >= 5 && dims[2] >= 64 && n * 4 >= ((size_t)256 << 20) &&
+                       b2m_host_is_pinned(h_img);
   int rc = overlap ? b2m_h2d_chunked_begin(ctx, b2m_ptr<float>(ctx, BUF_INPUT), h_img, (size_t)dims[0] * dims[1], (int)dims[2])
                    : b2m_copy_h2d(ctx, ctx->buf[BUF_INPUT].p, h_img, n * 4);
   const double t1 = wall_ms();
@@ -599,6 +624,8 @@ extern "C" int b2m_stage_weld(b2m_ctx *ctx, double *h_verts, int *h_tris, int *n
   b2m_weld_out wo;
   memset(&wo, 0, sizeof(wo));
   B2M_TRY(b2m_weld_run(ctx, nullptr, &mesh, 1, &wo));
+  B2M_TRY(b2m_fetch_scalars(ctx));
+  B2M_TRY(b2m_weld_finish(ctx, nullptr, &mesh, &wo));
   b2m_result res;
   memset(&res, 0, sizeof(res));
   res.d_verts = wo.verts; res.d_tris = wo.tris; res.nverts = (int)wo.nv_local; res.ntris = (int)wo.nt_local;

@@ -393,18 +393,20 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
   float vmin = INFINITY, vmax = -INFINITY;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t n4 = n / 4;
-  const float4 *in4 = reinterpret_cast<const float4 *>(in);
+  // 16-byte vector loads on the aligned middle; the (at most 3) voxels before the first aligned address and the tail go
+  // one by one: callers hand in any 4-byte aligned pointer (a slab that starts at plane z0 of a volume whose plane
+  // size is not a multiple of 4, a cropped atlas box)
+  const size_t head = min(n, (size_t)((16u - (unsigned)(reinterpret_cast<uintptr_t>(in) & 15u)) & 15u) / 4);
+  const size_t n4 = (n - head) / 4;
+  const float4 *in4 = reinterpret_cast<const float4 *>(in + head);
   for (size_t k = i; k < n4; k += stride) {
     float4 v = __ldg(in4 + k);
     vmin = fminf(fminf(vmin, v.x), fminf(v.y, fminf(v.z, v.w)));
     vmax = fmaxf(fmaxf(vmax, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
   }
-  for (size_t k = n4 * 4 + i; k < n; k += stride) {
-    float v = in[k];
-    vmin = fminf(vmin, v);
-    vmax = fmaxf(vmax, v);
-  }
+  const size_t tail0 = head + n4 * 4;  // head and tail hold at most 3 voxels each: threads 0..2 of the grid take them
+  if (i < head) { const float v = in[i]; vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
+  if (tail0 + i < n) { const float v = in[tail0 + i]; vmin = fminf(vmin, v); vmax = fmaxf(vmax, v); }
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
     vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
@@ -542,12 +544,10 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
   const bool vec = (g.nx % 4 == 0) && (((uintptr_t)src.main | (uintptr_t)src.lo | (uintptr_t)src.hi | (uintptr_t)d_out) % 16 == 0);
   // more than 48 KB of dynamic shared memory: opt in once PER DEVICE (function attributes belong to the device's
   // context; one process may drive several GPUs - local slab groups, atlas threads)
-  static bool attr_done[64] = {};
-  const int dv = ctx->device >= 0 && ctx->device < 64 ? ctx->device : 63;
-  if (!attr_done[dv] || dv == 63) {
+  if (!ctx->smooth_attr_done) {  // per ctx (= per host thread and device): no shared flag to race on
     CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
     CU_TRY(cudaFuncSetAttribute(k_smooth3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
-    attr_done[dv] = true;
+    ctx->smooth_attr_done = 1;
   }
   if (vec)
     KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));

@@ -267,7 +267,7 @@ struct weld_geom {
 struct weld_bases {  // computed on the device by k_w_bases, read back once
   uint32_t new_e_off, nve_new, new_c_base, nvc_new, n_dead, n_extra, pad[2];
 };
-__global__ void k_w_bases(weld_geom g, weld_tables w, const uint32_t *n_dead, const uint32_t *n_extra, weld_bases *out) {
+__global__ void k_w_bases(weld_geom g, weld_tables w, const uint32_t *n_dead, const uint32_t *n_extra, weld_bases *out, b2m_scalars *sc) {
   bool d;
   const uint32_t a = g.e_off - dead_below(w, g.e_off, &d);
   const uint32_t b = (g.e_off + g.nv_edge) - dead_below(w, g.e_off + g.nv_edge, &d);
@@ -276,6 +276,9 @@ __global__ void k_w_bases(weld_geom g, weld_tables w, const uint32_t *n_dead, co
   out->new_e_off = a; out->nve_new = b - a; out->new_c_base = c; out->nvc_new = e - c;
   out->n_dead = n_dead ? *n_dead : 0; out->n_extra = n_extra ? *n_extra : 0;
   out->pad[0] = out->pad[1] = 0;
+  // the host reads them with the last sync of the call (b2m_weld_finish)
+  sc->wb_new_e_off = a; sc->wb_nve_new = b - a; sc->wb_new_c_base = c; sc->wb_nvc_new = e - c;
+  sc->wb_n_dead = out->n_dead; sc->wb_n_extra = out->n_extra;
 }
 
 // own vertices -> compacted local array [edge block | centroid block | extras (last rank)]
@@ -463,6 +466,10 @@ struct carve {
   }
 };
 
+// Enqueues the whole weld + triangle clean-up without waiting for the device: every count the host needs afterwards
+// (weld bases, surviving triangles, consistency flags) is left in the scalar block, which the caller fetches with ONE
+// synchronisation (b2m_sync_scalars) before b2m_weld_finish() turns it into the b2m_weld_out.  Buffers whose exact size
+// is only known on the device are reserved at their upper bounds.
 int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items, b2m_weld_out *wo) {
   b2m_scalars *d_sc = b2m_ptr<b2m_scalars>(ctx, BUF_SCALARS);
   const unsigned nvl = mesh->nv_edge + mesh->nv_c, nt = mesh->nt;
@@ -479,6 +486,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
   g.classic_soup = mesh->classic_soup;
   weld_tables w;
   memset(&w, 0, sizeof(w));
+  memset(wo, 0, sizeof(*wo));
 
   // ---- the item set (all ranks' items, identical on every rank) ----
   b2m_item *items = nullptr;
@@ -492,8 +500,8 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
     B2M_TRY(b2m_comm_gather_items(ctx, comm, mesh->nitems, &items, &n));
   }
   double *verts = mesh->verts;
-  unsigned nv_out_local = nvl, n_dead = 0, n_extra = 0;
-  unsigned new_e_off = mesh->e_off, nve_new = mesh->nv_edge, new_c_base = g.c_base, nvc_new = mesh->nv_c;
+  wo->verts = verts;
+  wo->n_items = n;
   if (n >= 2) {
     const unsigned nbQ = (unsigned)((((uint64_t)(mesh->classic_soup ? 3ull * mesh->NT : g.NV)) >> WB_SHIFT) + 2);
     const unsigned nbP = (unsigned)(((uint64_t)g.NV >> WB_SHIFT) + 2);
@@ -544,61 +552,58 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
     KT_LAUNCH(ctx, "weld_table", k_w_table<<<b2m_cdiv(nbQ, 256), 256, 0, ctx->stream>>>(S_id, nullptr, n, Q, nbQ));
     w.Q = Q; w.S_id = S_id; w.P = P; w.R_vid = R_vid; w.S_out = S_out; w.S_top = S_top; w.S_pos = S_pos;
     KT_LAUNCH(ctx, "weld_out", k_w_item_out<<<nb, 256, 0, ctx->stream>>>(n, inv, head, top, cslot, w, g.NV, d_cnt + 2, S_out, S_top));
-    KT_LAUNCH(ctx, "weld_out", k_w_bases<<<1, 1, 0, ctx->stream>>>(g, w, d_cnt + 2, d_cnt + 0, d_bs));
+    KT_LAUNCH(ctx, "weld_out", k_w_bases<<<1, 1, 0, ctx->stream>>>(g, w, d_cnt + 2, d_cnt + 0, d_bs, d_sc));
     CU_TRY(cudaGetLastError());
-    weld_bases hb;
-    CU_TRY(cudaMemcpyAsync(&hb, d_bs, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(cudaStreamSynchronize(ctx->stream));
-    n_dead = hb.n_dead; n_extra = hb.n_extra;
-    new_e_off = hb.new_e_off; nve_new = hb.nve_new; new_c_base = hb.new_c_base; nvc_new = hb.nvc_new;
-    if (n_dead == 0 && n_extra == 0) {
-      // nothing merged ("Unify vertices found no shared vertices", src/meshify.c:82-87): ids unchanged
-      w.P = nullptr; w.R_vid = nullptr; w.Q = nullptr; w.S_id = nullptr;
-    } else {
-      nv_out_local = nve_new + nvc_new + (g.last_rank ? n_extra : 0);
-      B2M_TRY(b2m_reserve(ctx, BUF_VERTS2, (size_t)nv_out_local * 24));
-      double *v2 = b2m_ptr<double>(ctx, BUF_VERTS2);
-      KT_LAUNCH(ctx, "compact_verts", k_compact_verts<<<b2m_cdiv(nvl, 256), 256, 0, ctx->stream>>>(verts, v2, g, w, d_bs));
-      if (mesh->classic_soup)
-        KT_LAUNCH(ctx, "weld_patch", k_w_patch<<<nb, 256, 0, ctx->stream>>>(n, head, top, cslot, g, w, d_bs, v2));
-      wo->verts = v2;
-    }
+    // the compaction runs whether or not anything merged (with no dead ids and no extras it is a plain copy): that is
+    // only known on the device here.  Upper bound of the output: every own vertex + every item as an extra
+    B2M_TRY(b2m_reserve(ctx, BUF_VERTS2, ((size_t)nvl + (g.last_rank ? n : 0)) * 24));
+    double *v2 = b2m_ptr<double>(ctx, BUF_VERTS2);
+    KT_LAUNCH(ctx, "compact_verts", k_compact_verts<<<b2m_cdiv(nvl, 256), 256, 0, ctx->stream>>>(verts, v2, g, w, d_bs));
+    if (mesh->classic_soup)
+      KT_LAUNCH(ctx, "weld_patch", k_w_patch<<<nb, 256, 0, ctx->stream>>>(n, head, top, cslot, g, w, d_bs, v2));
+    wo->verts = v2;
   }
-  if (!wo->verts) wo->verts = verts;
   CU_TRY(cudaEventRecord(e1, ctx->stream));
   CU_TRY(cudaEventRecord(e2, ctx->stream));
   // ---- degenerate triangles ----
-  int *tris = mesh->tris;
-  unsigned nt_out = nt;
+  wo->tris = mesh->tris;
   if (nt > 0) {
     const size_t nw32 = ((size_t)nt + 31) / 32;
     B2M_TRY(b2m_reserve(ctx, BUF_FLAGS, nw32 * 12 + 64));
     uint32_t *kb = b2m_ptr<uint32_t>(ctx, BUF_FLAGS), *kc = kb + nw32, *ks = kc + nw32;
-    KT_LAUNCH(ctx, "tri_degen", k_tri_degen<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(tris, nt, verts, mesh->halo_verts, mesh->nearbits, g, w, kb, kc, ks, &d_sc->overflow));
+    KT_LAUNCH(ctx, "tri_degen", k_tri_degen<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(mesh->tris, nt, verts, mesh->halo_verts, mesh->nearbits, g, w, kb, kc, ks, &d_sc->overflow));
     B2M_TRY(b2m_exclusive_scan_u32(ctx, kc, kc, nw32, &d_sc->n_tri_kept));
-    CU_TRY(cudaGetLastError());
-    B2M_TRY(b2m_fetch_scalars(ctx));
-    if (ctx->h_scalars->overflow & 2u) { b2m_set_error("weld: triangle references a vertex outside this rank's blocks"); return B2M_ECUDA; }
-    nt_out = ctx->h_scalars->n_tri_kept;
-    if (nt_out != nt || w.Q || w.P) {  // something to drop or to renumber: one pass does both
-      B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)(nt_out ? nt_out : 1) * 12));
-      int *t2 = b2m_ptr<int>(ctx, BUF_TRIS2);
-      KT_LAUNCH(ctx, "tri_finish", k_tri_finish<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(tris, t2, kb, kc, ks, nt, g, w));
-      tris = t2;
-    }
+    // drop + renumber in one pass; the output is reserved for every triangle (how many survive is on the device)
+    B2M_TRY(b2m_reserve(ctx, BUF_TRIS2, (size_t)nt * 12));
+    int *t2 = b2m_ptr<int>(ctx, BUF_TRIS2);
+    KT_LAUNCH(ctx, "tri_finish", k_tri_finish<<<b2m_cdiv(nt, TRI_PER_BLOCK), 256, 0, ctx->stream>>>(mesh->tris, t2, kb, kc, ks, nt, g, w));
+    wo->tris = t2;
+  } else {
+    CU_TRY(cudaMemsetAsync(&d_sc->n_tri_kept, 0, 4, ctx->stream));
   }
   CU_TRY(cudaEventRecord(e3, ctx->stream));
   CU_TRY(cudaGetLastError());
-  wo->tris = tris;
-  wo->nv_local = nv_out_local;
-  wo->nve_local = nve_new;
-  wo->nvc_local = nvc_new;
-  wo->nx_local = g.last_rank ? n_extra : 0;
-  wo->nt_local = nt_out;
-  wo->v_edge_off = new_e_off;
-  wo->v_c_off = new_c_base;
-  wo->nv_global = g.NV - n_dead + n_extra;
-  wo->n_dead = n_dead;
-  wo->n_extra = n_extra;
+  return B2M_OK;
+}
+
+// after the caller's b2m_sync_scalars(): the counts of this rank's welded blocks
+int b2m_weld_finish(b2m_ctx *ctx, b2m_comm *comm, const b2m_mesh_dev *mesh, b2m_weld_out *wo) {
+  const b2m_scalars *h = ctx->h_scalars;
+  if (h->overflow & 2u) { b2m_set_error("weld: triangle references a vertex outside this rank's blocks"); return B2M_ECUDA; }
+  const bool last_rank = b2m_comm_rank(comm) == b2m_comm_world(comm) - 1;
+  const unsigned NV = mesh->NVE + mesh->NVC;
+  if (wo->n_items >= 2) {
+    wo->n_dead = h->wb_n_dead; wo->n_extra = h->wb_n_extra;
+    wo->nve_local = h->wb_nve_new; wo->nvc_local = h->wb_nvc_new;
+    wo->v_edge_off = h->wb_new_e_off; wo->v_c_off = h->wb_new_c_base;
+  } else {
+    wo->n_dead = wo->n_extra = 0;
+    wo->nve_local = mesh->nv_edge; wo->nvc_local = mesh->nv_c;
+    wo->v_edge_off = mesh->e_off; wo->v_c_off = mesh->NVE + mesh->c_off;
+  }
+  wo->nx_local = last_rank ? wo->n_extra : 0;
+  wo->nv_local = wo->nve_local + wo->nvc_local + wo->nx_local;
+  wo->nt_local = h->n_tri_kept;
+  wo->nv_global = NV - wo->n_dead + wo->n_extra;
   return B2M_OK;
 }

@@ -13,6 +13,7 @@ legs may import this package.  The product (``nii2mesh_b200``) never does.
 """
 import ctypes as C
 import os
+import sys
 import subprocess
 from pathlib import Path
 
@@ -289,17 +290,45 @@ class Ref:
         return v
 
     def meshify(self, vol, iso, original_mc=0, pre_smooth=True, only_largest=True, fill_bubbles=False,
-                return_img=False):
+                return_img=False, counts=False):
+        """counts=True: run verbose with the process's stdout (fd 1) redirected to a temporary file and parse the
+        reference's own diagnostics (src/meshify.c:84,104,166,318) -> pre_nv, pre_nt, iso_reset.  NOT thread-safe
+        (fd 1 is process-wide): callers that want parallelism use processes."""
         v = _f32(vol).copy()
         nz, ny, nx = v.shape
         dim = (C.c_short * 3)(nx, ny, nz)
         pp, pt, nv, nt = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
-        rc = self.lib.meshify(v.ctypes.data, dim, int(original_mc), iso, C.byref(pt), C.byref(pp), C.byref(nt),
-                              C.byref(nv), bool(pre_smooth), bool(only_largest), bool(fill_bubbles), False)
+        log = ""
+        if counts:
+            import tempfile
+            _libc.fflush(None)
+            sys.stdout.flush()
+            tmp = tempfile.TemporaryFile(mode="w+b")
+            saved = os.dup(1)
+            os.dup2(tmp.fileno(), 1)
+        try:
+            rc = self.lib.meshify(v.ctypes.data, dim, int(original_mc), iso, C.byref(pt), C.byref(pp), C.byref(nt),
+                                  C.byref(nv), bool(pre_smooth), bool(only_largest), bool(fill_bubbles), bool(counts))
+        finally:
+            if counts:
+                _libc.fflush(None)
+                os.dup2(saved, 1)
+                os.close(saved)
+                tmp.seek(0)
+                log = tmp.read().decode(errors="replace")
+                tmp.close()
         if rc:
-            return dict(rc=rc)
+            return dict(rc=rc, log=log)
         verts, tris = _take_mesh(_libc.free, pp, pt, nv.value, nt.value)
         out = dict(rc=0, verts=verts, tris=tris)
         if return_img:
             out["img"] = v
+        if counts:
+            import re
+            m = re.search(r"vertex welding (\d+) -> (\d+)", log)
+            out["pre_nv"] = int(m.group(1)) if m else len(verts)
+            m = re.search(r"remove degenerate triangles (\d+) -> (\d+)", log)
+            out["pre_nt"] = int(m.group(1)) if m else len(tris)
+            out["iso_reset"] = "Suggested isolevel out of range" in log
+            out["log"] = log
         return out

@@ -8,6 +8,11 @@
 #   libref_classic.so : same with -DUSE_CLASSIC_CUBES oldcubes.c                (default make)
 #   mctest            : MarchingCubes.c self-test (10 analytic 60^3 surfaces)
 #   nii2mesh_lewiner / nii2mesh_classic : the reference CLI
+#   nii2mesh_b2m      : the reference CLI (main(), flag parsing, load_nii, atlas loop, nii2(), every mesh writer, quadric
+#                       simplification - all from the reference's own sources, untouched) linked against libb2m.so for
+#                       meshify(), setThreshold() and laplacian_smoothHC(): the drop-in of INTEGRATION.md section 2,
+#                       exercised by tests/test_cli_dropin.py.  No reference hot-path object is linked: the macro renames
+#                       below only move the reference's OWN definitions out of the way inside their translation units.
 # meshify.c alone is compiled with -Dstatic= so that its file-local stage functions
 # (quick_smooth, dilate, unify_vertices, remove_degenerate_triangles) are callable from tests.
 set -euo pipefail
@@ -34,5 +39,21 @@ gcc -O3 -DMC_SELF_TEST "$SRC/MarchingCubes.c" -o "$OUT/mctest" -lm 2>/dev/null
 L="isolevel.c meshify.c quadric.c bwlabel.c radixsort.c nii2mesh.c base64.c"
 (cd "$SRC" && gcc -O3 -DNII2MESH $L -DHAVE_FORMATS MarchingCubes.c -lm -lz -DHAVE_ZLIB -o "$OUT/nii2mesh_lewiner" 2>/dev/null)
 (cd "$SRC" && gcc -O3 -DNII2MESH $L -DHAVE_FORMATS -DUSE_CLASSIC_CUBES oldcubes.c -lm -lz -DHAVE_ZLIB -o "$OUT/nii2mesh_classic" 2>/dev/null)
+# ---- the drop-in build: reference CLI + writers over libb2m.so ----
+B2M="$(cd "$HERE/../nii2mesh_b200" && pwd)"
+if [ -f "$B2M/libb2m.so" ]; then
+  O="$OUT/obj_d"; mkdir -p "$O"
+  DF="-O3 -DNII2MESH -DHAVE_ZLIB -DHAVE_FORMATS -I$SRC -ffunction-sections -fdata-sections"
+  # meshify.c holds the ten mesh writers AND the CPU hot path: its meshify() and the host utilities the library also
+  # exports are renamed inside this translation unit only, so every call from nii2mesh.c binds to libb2m.so
+  gcc $DF -Dmeshify=ref_cpu_meshify -Dapply_sform=ref_cpu_apply_sform -c "$SRC/meshify.c" -o "$O/meshify_io.o" 2>/dev/null
+  # quadric.c: the edge-collapse simplification stays the reference's; its Laplacian smooth yields to the library's
+  gcc $DF -Dlaplacian_smoothHC=ref_cpu_laplacian_smoothHC -c "$SRC/quadric.c" -o "$O/quadric.o" 2>/dev/null
+  for f in nii2mesh.c base64.c bwlabel.c radixsort.c MarchingCubes.c; do gcc $DF -c "$SRC/$f" -o "$O/${f%.c}.o" 2>/dev/null; done
+  # (bwlabel / radixsort / MarchingCubes only satisfy the references of the renamed, never-called ref_cpu_meshify;
+  #  --gc-sections drops them from the binary.  isolevel.c is NOT linked: setThreshold() comes from libb2m.so)
+  gcc -o "$OUT/nii2mesh_b2m" "$O"/*.o -Wl,--gc-sections -L"$B2M" -lb2m -Wl,-rpath,'$ORIGIN/../../nii2mesh_b200' -lm -lz
+  rm -rf "$O"
+fi
 rm -rf "$OUT/obj_l" "$OUT/obj_c"
 ls -la "$OUT"

@@ -6,7 +6,7 @@
  * are compared against in tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.
  *
  * PINNING: this restatement is pinned bit-for-bit against the unmodified reference compiled by
- * oracle/build_ref.sh into oracle/_ref/libref_{lewiner,classic}.so (tests/test_oracle_vs_ref.py)
+ * oracle/build_ref.sh into oracle/_ref/libref_{lewiner,classic}.so (tests/test_oracle.py)
  * and against golden vectors generated from that build (tests/golden/, tools/make_golden.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fPIC -shared oracle.c -o liboracle.so -lm
@@ -122,6 +122,7 @@ int orc_cc_label(const uint8_t *bw, uint32_t *lab, int nx, int ny, int nz, int c
 /* src/bwlabel.c:429-476 (bwlabelCore): label img!=0; onlyLargest keeps the label with the most
  * voxels, strict '>' so ties go to the lowest label (:462-466), output 0/1. */
 int orc_bwlabel_core(float *img, int conn, int nx, int ny, int nz, int onlyLargest) {
+  if (nx < 2 || ny < 2 || nz < 1) return 0; /* :434-437: refused, img left as it is ("must be 2 or 3-dimensional") */
   size_t n = (size_t)nx * ny * nz;
   uint8_t *bw = (uint8_t *)malloc(n);
   uint32_t *lab = (uint32_t *)malloc(n * sizeof(uint32_t));
@@ -149,6 +150,7 @@ int orc_bwlabel_core(float *img, int conn, int nx, int ny, int nz, int onlyLarge
  * there is at most one background component (:488-491); then the foreground labelling. */
 int orc_bwlabel(float *img, int conn, int nx, int ny, int nz, int onlyLargest, int fillBubbles) {
   if (!fillBubbles) return orc_bwlabel_core(img, conn, nx, ny, nz, onlyLargest);
+  if (nx < 2 || ny < 2 || nz < 1) return 0; /* both bwlabelCore calls refuse: no bubbles (:488-491), mask untouched */
   size_t n = (size_t)nx * ny * nz, nxy = (size_t)nx * ny;
   uint8_t *bw = (uint8_t *)malloc(n);
   uint32_t *lab = (uint32_t *)malloc(n * sizeof(uint32_t));

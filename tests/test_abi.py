@@ -139,3 +139,16 @@ def test_host_copy_kernels(libb2m):
             libb2m.b2m_stream_widen(dst.ctypes.data + 8 * do, f.ctypes.data + 4, n)
             assert np.array_equal(dst[do:do + n].view(np.uint64), f[1:1 + n].astype(np.float64).view(np.uint64))
             assert (dst[:do] == 7.0).all() and (dst[do + n:] == 7.0).all()
+
+
+@pytest.mark.timeout(120)
+def test_copy_pool_concurrent_callers_do_not_deadlock(libb2m):
+    """a pre-fault job used to keep the process-wide pool locked until its owner returned from the collective
+    pipeline, so a second rank of a single-process slab group blocked in its own copy and never reached the barrier.
+    Several callers, blocks >= 64 MiB (the pre-fault threshold), a barrier between pre-fault and copy; no GPU needed."""
+    libb2m.b2m_pool_selftest.argtypes = [C.c_size_t, C.c_int]
+    libb2m.b2m_set_copy_threads.argtypes = [C.c_int]
+    assert libb2m.b2m_set_copy_threads(4) in (0, 1)
+    assert libb2m.b2m_get_copy_threads() >= 1
+    for callers in (1, 2, 3):
+        assert libb2m.b2m_pool_selftest(40 << 20, callers) == 0, callers

@@ -111,12 +111,22 @@ def test_atlas_d99_golden(eng):
                 gv, gt, r = eng.meshify_label(d, info, 0.5, 0, ps, fb, 0)
                 assert (len(gv), len(gt)) == (e["nverts"], e["ntris"]), (lab, ps, fb)
                 assert topology_digest(gv, gt)[2] == e["digest"], (lab, ps, fb)
-        # every label of the atlas meshes (or fails like the reference: none does here)
-        ok = 0
+        # EVERY label against the unmodified reference's per-label mesh (tools/make_golden_big.py: whole-volume
+        # binarisation + the reference's meshify(), -p1 -l0 -b0 iso 0.5): counts, topology + f32-exact positions, and
+        # the four labels whose smoothed maximum stays below 0.5 so that the isolevel is reset (src/meshify.c:316-319)
+        big = json.loads((GOLDEN / "golden_big.json").read_text())["atlas"]
+        assert big["nlabel"] == gold["nlabel"] and big["nonempty"] == gold["nonempty"] == 365
+        resets = []
         for info in infos[1:]:
-            if info.nvox:
-                _, _, r = eng.meshify_label(d, info, 0.5, 0, 1, 0, 0, fetch=False)
-                ok += r.nverts >= 3
-        assert ok == gold["nonempty"]
+            e = big["labels"][str(info.label)]
+            assert info.nvox == e["nvox"], info.label
+            if not info.nvox:
+                continue
+            gv, gt, r = eng.meshify_label(d, info, 0.5, 0, 1, 0, 0)
+            assert (len(gv), len(gt)) == (e["nverts"], e["ntris"]), info.label
+            assert topology_digest(gv, gt)[2] == e["digest"], info.label
+            if r.iso_reset:
+                resets.append(info.label)
+        assert resets == big["resets"] == [127, 180, 188, 192]
     finally:
         d.free()

@@ -248,6 +248,11 @@ def test_gyroid_full_size_known_counts(eng, n, post):
             # closed-surface bookkeeping that does not depend on size: every index in range and used
             assert t.min() >= 0 and t.max() < len(v)
             assert len(np.unique(t)) >= len(v) - r.ndegenerate
+            # topology + bit-exact positions against the unmodified reference's mesh of the same volume (recorded by
+            # tools/make_golden_big.py: 4 s / 30 s of reference CPU time)
+            g = json.loads((GOLDEN / "golden_big.json").read_text())["gyroid"][str(n)]
+            assert (len(v), len(t)) == (g["nverts"], g["ntris"])
+            assert topology_digest(v, t)[2] == g["digest"]
     finally:
         d.free()
 
@@ -348,3 +353,44 @@ def test_repeated_host_calls_large_pageable_volume(eng):
     b = eng.meshify(vol, 0.0, 0, 1, 1, 1, 0)
     assert a[2].nverts * 24 + a[2].ntris * 12 > (64 << 20)
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[0].view(np.uint64), b[0].view(np.uint64))
+
+
+def test_narrow_volumes(eng, orc):
+    """bwlabelCore() refuses volumes narrower than 2 voxels in x or y (src/bwlabel.c:434-437): -l / -b are no-ops there"""
+    import test_oracle
+    for name, vol in test_oracle._narrow_volumes().items():
+        for ps, ol, fb in ((0, 1, 0), (0, 1, 1), (0, 0, 1), (1, 1, 1)):
+            a, b = eng.front(vol, 0.1, ps, ol, fb), orc.front(vol, 0.1, ps, ol, fb)
+            assert np.array_equal(a["mask"] != 0, b["mask"] != 0), (name, ps, ol, fb)
+            assert bits_differ(a["img"], b["img"]) == 0 and a["lo"] == b["lo"] and a["hi"] == b["hi"], (name, ps, ol, fb)
+
+
+def test_pinned_input_overlapped_h2d(eng):
+    """a pinned host volume >= 256 MiB goes up in z-chunks on a second stream while the smooth follows the transfer
+    (b2m_meshify_host); the mesh equals the device-resident path bit for bit"""
+    from nii2mesh_b200 import lib, synth
+    n = 448   # 343 MiB
+    L = eng.lib
+    hp = C.c_void_p()
+    eng._chk(L.b2m_host_alloc(C.byref(hp), n ** 3 * 4))
+    try:
+        hvol = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_float)), shape=(n, n, n))
+        hvol[...] = synth.gyroid(n)
+        o = lib.Opts(0.0, 0, 1, 1, 1, 0, 0)
+        r = lib.Result()
+        pv, pt = C.c_void_p(), C.c_void_p()
+        eng._chk(L.b2m_meshify_host(eng.ctx, hp, (C.c_int64 * 3)(n, n, n), C.byref(o), C.byref(pv), C.byref(pt), C.byref(r)))
+        v = np.ctypeslib.as_array(C.cast(pv, C.POINTER(C.c_double)), shape=(r.nverts, 3)).copy()
+        t = np.ctypeslib.as_array(C.cast(pt, C.POINTER(C.c_int)), shape=(r.ntris, 3)).copy()
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        libc.free(pv)
+        libc.free(pt)
+        d = eng.upload(hvol)
+        try:
+            v2, t2, _ = eng.meshify_device(d, 0.0, 0, 1, 1, 1, 0)
+        finally:
+            d.free()
+        assert np.array_equal(t, t2) and np.array_equal(v.view(np.uint64), v2.view(np.uint64))
+    finally:
+        L.b2m_host_free(hp)

@@ -119,3 +119,101 @@ def test_slabs_bad_geometry_fails_loudly(eng, groups):
     # the group is usable again afterwards
     gv, gt, _ = groups[2].meshify(vol, [0, 20, 40], iso)
     assert len(gv) > 0 and len(gt) > 0
+
+
+def _snake_volume():
+    nz, ny, nx = 48, 40, 70
+    v = np.full((nz, ny, nx), -1.0, np.float32)
+    for i, x in enumerate(range(4, 60, 8)):
+        v[4:44, 10:14, x:x + 3] = 1.0
+        z = 41 if i % 2 == 0 else 4
+        v[z:z + 3, 10:14, x:x + 11] = 1.0
+    v[6:10, 25:29, 5:9] = 1.0
+    v[36:40, 25:29, 5:9] = 1.0
+    v[18:30, 22:34, 40:52] = 1.0
+    v[21:27, 25:31, 43:49] = -1.0
+    v += np.random.default_rng(3).normal(0, 0.01, v.shape).astype(np.float32)
+    return v
+
+
+@pytest.mark.parametrize("caps", [("1", "1"), ("3", "100000"), ("100000", "2")])
+def test_slabs_seam_block_overflow_takes_the_slow_path(eng, groups, monkeypatch, caps):
+    """the fast seam merge ships one fixed-size block of seam roots / pairs per rank; when a rank has more (noise
+    volumes), every rank sees the overflow flag in the gathered headers, untags its roots and the sorted-list path
+    takes over.  Forced here with tiny capacities; the result must not change."""
+    monkeypatch.setenv("B2M_SEAM_ENT_CAP", caps[0])
+    monkeypatch.setenv("B2M_SEAM_PAIR_CAP", caps[1])
+    for vol, iso in ((_snake_volume(), 0.0), VOLS["blobs"], VOLS["sphere40"]):
+        d = eng.upload(vol)
+        try:
+            for world in (2, 4):
+                if vol.shape[0] < 4 * world:
+                    continue
+                for ps, ol, fb in ((0, 1, 1), (1, 1, 0), (0, 0, 1)):
+                    sv, st, sr = eng.meshify_device(d, iso, 0, ps, ol, fb, 0)
+                    gv, gt, rs = groups[world].meshify(vol, _cuts(vol.shape[0], world, False), iso, original_mc=0, pre_smooth=ps,
+                                                       only_largest=ol, fill_bubbles=fb, backend=0)
+                    assert np.array_equal(gt, st) and np.array_equal(gv.view(np.uint64), sv.view(np.uint64)), (caps, world, ps, ol, fb)
+        finally:
+            d.free()
+
+
+def test_slabs_unaligned_slab_pointers(eng, groups):
+    """slabs handed in as d_volume + z0 * nx * ny of ONE device volume whose plane size is odd: only 4-byte aligned
+    (the range reduction of the -p 0 path read float4 from such pointers)"""
+    from nii2mesh_b200 import lib
+    vol, iso = VOLS["blobs"]          # 30 x 37 x 41: 1517 voxels per plane
+    nz, ny, nx = vol.shape
+    d = eng.upload(vol)
+    try:
+        for world in (2, 3):
+            cuts = _cuts(nz, world, True)
+            views = [lib.DeviceVolume(eng, (cuts[i + 1] - cuts[i], ny, nx), d.ptr.value + cuts[i] * ny * nx * 4) for i in range(world)]
+            assert any(v.ptr % 16 for v in views)
+            for ps, ol, fb in ((0, 0, 0), (0, 1, 1), (1, 1, 0)):
+                sv, st, _ = eng.meshify_device(d, iso, 0, ps, ol, fb, 0)
+                gv, gt, _ = groups[world].meshify_device(views, vol.shape, cuts, iso, original_mc=0, pre_smooth=ps,
+                                                         only_largest=ol, fill_bubbles=fb, backend=0)
+                assert np.array_equal(gt, st) and np.array_equal(gv.view(np.uint64), sv.view(np.uint64)), (world, ps, ol, fb)
+    finally:
+        d.free()
+
+
+@pytest.mark.timeout(600)
+def test_slab_host_local_group_large_mesh(eng):
+    """b2m_meshify_slab_host() driven by the host threads of ONE process (local transport) with output blocks beyond the
+    pre-fault threshold (64 MiB per rank): ADVICE r1's deadlock - a rank kept the process-wide copy pool while it waited
+    in a collective for a rank that was waiting for the pool.  G512 in two slabs; the assembled mesh is the reference's
+    (counts + topology digest recorded from the unmodified reference, tests/golden/golden_big.json)."""
+    import json
+    import threading
+    from conftest import GOLDEN
+    from nii2mesh_b200 import lib, synth, slabs
+    from oracle.canon import topology_digest
+    n = 512
+    vol = np.tile(synth.gyroid_tile(128), (n // 128,) * 3)
+    grp = lib.LocalSlabGroup(2)
+    cuts = [0, 256, 512]
+    out, err = [None, None], [None, None]
+
+    def work(i):
+        try:
+            r, v, t = grp.engs[i].meshify_slab_host(grp.comms[i], vol[cuts[i]:cuts[i + 1]], vol.shape, cuts[i], 0.0, 0, 1, 1, 1, 0)
+            out[i] = slabs.part_of(r, v, t)
+        except Exception as ex:  # noqa: BLE001
+            err[i] = ex
+    try:
+        for rep in range(2):   # the second call pre-faults its blocks from the first call's totals, before the H2D
+            th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not any(err), err
+            assert min((p["nv_edge"] + p["nv_cent"]) * 24 + p["ntris_local"] * 12 for p in out) > (64 << 20)
+        V, T = slabs.assemble(out)
+    finally:
+        grp.close()
+    g = json.loads((GOLDEN / "golden_big.json").read_text())["gyroid"]["512"]
+    assert (len(V), len(T)) == (g["nverts"], g["ntris"]) == (5802752, 11606149)
+    assert topology_digest(V, T)[2] == g["digest"]

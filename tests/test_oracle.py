@@ -110,6 +110,27 @@ def test_meshify_vs_reference(orc, ref_lewiner, ref_classic, name):
             assert np.array_equal(o["verts"], r["verts"]) and np.array_equal(o["tris"], r["tris"])
 
 
+def _narrow_volumes():
+    rng = np.random.default_rng(21)
+    return {"nx1": rng.standard_normal((12, 10, 1)).astype(np.float32), "ny1": rng.standard_normal((12, 1, 10)).astype(np.float32),
+            "nx1_ny1": rng.standard_normal((20, 1, 1)).astype(np.float32), "nz1": rng.standard_normal((1, 9, 11)).astype(np.float32)}
+
+
+def test_narrow_volumes_vs_reference(orc, ref_lewiner):
+    """bwlabelCore() refuses dim[0] < 2 or dim[1] < 2 and leaves the mask as thresholded (src/bwlabel.c:434-437):
+    -l / -b become no-ops there, while a single-plane volume (nz == 1) is labelled normally"""
+    for name, vol in _narrow_volumes().items():
+        mask = (vol >= np.float32(0.1)).astype(np.float32)
+        for ol, fb in ((1, 0), (0, 1), (1, 1)):
+            assert np.array_equal(orc.bwlabel(mask, 18, ol, fb), ref_lewiner.bwlabel(mask, 18, ol, fb)), (name, ol, fb)
+        for ps, ol, fb in ((0, 1, 0), (0, 1, 1), (1, 1, 1)):
+            r = ref_lewiner.meshify(vol, 0.1, 0, ps, ol, fb)
+            o = orc.meshify(vol, 0.1, 0, ps, ol, fb, 0)
+            assert o["rc"] == r["rc"], (name, ps, ol, fb)
+            if r["rc"] == 0:
+                assert np.array_equal(o["verts"], r["verts"]) and np.array_equal(o["tris"], r["tris"])
+
+
 def test_weld_adversarial_vs_reference(orc, ref_lewiner):
     """near-duplicate vertices around the 1e-5 tolerance, incl. chains (later heads steal)"""
     rng = np.random.default_rng(11)

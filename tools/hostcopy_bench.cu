@@ -37,11 +37,17 @@ int main() {
   printf("cores %ld\n", sysconf(_SC_NPROCESSORS_ONLN));
   char *pin; cudaMallocHost(&pin, (size_t)256 << 20);
   char *dev; cudaMalloc(&dev, N); cudaMemset(dev, 1, N);
-  for (int huge = 0; huge < 2; huge++) {
+  for (int huge = 0; huge < 4; huge++) {
     char *m = (char *)malloc(N + (2 << 20));
     char *a = (char *)(((uintptr_t)m + (2 << 20) - 1) & ~(uintptr_t)((2 << 20) - 1));
-    if (huge) madvise(a, N, MADV_HUGEPAGE);
-    printf("huge=%d touch(16 thr) %.1f ms\n", huge, par(a, nullptr, N, 16, 1 << 20));
+    if (huge & 1) madvise(a, N, MADV_HUGEPAGE);
+    if (huge < 2) printf("huge=%d touch(16 thr) %.1f ms\n", huge, par(a, nullptr, N, 16, 1 << 20));
+    else {
+#ifdef MADV_POPULATE_WRITE
+      double tp0 = now(); int rcp = madvise(a, N, MADV_POPULATE_WRITE); double tp1 = now();
+      printf("huge=%d MADV_POPULATE_WRITE (1 thr) rc %d: %.1f ms\n", huge, rcp, tp1 - tp0);
+#endif
+    }
     for (int nt : {4, 8, 16, 32}) {
       double t = 0;
       for (size_t o = 0; o < N; o += (size_t)256 << 20) t += par(a + o, pin, (size_t)256 << 20, nt, 1 << 20);
