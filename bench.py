@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py — Gvoxels/s of the meshify() hot path (smooth + CC + MC + weld) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 1024] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--size 1024] [--volume 2048] [--impl reference]
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic "gyroid + bumps"
 float32 volume (128^3 period), Lewiner MC33, -p 1 -l 1 -b 1, isolevel 0.  A step is one whole meshify() pass.
@@ -9,6 +9,11 @@ float32 volume (128^3 period), Lewiner MC33, -p 1 -l 1 -b 1, isolevel 0.  A step
   N > 1 : ONE volume of N * 2^30 voxels cut into N z-slabs, one rank (process, GPU) per slab, NCCL over NVLink
           for the halo planes / seam lists (b2m_meshify_slab): 2048x1024x1024, 2048x2048x1024 and, at N = 8,
           2048^3 (BASELINE configs[4]).  Per-GPU work is fixed (2^30 voxels): weak scaling.
+
+  --volume V : STRONG scaling instead: ONE V^3 volume (BASELINE configs[4] as written: 2048^3) cut into N z-slabs whatever
+          N is (a slab holds up to 2^32 voxels, so 2048^3 runs on 2, 4 and 8 GPUs), known answer asserted.
+  N > 1 also runs a parity pre-pass (config.parity): a G256 volume meshed as N slabs over NCCL, assembled on rank 0 and
+          compared with rank 0's single-GPU mesh and with the digest recorded from the unmodified reference.
 
   value : volume resident in HBM, mesh left in HBM; K steps between one CUDA-event pair on the library's
           stream (b2m_timer_start/stop), barrier + synchronize on both sides, max over ranks.
@@ -89,6 +94,17 @@ def kernel_bytes(name, n, nv, nt, nwords):
         "cc_select": nwords * 8, "dilate_bbox": nwords * 12,
     }
     return table.get(name)
+
+
+def known_counts(gshape):
+    """PRE-weld vertex / triangle counts of the reference for a G volume of gshape = (nz, ny, nx), all multiples of 128:
+    exact polynomial in the tiles per axis (a, b, c), fitted on reference runs of 10 small boxes and checked on 6 held-out
+    ones (tools/make_golden_big.py -> tests/golden/golden_big.json "boxlaw"); for cubes it is SURVEY.md 8e's cubic law."""
+    if any(d % 128 for d in gshape):
+        return None
+    c, b, a = (d // 128 for d in gshape)
+    f = lambda k3, k2, k1: k3 * a * b * c + k2 * (a * b + b * c + c * a) + k1 * (a + b + c)  # noqa: E731
+    return f(79416, 15152, -470), f(158848, 30304, -944)
 
 
 def slab_volume(world, n):
@@ -240,12 +256,49 @@ def run_reference(args, rank, emit):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
                                   f"each step = {T} G{n} volumes of the same generator, one per host core (bounded sample)"},
-           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "kind": kind, "cpu": cpu_model(),
+           "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "per_core_mvox_s": n ** 3 / dt / 1e6, "kind": kind, "cpu": cpu_model(),
                             "sample": f"{T} x G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris each; meshify() is "
                                       f"single-threaded, one volume per core"},
            "e2e": {"value": val, "unit": "Gvoxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
+
+
+def verify_slabs(eng, comm, dist, rank, world, tile):
+    """parity pre-pass of every multi-GPU run: G256 (BASELINE config 3 family, Lewiner -p1 -l1 -b1) meshed as `world`
+    z-slabs over NCCL, the blocks gathered and assembled on rank 0, against (a) rank 0's single-GPU mesh of the same
+    volume, array for array, and (b) the topology digest recorded from the unmodified reference"""
+    from nii2mesh_b200 import slabs
+    sys.path.insert(0, str(ROOT))
+    n = 256
+    nzl = n // world
+    d = eng.tiled_volume(tile, (nzl, n, n), z_offset=rank * nzl)
+    try:
+        sr = eng.meshify_slab(comm, d, (n, n, n), rank * nzl, ISO, **FLAGS)
+        v, t = eng.fetch_slab(sr)
+    finally:
+        d.free()
+    parts = slabs.gather_parts(dist, rank, world, sr, v, t)
+    if rank != 0:
+        return None
+    V, T = slabs.assemble(parts)
+    dw = eng.tiled_volume(tile, (n, n, n))
+    try:
+        sv, st, r1 = eng.meshify_device(dw, ISO, **FLAGS)
+    finally:
+        dw.free()
+    same = bool(np.array_equal(T, st) and np.array_equal(V.view(np.uint64), sv.view(np.uint64)))
+    out = {"volume": "G256 in %d z-slabs over NCCL, assembled" % world, "nverts": int(len(V)), "ntris": int(len(T)),
+           "equals_single_gpu_arrays": same}
+    try:
+        from oracle.canon import topology_digest
+        g = json.loads((ROOT / "tests" / "golden" / "golden_big.json").read_text())["gyroid"]["256"]
+        out["equals_reference_digest"] = bool(topology_digest(V, T)[2] == g["digest"] and (len(V), len(T)) == (g["nverts"], g["ntris"]))
+    except Exception as ex:  # noqa: BLE001
+        out["equals_reference_digest"] = None
+        out["note"] = f"reference digest not checked: {ex}"
+    assert same and out["equals_reference_digest"] is not False, f"slab parity pre-pass failed: {out}"
+    return out
 
 
 def main():
@@ -262,6 +315,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=1024, help="cube edge of the per-GPU volume (multiple of 128)")
     ap.add_argument("--impl", default="b2m")
+    ap.add_argument("--volume", type=int, default=0, help="strong scaling: ONE cube of this edge (e.g. 2048) cut into --gpus z-slabs")
+    ap.add_argument("--no-verify", action="store_true", help="skip the N > 1 parity pre-pass")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -294,7 +349,12 @@ def main():
     from nii2mesh_b200 import lib, synth
     eng = lib.Engine(local)
     n = args.size
-    gshape = slab_volume(world, n)          # (nz, ny, nx) of the whole volume
+    strong = args.volume > 0
+    if strong:
+        assert world > 1 and args.volume % world == 0, "--volume needs --gpus > 1 slabs that divide it"
+        gshape = (args.volume,) * 3
+    else:
+        gshape = slab_volume(world, n)      # (nz, ny, nx) of the whole volume
     GN = gshape[0] * gshape[1] * gshape[2]
     nzl = gshape[0] // world
     z0 = rank * nzl
@@ -307,6 +367,10 @@ def main():
         # torch.distributed is plumbing only: it carries the 128-byte NCCL id of the library's own communicator
         from nii2mesh_b200 import slabs
         comm = slabs.nccl_comm_from_torch(eng, dist, rank, world)
+
+    parity = None
+    if world > 1 and not args.no_verify:
+        parity = verify_slabs(eng, comm, dist, rank, world, tile)
 
     def step():
         if world == 1:
@@ -442,7 +506,31 @@ def main():
                 libc.free(pt)
             breakdown = {"h2d_ms": round(r2.h2d_ms, 2), "device_ms": round(r2.ms[7], 2), "d2h_ms": round(r2.d2h_ms, 2)}
             d2h = int(r2.d2h_bytes)  # bytes that crossed PCIe: Lewiner vertices travel as f32 (exact) and are widened on the host
-        e2e = {"value": GN / dt / 1e9, "breakdown": breakdown, "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
+        pageable = None
+        if world == 1:
+            # the drop-in caller hands meshify() a malloc()'d volume (src/nii2mesh.c:141): the same call on pageable memory
+            # (the library stages it through pinned buffers with its copy pool)
+            pg = np.empty(sshape, np.float32)
+            pg[...] = hvol
+            ppg = C.c_void_p(pg.ctypes.data)
+
+            def one_pg():
+                pt, pp, cnt, cnv = C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+                rc = L.meshify(ppg, dim, 0, ISO, C.byref(pt), C.byref(pp), C.byref(cnt), C.byref(cnv), True, True, True, False)
+                assert rc == 0 and (cnv.value, cnt.value) == (nv, nt)
+                libc.free(pp)
+                libc.free(pt)
+            one_pg()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                one_pg()
+            dtp = (time.perf_counter() - t0) / 3
+            pageable = {"value": GN / dtp / 1e9, "ms_per_step": dtp * 1e3, "steps": 3,
+                        "note": "same meshify() call, volume in pageable (numpy / malloc) memory"}
+            del pg
+        L.b2m_get_copy_threads.restype = C.c_int
+        e2e = {"value": GN / dt / 1e9, "breakdown": breakdown, "pageable_input": pageable, "copy_threads": int(L.b2m_get_copy_threads()),
+               "unit": "Gvoxels/s", "h2d_bytes_per_step": N * 4,
                "d2h_bytes_per_step": d2h, "d2h_delivered_bytes_per_step": (nv * 24 + nt * 12) if world == 1 else None, "bytes_scope": "per rank" if world > 1 else "whole job",
                "ms_per_step": dt * 1e3, "steps": ke, "api": api}
         L.b2m_host_free(hp)
@@ -451,29 +539,30 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         sn, T = 256, host_threads()
         dt, kind, cnv, cnt = ref_meshify_time(sn, 1, 0, T)
-        cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "kind": kind, "cpu": cpu_model(),
+        cpu = {"value": T * sn ** 3 / dt / 1e9, "unit": "Gvoxels/s", "cores": T, "per_core_mvox_s": sn ** 3 / dt / 1e6, "kind": kind, "cpu": cpu_model(),
                "sample": f"{T} x G{sn} ({sn}^3 voxels, same generator and flags) concurrently, one per host core, "
                          f"{dt:.1f} s, {cnv} verts {cnt} tris each; meshify() itself is single-threaded"}
     # known answer of the G family: the reference's PRE-weld counts are exactly cubic in the number
     # of 128-voxel tiles per axis; they pin the full-size runs no CPU oracle can reach (2048^3: 336 902 112 / 673 869 568)
     known = None
-    if gshape[0] == gshape[1] == gshape[2] and gshape[0] % 128 == 0:
-        t = gshape[0] // 128
-        exp = (79416 * t ** 3 + 45456 * t ** 2 - 1410 * t, 158848 * t ** 3 + 90912 * t ** 2 - 2832 * t)
-        known = {"pre_nverts": exp[0], "pre_ntris": exp[1], "match": (r.pre_nverts, r.pre_ntris) == exp}
+    exp = known_counts(gshape)
+    if exp:
+        known = {"pre_nverts": exp[0], "pre_ntris": exp[1], "match": (r.pre_nverts, r.pre_ntris) == exp,
+                 "source": "reference's pre-weld count law of the G family (exact fit on reference runs, tests/golden/golden_big.json)"}
         assert known["match"], f"pre-weld counts {r.pre_nverts}/{r.pre_ntris} differ from the reference's {exp}"
     if rank == 0:
         if world == 1:
             workload = f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])"
             par = "single GPU"
         else:
-            workload = (f"gyroid+bumps {gshape[2]}x{gshape[1]}x{gshape[0]} f32 ({world} x 2^{int(np.log2(N))} voxels), Lewiner MC33 "
-                        f"-p1 -l1 -b1 iso 0, ONE volume in {world} z-slabs (BASELINE configs[4] family; 2048^3 at 8 GPUs)")
+            workload = (f"gyroid+bumps {gshape[2]}x{gshape[1]}x{gshape[0]} f32 ({world} x {N} voxels), Lewiner MC33 "
+                        f"-p1 -l1 -b1 iso 0, ONE volume in {world} z-slabs (BASELINE configs[4]" +
+                        (" as written: the same cube at every GPU count)" if strong else " family; 2048^3 at 8 GPUs)"))
             par = f"{world} z-slabs of {nzl} planes, one rank per GPU; NCCL halo/seam exchange (b2m_meshify_slab)"
         out = {"metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": workload, "voxels_per_gpu": N, "voxels": GN, "parallelism": par,
+               "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": workload, "voxels_per_gpu": N, "voxels": GN, "parallelism": par, "parity": parity,
                           "l2": "inputs (4 B/voxel volume) larger than the 126 MB L2; no flush needed",
                           "mesh": {"nverts": nv, "ntris": nt, "pre_nverts": r.pre_nverts, "pre_ntris": r.pre_ntris},
                           "known_answer": known},

@@ -171,6 +171,23 @@ void b2m_atlas_free(b2m_label_info *infos);
 int b2m_meshify_label_device(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_label_info *info,
                              const b2m_opts *opts, b2m_result *res);
 
+/* The whole label loop in one call (src/nii2mesh.c:540-579, which the reference runs under OpenMP when built with OMP=1):
+ * scan, then every non-empty label meshed as b2m_meshify_label_device() does, the labels handed out to `workers` host
+ * threads owned by the library (each with its own stream and workspace on ctx's device; <= 0: 8), so that the per-label
+ * pipelines overlap on the GPU.  *meshes: malloc()'d array of nlabel+1 entries (index = label; b2m_atlas_meshes_free).
+ * rc = 0 meshed, 1 the reference's EXIT_FAILURE for that label, -100 skipped (no voxels), other negative: error.
+ * fetch != 0: verts (nverts x 3 f64) / tris (ntris x 3 i32) are copied to malloc()'d host blocks; else counts only. */
+typedef struct {
+  int label, rc;
+  long long nvox;
+  int nverts, ntris;
+  void *verts, *tris;
+  b2m_result r;   /* counts, isolevel actually used, iso_reset, bright box, stage times of this label */
+} b2m_label_mesh;
+int b2m_atlas_meshify_all(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts, int workers, int fetch,
+                          int *nlabel, b2m_label_mesh **meshes);
+void b2m_atlas_meshes_free(b2m_label_mesh *meshes, int nlabel);
+
 /* ---- automatic isolevel (-i d / m / b): replaces setThreshold(), src/isolevel.c:245-277 ----
  * dark_medium_bright_123 = 1 dark, 2 medium, 3 bright (src/nii2mesh.c:398-407).  Range, NaN count and the two
  * histograms are GPU reductions; the 256-bin Otsu search runs on the host.  The value equals the reference's float. */

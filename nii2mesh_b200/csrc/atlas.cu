@@ -171,3 +171,109 @@ extern "C" int b2m_meshify_label_device(b2m_ctx *ctx, const float *d_img, const 
   }
   return rc;
 }
+
+
+// ---- all labels in one call ------------------------------------------------------------------------------------------
+// The label loop of the reference (src/nii2mesh.c:540-579: one meshify() per non-empty label, under OpenMP when built
+// with OMP=1) as ONE library call: a scan of the volume, then the labels - largest first - are handed out through an
+// atomic counter to `workers` host threads that the library owns, each with its own b2m_ctx (stream + workspace) on the
+// caller's device, so that the launch- and round-trip-bound per-label pipelines of different labels overlap on the GPU.
+// The worker contexts live in the caller's ctx and are reused by later calls.
+#include <pthread.h>
+#include <atomic>
+namespace {
+struct atlas_job {
+  const float *d_img;
+  const int64_t *dims;
+  const b2m_opts *opts;
+  const b2m_label_info *infos;
+  const int *order;
+  int n;
+  int fetch;
+  b2m_label_mesh *out;
+  std::atomic<int> next{0};
+};
+struct atlas_worker_arg { atlas_job *job; b2m_ctx *ctx; };
+void *atlas_worker(void *a_) {
+  atlas_worker_arg *a = (atlas_worker_arg *)a_;
+  atlas_job *j = a->job;
+  cudaSetDevice(a->ctx->device);
+  for (;;) {
+    const int k = j->next.fetch_add(1);
+    if (k >= j->n) break;
+    const int lab = j->order[k];
+    b2m_label_mesh *m = &j->out[lab];
+    m->rc = b2m_meshify_label_device(a->ctx, j->d_img, j->dims, &j->infos[lab], j->opts, &m->r);
+    if (m->rc != B2M_OK) continue;
+    m->nverts = m->r.nverts; m->ntris = m->r.ntris;
+    if (j->fetch) {
+      m->verts = malloc((size_t)m->nverts * 24 + 8);
+      m->tris = malloc((size_t)m->ntris * 12 + 8);
+      if (!m->verts || !m->tris) { m->rc = B2M_ENOMEM; continue; }
+      m->rc = b2m_fetch_mesh(a->ctx, &m->r, m->verts, m->tris);
+    }
+    m->r.d_verts = nullptr; m->r.d_tris = nullptr;  // the worker's buffers are reused by its next label
+  }
+  return nullptr;
+}
+}  // namespace
+
+extern "C" int b2m_atlas_meshify_all(b2m_ctx *ctx, const float *d_img, const int64_t dims[3], const b2m_opts *opts, int workers,
+                                     int fetch, int *nlabel, b2m_label_mesh **meshes) {
+  if (!ctx || !d_img || !dims || !opts || !nlabel || !meshes) { b2m_set_error("null argument"); return B2M_EARG; }
+  if (workers < 1) workers = 8;
+  if (workers > B2M_ATLAS_WORKERS_MAX) workers = B2M_ATLAS_WORKERS_MAX;
+  b2m_label_info *infos = nullptr;
+  int nl = 0;
+  B2M_TRY(b2m_atlas_scan(ctx, d_img, dims, &nl, &infos));
+  b2m_label_mesh *out = (b2m_label_mesh *)calloc((size_t)nl + 1, sizeof(b2m_label_mesh));
+  int *order = (int *)malloc(((size_t)nl + 1) * sizeof(int));
+  if (!out || !order) { free(out); free(order); b2m_atlas_free(infos); return B2M_ENOMEM; }
+  int n = 0;
+  for (int i = 0; i <= nl; i++) {
+    out[i].label = i;
+    out[i].nvox = infos[i].nvox;
+    out[i].rc = -100;  // skipped: no voxels (src/nii2mesh.c:564-567)
+    if (i >= 1 && infos[i].nvox > 0) order[n++] = i;
+  }
+  // largest boxes first: the long jobs start early and the small ones fill the gaps
+  auto vol = [&](int l) { long long v = 1; for (int a = 0; a < 3; a++) v *= infos[l].hi[a] - infos[l].lo[a] + 9; return v; };
+  for (int i = 1; i < n; i++) {
+    const int l = order[i];
+    const long long v = vol(l);
+    int k = i - 1;
+    while (k >= 0 && vol(order[k]) < v) { order[k + 1] = order[k]; k--; }
+    order[k + 1] = l;
+  }
+  if (workers > n) workers = n > 0 ? n : 1;
+  int rc = B2M_OK;
+  for (int w = 0; w < workers && rc == B2M_OK; w++)
+    if (!ctx->atlas_workers[w]) rc = b2m_create(&ctx->atlas_workers[w], ctx->device);
+  if (rc == B2M_OK && n > 0) {
+    atlas_job job;
+    job.d_img = d_img; job.dims = dims; job.opts = opts; job.infos = infos; job.order = order; job.n = n; job.fetch = fetch; job.out = out;
+    atlas_worker_arg args[B2M_ATLAS_WORKERS_MAX];
+    pthread_t th[B2M_ATLAS_WORKERS_MAX];
+    int started = 0;
+    for (int w = 0; w < workers; w++) {
+      args[w].job = &job; args[w].ctx = ctx->atlas_workers[w];
+      if (pthread_create(&th[w], nullptr, atlas_worker, &args[w]) != 0) break;
+      started++;
+    }
+    if (started == 0) { args[0].job = &job; args[0].ctx = ctx->atlas_workers[0]; atlas_worker(&args[0]); }
+    for (int w = 0; w < started; w++) pthread_join(th[w], nullptr);
+    CU_TRY(cudaSetDevice(ctx->device));
+  }
+  free(order);
+  b2m_atlas_free(infos);
+  if (rc != B2M_OK) { b2m_atlas_meshes_free(out, nl); return rc; }
+  *nlabel = nl;
+  *meshes = out;
+  return B2M_OK;
+}
+
+extern "C" void b2m_atlas_meshes_free(b2m_label_mesh *m, int nlabel) {
+  if (!m) return;
+  for (int i = 0; i <= nlabel; i++) { free(m[i].verts); free(m[i].tris); }
+  free(m);
+}

@@ -162,9 +162,19 @@ __device__ __forceinline__ void lunion(uint32_t *par, uint32_t a, uint32_t b) {
 // Enumerates the backward neighbour runs of run [s,e] (mask rm) of the word at tile-local (lx,ly,lz)
 // and calls link(neighbour word delta (dx,dy,dz), neighbour word bits, start bit of the neighbour run).
 // fetch(dx,dy,dz) returns the neighbour word's bits or 0 when that pair is not this phase's business.
+// Links that are implied by others are skipped (a solid region would otherwise pay nine unions per word, six of them
+// redundant):
+//   * word-diagonal link of a wide row (run starts at bit 0 / ends at bit 31 and the neighbour row's previous / next word
+//     ends / starts with a set bit): implied when the neighbour row's centre word has bit 0 / bit 31 set - the run links
+//     to the centre word's run at that bit, and that run continues into the diagonal word (in-row link);
+//   * run of a plane-diagonal row (dy = +-1, dz = -1): implied when, at some voxel where both runs are set, one of the
+//     two intermediate face neighbours (dy, 0) or (0, -1) is set too - both runs are face-linked to that voxel's run.
+// The implying links are made by this or another thread of this kernel or of its sibling (tile-local / tile-border):
+// `fetch` returns 0 for words the calling kernel does not handle, which keeps the test conservative - a link is only
+// dropped when the words that imply it are visible to the same kernel.
 template <int CONN, class Fetch, class Link>
 __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, Fetch fetch, Link link) {
-  auto row = [&](int dy, int dz, bool wide) {
+  auto row = [&](int dy, int dz, bool wide, uint32_t covered) {
     const uint32_t nw = fetch(0, dy, dz);
     uint32_t m = rm;
     if (wide) m |= (rm << 1) | (rm >> 1);
@@ -173,15 +183,16 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
       const int b = __ffs(t) - 1;
       const int st = run_start(nw, b);
       const int en = run_end(nw, st);
-      link(0, dy, dz, st, nw);
-      t &= ~bits_range(st, en);
+      const uint32_t rb = bits_range(st, en);
+      if (!(rb & rm & covered)) link(0, dy, dz, st, nw);
+      t &= ~rb;
     }
     if (wide) {
-      if (s == 0) {
+      if (s == 0 && !(nw & 1u)) {
         const uint32_t pw = fetch(-1, dy, dz);
         if (pw >> 31) link(-1, dy, dz, run_start(pw, 31), pw);
       }
-      if (e == 31) {
+      if (e == 31 && !(nw >> 31)) {
         const uint32_t nx = fetch(1, dy, dz);
         if (nx & 1u) link(1, dy, dz, 0, nx);
       }
@@ -192,11 +203,12 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
     if (pw >> 31) link(-1, 0, 0, run_start(pw, 31), pw);
   }
   const bool wide = CONN >= 18;
-  row(-1, 0, wide);
-  row(0, -1, wide);
+  row(-1, 0, wide, 0u);
+  row(0, -1, wide, 0u);
   if (wide) {
-    row(-1, -1, false);
-    row(1, -1, false);
+    const uint32_t below = fetch(0, 0, -1);
+    row(-1, -1, false, fetch(0, -1, 0) | below);
+    row(1, -1, false, fetch(0, 1, 0) | below);
   }
 }
 
@@ -1423,6 +1435,7 @@ int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     return b2m_comm_exchange(ctx, comm, ext + own_off + (size_t)(sl.nzl - 1) * pw, sl.hh ? pw * 4 : 0, ext, sl.hl ? pw * 4 : 0,
                              ext + own_off, sl.hl ? pw * 4 : 0, ext + own_off + (size_t)sl.nzl * pw, sl.hh ? pw * 4 : 0);
   };
+  if (o->fill_bubbles && refused) { fo->fill = fg; }  // no bubbles found: the "filled" mask is the thresholded one
   if (o->fill_bubbles && !refused) {
     B2M_TRY(b2m_reserve(ctx, BUF_FILL, wbytes));
     uint32_t *fill = b2m_ptr<uint32_t>(ctx, BUF_FILL);

@@ -161,6 +161,7 @@ struct b2m_ktimer {
   cudaEvent_t e0, e1;
 };
 
+#define B2M_ATLAS_WORKERS_MAX 32
 #define B2M_PEND_MAX 16
 #define B2M_RING_CHUNK ((size_t)8 << 20)   /* streamed D2H: DMA granule */
 #define B2M_RING_SLOTS 12                  /* = 3 * B2M_STAGE_BYTES / B2M_RING_CHUNK */
@@ -182,6 +183,7 @@ struct b2m_ctx {
   b2m_scalars *h_scalars;  // pinned mirror
   uint64_t launches;
   int tables_ready;
+  int smooth_tma_attr_done;
   int smooth_attr_done;    // the > 48 KB dynamic shared memory opt-in of the smooth kernel was made through this ctx
   int sm_count;
   unsigned ev_mask;        // which stage event pairs were recorded in the current call
@@ -197,6 +199,7 @@ struct b2m_ctx {
   int pend_n, pend_last;   // chunks not yet consumed / index of the last chunk of the transfer
   cudaStream_t aux_stream; // slabs: halo exchanges that run next to kernels of `stream` (high priority, created on demand)
   cudaEvent_t aux_ev[2];
+  b2m_ctx *atlas_workers[B2M_ATLAS_WORKERS_MAX];  // worker contexts of b2m_atlas_meshify_all (created on demand, same device)
   int profile;             // record an event pair around every kernel launch
   int nkt, nkt_events;     // entries used in this call / event pairs created so far
   b2m_ktimer kt[B2M_KT_MAX];

@@ -57,6 +57,8 @@ extern "C" int b2m_create(b2m_ctx **out, int device) {
 
 extern "C" void b2m_destroy(b2m_ctx *c) {
   if (!c) return;
+  for (int i = 0; i < B2M_ATLAS_WORKERS_MAX; i++)
+    if (c->atlas_workers[i]) b2m_destroy(c->atlas_workers[i]);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (int i = 0; i < BUF_COUNT; i++)

@@ -227,9 +227,6 @@ __device__ __noinline__ void mc33_select(const signed char *__restrict__ tab, co
 // Per segment the kernel leaves {xbits, ybits, zbits, packed counts}; packed counts = nv | nt << 7 | nc << 16
 // (nv <= 96, nt <= 384, nc <= 32), turned into exclusive bases by scan3.  Active voxels are appended to a
 // warp-private shared-memory buffer and flushed to the global list with one atomic per ~150 records.
-#ifndef MC_EMIT_EARLY
-#define MC_EMIT_EARLY 0  /* 1: emit looks the edge-vertex ids up before the vertex stores, one record load per (row, segment): parity green on the single-volume suite, 2.10 -> 2.06 ms; off until the slab suites have run with it */
-#endif
 #define MCB_THREADS 128
 #define MCB_ZC 8
 #define MCB_BUF 192
@@ -616,9 +613,8 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     c[2] = c[5] = c[6] = c[7] = c[0];
   }
   const float flo0 = (float)(p.lo0 + p.org0), flo1 = (float)(p.lo1 + p.org1), flo2 = (float)(p.lo2 + p.org2);
-#if MC_EMIT_EARLY
   // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
-  // Looked up BEFORE the vertex stores below: behind them (and behind the `ntri == 0` exit) the segment-record loads
+  // Looked up BEFORE the vertex stores below (r1: validated on the single-volume and slab suites, 2.10 -> 2.06 ms): behind them (and behind the `ntri == 0` exit) the segment-record loads
   // started only after the corner values had arrived and the vertices were written - a third dependent round trip
   // through L2 per thread.  One record load serves every edge that shares a (row, segment): <= 4 loads instead of 12.
   uint32_t ev[13];
@@ -673,7 +669,6 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     }
     ev[12] = 0xffffffffu;
   }
-#endif
   // ---- own edge vertices ----
   if (ex | ey | ez) {
     uint32_t vid = __ldg(&p.segbits[sidx].w) + (uint32_t)pv;
@@ -747,28 +742,6 @@ __global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params
     }
   }
   if (!ntri) return;
-#if !MC_EMIT_EARLY
-  // ---- vertex ids of the 12 cube edges (src/MarchingCubes.c:813-825) ----
-  const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
-  uint32_t ev[13];
-  // inside bits of the corners = the cube index the classify pass built from the inside-bit rows
-  const unsigned lut = r.w;
-  const bool in0 = lut & 1u, in1 = (lut >> 1) & 1u, in2 = (lut >> 2) & 1u, in3 = (lut >> 3) & 1u;
-  const bool in4 = (lut >> 4) & 1u, in5 = (lut >> 5) & 1u, in6 = (lut >> 6) & 1u, in7 = (lut >> 7) & 1u;
-  ev[0] = in0 != in1 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
-  ev[1] = in1 != in2 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
-  ev[2] = in3 != in2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
-  ev[3] = in0 != in3 ? mc_vidx(p, row, x, 1) : 0xffffffffu;
-  ev[4] = in4 != in5 ? mc_vidx(p, rowZ, x, 0) : 0xffffffffu;
-  ev[5] = in5 != in6 ? mc_vidx(p, rowZ, x + 1, 1) : 0xffffffffu;
-  ev[6] = in7 != in6 ? mc_vidx(p, rowYZ, x, 0) : 0xffffffffu;
-  ev[7] = in4 != in7 ? mc_vidx(p, rowZ, x, 1) : 0xffffffffu;
-  ev[8] = in0 != in4 ? mc_vidx(p, row, x, 2) : 0xffffffffu;
-  ev[9] = in1 != in5 ? mc_vidx(p, row, x + 1, 2) : 0xffffffffu;
-  ev[10] = in2 != in6 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
-  ev[11] = in3 != in7 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
-  ev[12] = 0xffffffffu;
-#endif
   if (hasc) {
     // centroid of the cube's existing edge vertices, summed in edge-code order in f32 local
     // coordinates, divided by the f32 count (src/MarchingCubes.c:1042-1071); then + lo in f32.

@@ -6,6 +6,8 @@
 //   right in FP64 (no FMA: __dmul_rn/__dadd_rn), ONE rounding to f32 per pass; voxels whose index
 //   on the pass axis is < 2 or >= n-2 keep the previous pass's value; nothing happens when a
 //   dim < 5 (the reference ignores quick_smooth's EXIT_FAILURE, meshify.c:301).
+#include <cuda.h>
+
 #include "common.cuh"
 
 // ---- tile geometry ----
@@ -387,6 +389,225 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   }
 }
 
+
+// ================================================================================================================
+// TMA variant (sm_100a): the raw planes are brought into shared memory by the tensor-memory accelerator instead of by
+// per-thread loads.  One elected thread issues ONE cp.async.bulk.tensor per plane - a 3-D box {SXT_BW x SX_ROWS x 1}
+// at (x0-4, y0-2, plane) of the raw volume, whose bytes complete an mbarrier transaction (SASS: UTMALDG) - three planes
+// ahead of the x pass.  Out-of-volume parts of the box (tile halos beyond the faces, partial tiles) arrive as zeros, so
+// the kernel has no halo loads, no neighbour shuffles, no row / column predicates and no prefetch registers: the x pass
+// reads its 8 inputs per lane from shared memory (4 x LDS.64).  Everything after the x pass is the kernel above.
+// Requirements of the tensor maps: nx % 4 == 0 and 16-byte aligned pieces (the same condition as the vector path).
+#define SXT_BW 136                            /* box width: 128 + 2 x 4 (the left halo padded to a 16-byte boundary) */
+#define SXT_RAW 3                             /* raw planes in flight */
+#define SXT_RAW_BYTES (SX_ROWS * SXT_BW * 4)  /* 15232 = 119 x 128: the slots stay 128-byte aligned */
+#define SXT_SMEM (SX_SMEM + SXT_RAW * SXT_RAW_BYTES + 128)
+struct smooth_tmaps {
+  CUtensorMap lo, main, hi;
+};
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)),
+               "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+// x pass of one staged row out of shared memory: the lane's 4 outputs x0 + 4 lane + k need the box columns
+// 4 lane + 2 .. 4 lane + 9
+template <bool FAST, bool XEDGE>
+__device__ __forceinline__ void x_pass_row_smem(const float f[8], int lane, int gx, int nx, double2 *__restrict__ dst) {
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[k] = (double)f[k];
+  double o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int x = gx + k;
+    const double r = round_to_f32<FAST>(fir5(v[k], v[k + 1], v[k + 2], v[k + 3], v[k + 4]));
+    o[k] = (XEDGE && (x < 2 || x >= nx - 2)) ? v[k + 2] : r;
+  }
+  dst[lane] = make_double2(o[0], o[1]);
+  dst[32 + lane] = make_double2(o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3_tma(const __grid_constant__ smooth_tmaps maps, const __grid_constant__ smooth_src src,
+                                                               float *__restrict__ out, int nx, int ny, int zc, unsigned int *__restrict__ mm_enc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // [raw ring: SXT_RAW x SX_ROWS x SXT_BW f32][x-pass ring: SX_RING x SX_ROWS x 2 x 32 double2]
+  unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  float *rawbuf = reinterpret_cast<float *>(base);
+  double2 *xs2 = reinterpret_cast<double2 *>(base + SXT_RAW * SXT_RAW_BYTES);
+  __shared__ float red[2][SX_WARPS];
+  __shared__ __align__(8) unsigned long long mbar[2], rbar[SXT_RAW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
+  const int nz = src.gnz;
+  const int z0 = src.oz0 + blockIdx.z * zc, z1 = min(z0 + zc, src.oz0 + src.onz);
+  const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
+  const int gx = x0 + lane * 4;
+  const size_t nxy = (size_t)nx * ny;
+  double S[2][4][4];
+#pragma unroll
+  for (int r = 0; r < 2; r++)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int q = 0; q < 4; q++) S[r][k][q] = 0.0;
+  float vmin = INFINITY, vmax = -INFINITY;
+  const int oy0 = y0 + 2 * warp;  // output rows oy0, oy0 + 1 (warps < SX_TY / 2)
+  const bool yb0 = oy0 < 2 || oy0 >= ny - 2, yb1 = oy0 + 1 < 2 || oy0 + 1 >= ny - 2;
+  const bool ok0 = oy0 < ny && gx < nx, ok1 = oy0 + 1 < ny && gx < nx;
+  const bool xedge = x0 == 0 || x0 + SX_TX > nx - 2;  // block-uniform
+  const bool yedge = y0 == 0 || y0 + SX_TY > ny - 2;  // block-uniform
+  float *outp = out + (size_t)oy0 * nx + gx;
+  const int zb1 = src.rz0 + src.n_lo, zb2 = zb1 + src.n_main;
+
+  // one thread feeds the raw ring: plane zp -> slot (zp - zs) % SXT_RAW
+  auto issue = [&](int zp) {
+    if (zp >= ze) return;
+    const int slot = (zp - zs) % SXT_RAW;
+    const CUtensorMap *m = zp < zb1 ? &maps.lo : (zp < zb2 ? &maps.main : &maps.hi);
+    const int q = zp < zb1 ? zp - src.rz0 : (zp < zb2 ? zp - zb1 : zp - zb2);
+    mbar_expect_tx(&rbar[slot], SXT_RAW_BYTES);
+    tma_load_3d(rawbuf + (size_t)slot * (SXT_RAW_BYTES / 4), m, x0 - 4, y0 - 2, q, &rbar[slot]);
+  };
+  // x pass of plane zp (two staged rows per warp) out of the raw ring into the x-pass ring
+  auto stage = [&](int zp) {
+    const int i = zp - zs;
+    mbar_wait(&rbar[i % SXT_RAW], (unsigned)(i / SXT_RAW) & 1u);
+    const float *rp = rawbuf + (size_t)(i % SXT_RAW) * (SXT_RAW_BYTES / 4) + (2 * warp) * SXT_BW + lane * 4 + 2;
+    double2 *buf = xs2 + (size_t)(i % SX_RING) * (SX_ROWS * 64);
+    float f[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const float2 t = *reinterpret_cast<const float2 *>(rp + q * SXT_BW + 2 * k);
+        f[q][2 * k] = t.x; f[q][2 * k + 1] = t.y;
+      }
+    unsigned m = 0u;
+#pragma unroll
+    for (int q = 0; q < 2; q++)
+#pragma unroll
+      for (int k = 0; k < 8; k++) m = max(m, input_bias(f[q][k]));
+    bool warp_bad = false;
+    if (__any_sync(0xffffffffu, m >= 0x64000000u)) {
+      bool bad = false;
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) bad |= input_unsafe(f[q][k]);
+      warp_bad = __any_sync(0xffffffffu, bad);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      double2 *dst = buf + (2 * warp + q) * 64;
+      if (xedge) {
+        if (!warp_bad) x_pass_row_smem<true, true>(f[q], lane, gx, nx, dst);
+        else x_pass_row_smem<false, true>(f[q], lane, gx, nx, dst);
+      } else {
+        if (!warp_bad) x_pass_row_smem<true, false>(f[q], lane, gx, nx, dst);
+        else x_pass_row_smem<false, false>(f[q], lane, gx, nx, dst);
+      }
+    }
+  };
+  if (tid == 0) {
+    mbar_init(&mbar[0], SX_THREADS); mbar_init(&mbar[1], SX_THREADS);
+    for (int k = 0; k < SXT_RAW; k++) mbar_init(&rbar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) { issue(zs); issue(zs + 1); issue(zs + 2); }
+  stage(zs);
+  mbar_arrive(&mbar[0]);
+  long long zoff = (long long)(zs - src.oz0) * (long long)nxy;
+  for (int zp = zs; zp < ze; zp++, zoff += (long long)nxy) {
+    const int i = zp - zs;
+    if (zp + 1 < ze) {  // block-uniform
+      stage(zp + 1);
+      mbar_arrive(&mbar[(i + 1) & 1]);
+    }
+    mbar_wait(&mbar[i & 1], (unsigned)(i >> 1) & 1u);
+    // every warp has finished the x pass of plane zp (it arrived for it): that plane's raw slot is free again
+    if (tid == 0) issue(zp + SXT_RAW);
+    const double2 *buf = xs2 + (size_t)(i % SX_RING) * (SX_ROWS * 64);
+    if (warp < SX_TY / 2) {
+      float ob[2][4], oi[2][4];
+      if (!yedge) yz_pass2<false>(buf, 2 * warp, lane, false, false, S, ob, oi);
+      else yz_pass2<true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
+      const bool zborder = zp < 2 || zp >= nz - 2;
+      const int zo = zp - 2;
+      const bool emit_border = zborder && zp >= z0 && zp < z1;
+      const bool emit_inner = zo >= z0 && zo < z1 && zo >= 2 && zo < nz - 2;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (r ? ok1 : ok0) {
+          if (emit_border) {
+            *reinterpret_cast<float4 *>(outp + zoff + (r ? nx : 0)) = make_float4(ob[r][0], ob[r][1], ob[r][2], ob[r][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { vmin = fminf(vmin, ob[r][k]); vmax = fmaxf(vmax, ob[r][k]); }
+          }
+          if (emit_inner) {
+            *reinterpret_cast<float4 *>(outp + (zoff - 2 * (long long)nxy) + (r ? nx : 0)) = make_float4(oi[r][0], oi[r][1], oi[r][2], oi[r][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { vmin = fminf(vmin, oi[r][k]); vmax = fmaxf(vmax, oi[r][k]); }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+  }
+  if (lane == 0) { red[0][warp] = vmin; red[1][warp] = vmax; }
+  __syncthreads();
+  if (tid < 32) {
+    vmin = tid < SX_WARPS ? red[0][tid] : INFINITY;
+    vmax = tid < SX_WARPS ? red[1][tid] : -INFINITY;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    }
+    if (tid == 0 && vmin <= vmax) {
+      atomicMin(&mm_enc[0], f32_enc(vmin));
+      atomicMax(&mm_enc[1], f32_enc(vmax));
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn tma_encoder(void) {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (encode_tiled_fn)p;
+    else cudaGetLastError();
+    tried = true;
+  }
+  return fn;
+}
+// raw planes [nplanes][ny][nx] f32 as a 3-D tensor, box SXT_BW x SX_ROWS x 1, zero fill outside
+static bool smooth_make_tmap(CUtensorMap *m, const float *p, int nx, int ny, int nplanes) {
+  encode_tiled_fn enc = tma_encoder();
+  if (!enc || nplanes < 1) return false;
+  const cuuint64_t dim[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nplanes};
+  const cuuint64_t stride[2] = {(cuuint64_t)nx * 4, (cuuint64_t)nx * ny * 4};
+  const cuuint32_t box[3] = {SXT_BW, SX_ROWS, 1}, estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(p), dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // intensity range of a volume (reference: src/meshify.c:306-311) when no smoothing precedes it
 __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, size_t n, unsigned int *__restrict__ mm_enc) {
   __shared__ float red[2][8];
@@ -548,6 +769,25 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
     CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
     CU_TRY(cudaFuncSetAttribute(k_smooth3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
     ctx->smooth_attr_done = 1;
+  }
+  // TMA path (default; B2M_SMOOTH_TMA=0 keeps the per-thread loads): needs what the vector path needs, a stride of
+  // the rows that is a multiple of 16 bytes, and a driver that can encode tensor maps
+  static const bool want_tma = !(getenv("B2M_SMOOTH_TMA") && atoi(getenv("B2M_SMOOTH_TMA")) == 0);
+  if (vec && want_tma && SX_STAGE_WARPS) {
+    smooth_tmaps maps;
+    memset(&maps, 0, sizeof(maps));
+    bool ok = smooth_make_tmap(&maps.main, src.main, g.nx, g.ny, src.n_main);
+    if (ok && src.n_lo) ok = smooth_make_tmap(&maps.lo, src.lo, g.nx, g.ny, src.n_lo);
+    if (ok && src.n_hi) ok = smooth_make_tmap(&maps.hi, src.hi, g.nx, g.ny, src.n_hi);
+    if (ok) {
+      if (!ctx->smooth_tma_attr_done) {
+        CU_TRY(cudaFuncSetAttribute(k_smooth3_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SXT_SMEM));
+        ctx->smooth_tma_attr_done = 1;
+      }
+      KT_LAUNCH(ctx, "smooth3", k_smooth3_tma<<<grid, SX_THREADS, SXT_SMEM, ctx->stream>>>(maps, src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
+      CU_TRY(cudaGetLastError());
+      return B2M_OK;
+    }
   }
   if (vec)
     KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));

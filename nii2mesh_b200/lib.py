@@ -46,6 +46,12 @@ class LabelInfo(C.Structure):
     _fields_ = [("label", C.c_int), ("nvox", C.c_longlong), ("lo", C.c_int * 3), ("hi", C.c_int * 3)]
 
 
+class LabelMesh(C.Structure):
+    """b2m_label_mesh: one entry of b2m_atlas_meshify_all()"""
+    _fields_ = [("label", C.c_int), ("rc", C.c_int), ("nvox", C.c_longlong), ("nverts", C.c_int), ("ntris", C.c_int),
+                ("verts", C.c_void_p), ("tris", C.c_void_p), ("r", Result)]
+
+
 class B2MError(RuntimeError):
     pass
 
@@ -95,6 +101,9 @@ def load():
     L.b2m_atlas_free.argtypes = [C.POINTER(LabelInfo)]
     L.b2m_atlas_free.restype = None
     L.b2m_meshify_label_device.argtypes = [vp, vp, i64p, C.POINTER(LabelInfo), C.POINTER(Opts), C.POINTER(Result)]
+    L.b2m_atlas_meshify_all.argtypes = [vp, vp, i64p, C.POINTER(Opts), C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.POINTER(LabelMesh))]
+    L.b2m_atlas_meshes_free.argtypes = [C.POINTER(LabelMesh), C.c_int]
+    L.b2m_atlas_meshes_free.restype = None
     L.b2m_isolevel_device.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     L.b2m_isolevel_host.argtypes = [vp, vp, C.c_size_t, C.c_int, C.POINTER(C.c_float)]
     L.setThreshold.argtypes = [vp, C.c_int, C.c_int]
@@ -352,6 +361,27 @@ class Engine:
         t = np.empty((r.ntris, 3), np.int32)
         self._chk(self.lib.b2m_fetch_mesh(self.ctx, C.byref(r), v.ctypes.data, t.ctypes.data))
         return v, t, r
+
+    def atlas_meshify_all(self, dvol, iso=0.5, original_mc=0, pre_smooth=True, fill_bubbles=False, backend=BACKEND_LEWINER,
+                          workers=8, fetch=True):
+        """the whole label loop in ONE call (b2m_atlas_meshify_all): {label: dict(rc, nvox, nverts, ntris, iso_reset,
+        verts, tris)} for every label 1..nlabel (rc -100: no voxels, skipped like the reference does)"""
+        o = self._opts(iso, original_mc, pre_smooth, 0, fill_bubbles, backend)
+        n, p = C.c_int(), C.POINTER(LabelMesh)()
+        self._chk(self.lib.b2m_atlas_meshify_all(self.ctx, dvol.ptr, _dims(dvol.shape), C.byref(o), int(workers), int(fetch),
+                                                 C.byref(n), C.byref(p)))
+        out = {}
+        try:
+            for i in range(1, n.value + 1):
+                m = p[i]
+                e = dict(rc=m.rc, nvox=m.nvox, nverts=m.nverts, ntris=m.ntris, iso_reset=m.r.iso_reset, verts=None, tris=None)
+                if m.rc == 0 and fetch:
+                    e["verts"] = np.ctypeslib.as_array(C.cast(m.verts, C.POINTER(C.c_double)), shape=(m.nverts, 3)).copy()
+                    e["tris"] = np.ctypeslib.as_array(C.cast(m.tris, C.POINTER(C.c_int)), shape=(m.ntris, 3)).copy()
+                out[i] = e
+        finally:
+            self.lib.b2m_atlas_meshes_free(p, n.value)
+        return out
 
     def meshify_slab(self, comm, dslab, gshape, z0, iso, original_mc=0, pre_smooth=True, only_largest=True,
                      fill_bubbles=False, backend=BACKEND_LEWINER, verbose=False):

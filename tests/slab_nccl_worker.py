@@ -13,6 +13,32 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 
+def inject_failure(eng, comm, dist, rank, world, vols):
+    """the last rank hands in a slab that does not fit (usage error, detected locally); every other rank must come back
+    with an error instead of waiting for ever in the first collective"""
+    import torch
+    from nii2mesh_b200 import lib
+    vol, iso = vols["blobs2"]
+    nz = vol.shape[0]
+    cuts = [(i * nz) // world for i in range(world + 1)]
+    lo, hi = cuts[rank], cuts[rank + 1]
+    if rank == world - 1:
+        hi -= 1            # one plane short of the volume: rejected by the argument check of this rank only
+    failed = False
+    try:
+        eng.meshify_slab_host(comm, vol[lo:hi], vol.shape, lo, iso, original_mc=0, pre_smooth=1, only_largest=1, fill_bubbles=1)
+    except lib.B2MError as ex:
+        failed = True
+        print(f"rank {rank}: {ex}", flush=True)
+    flag = torch.tensor([0 if failed else 1], device="cuda")
+    dist.all_reduce(flag)
+    eng.lib.b2m_comm_destroy(comm)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SLAB_NCCL_ABORT", "PASS" if int(flag.item()) == 0 else "FAIL: some rank did not fail", flush=True)
+    sys.exit(0)
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -25,7 +51,10 @@ def main():
     comm = slabs.nccl_comm_from_torch(eng, dist, rank, world)
     vols = cases.volumes()
     failures = 0
-    for name in ("blobs2", "gyroid160", "sphere64", "bet"):
+    if "--inject-failure" in sys.argv:
+        return inject_failure(eng, comm, dist, rank, world, vols)
+    names = os.environ.get("B2M_TEST_VOLS", "blobs2,gyroid160,sphere64,bet").split(",")
+    for name in names:
         vol, iso = vols[name]
         cuts = slabs.partition(vol.shape[0], world)
         for backend, omc, ps, ol, fb in cases.flag_sets(name):

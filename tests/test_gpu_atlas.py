@@ -130,3 +130,27 @@ def test_atlas_d99_golden(eng):
         assert resets == big["resets"] == [127, 180, 188, 192]
     finally:
         d.free()
+
+
+def test_atlas_all_labels_in_one_call(eng):
+    """b2m_atlas_meshify_all(): the label loop inside the library, labels spread over worker contexts; every label equals
+    the reference's recorded mesh (golden_big.json), the skipped ones are the reference's skipped ones"""
+    from nii2mesh_b200 import synth
+    big = json.loads((GOLDEN / "golden_big.json").read_text())["atlas"]
+    vol, _ = synth.load_nifti(GOLDEN / "D99_atlas_v2.0_right.nii.gz")
+    d = eng.upload(vol)
+    try:
+        for workers in (1, 8):
+            res = eng.atlas_meshify_all(d, 0.5, 0, 1, 0, 0, workers=workers, fetch=True)
+            assert len(res) == big["nlabel"]
+            for lab, e in res.items():
+                g = big["labels"][str(lab)]
+                assert e["nvox"] == g["nvox"], lab
+                if g["nvox"] == 0:
+                    assert e["rc"] == -100, lab
+                    continue
+                assert e["rc"] == 0 and (e["nverts"], e["ntris"]) == (g["nverts"], g["ntris"]), lab
+                assert topology_digest(e["verts"], e["tris"])[2] == g["digest"], lab
+                assert bool(e["iso_reset"]) == (lab in big["resets"]), lab
+    finally:
+        d.free()

@@ -10,17 +10,39 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def test_slabs_over_nccl(libb2m):
+def _run_worker(libb2m, env, port, extra=()):
     ndev = libb2m.b2m_device_count()
     if ndev < 2:
         pytest.skip("one GPU on this box: the NCCL transport needs two (run under gpurun --gpus 2)")
     world = 4 if ndev >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", str(ROOT / "tests" / "slab_nccl_worker.py")]
+           "--master-port", str(port), str(ROOT / "tests" / "slab_nccl_worker.py"), *extra]
     p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
-                       env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1", **env))
     sys.stdout.write(p.stdout[-4000:])
+    return p
+
+
+def test_slabs_over_nccl(libb2m):
+    """default transport: scalar blocks through the node-local host segment, fast (sort-free) seam merge"""
+    p = _run_worker(libb2m, {}, 29533)
     assert p.returncode == 0 and "SLAB_NCCL_RESULT PASS" in p.stdout
+
+
+@pytest.mark.parametrize("env", [{"B2M_SCALARS_NCCL": "1"}, {"B2M_SEAM_ENT_CAP": "2", "B2M_SEAM_PAIR_CAP": "8"}, {"B2M_SEAM_SLOW": "1"}],
+                         ids=["scalars_by_nccl", "seam_block_overflow", "seam_slow_path"])
+def test_slabs_over_nccl_other_paths(libb2m, env):
+    """the scalar exchange as an NCCL all-gather (what ranks on different nodes use), and the sorted-list seam merge
+    (forced, and reached through the overflow of a tiny seam block)"""
+    p = _run_worker(libb2m, dict(env, B2M_TEST_VOLS="blobs2,bet"), 29534)
+    assert p.returncode == 0 and "SLAB_NCCL_RESULT PASS" in p.stdout
+
+
+def test_failed_rank_releases_its_peers(libb2m):
+    """a rank that fails on its own must not leave the others inside a collective: it poisons the host
+    segment, the peers' host waits notice, abort the communicator and return an error"""
+    p = _run_worker(libb2m, {}, 29535, extra=("--inject-failure",))
+    assert p.returncode == 0 and "SLAB_NCCL_ABORT PASS" in p.stdout
 
 
 def test_two_devices_in_one_process(libb2m):
