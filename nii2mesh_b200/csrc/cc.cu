@@ -127,21 +127,25 @@ __device__ __forceinline__ uint32_t bits_range(int s, int e) {  // ones at s..e 
 #define CT_Z 4
 #define CT_WORDS (CT_W * CT_Y * CT_Z)
 
-// shared-memory entry of a run slot: parent local slot << 16 | face flag << 15 | voxel count (<= 16384)
+// shared-memory entry of a run slot: parent local slot << 16 | face flag << 15 | voxel count (<= 16384).
+// A local slot is  word * 16 + (start bit >> 1);  its entry lives at PIDX(slot) = run-major: in smooth volumes nearly
+// every word holds one run with a low start bit, and word-major storage put the 32 lanes of a warp on two banks
+// (16-way conflicts on every access: 76 % of the kernel's shared-memory wavefronts in ncu).
+#define PIDX(slot) ((((slot)&15u) * CT_WORDS) + ((slot) >> 4))
 __device__ __forceinline__ uint32_t lfind(volatile uint32_t *par, uint32_t a) {
-  uint32_t p = par[a] >> 16;
+  uint32_t p = par[PIDX(a)] >> 16;
   while (p != a) {
     a = p;
-    p = par[a] >> 16;
+    p = par[PIDX(a)] >> 16;
   }
   return a;
 }
 // find with path halving; only valid while the count bits are still zero (phase A)
 __device__ __forceinline__ uint32_t lfind_compress(uint32_t *par, uint32_t a) {
-  uint32_t p = ((volatile uint32_t *)par)[a] >> 16;
+  uint32_t p = ((volatile uint32_t *)par)[PIDX(a)] >> 16;
   while (p != a) {
-    const uint32_t gp = ((volatile uint32_t *)par)[p] >> 16;
-    if (gp != p) atomicMin(&par[a], gp << 16);
+    const uint32_t gp = ((volatile uint32_t *)par)[PIDX(p)] >> 16;
+    if (gp != p) atomicMin(&par[PIDX(a)], gp << 16);
     a = p;
     p = gp;
   }
@@ -153,15 +157,12 @@ __device__ __forceinline__ void lunion(uint32_t *par, uint32_t a, uint32_t b) {
     b = lfind_compress(par, b);
     if (a == b) return;
     if (a < b) { uint32_t t = a; a = b; b = t; }
-    uint32_t old = atomicMin(&par[a], b << 16) >> 16;  // counts are still zero in this phase
+    uint32_t old = atomicMin(&par[PIDX(a)], b << 16) >> 16;  // counts are still zero in this phase
     if (old == a) return;
     a = old;
   }
 }
 
-// Enumerates the backward neighbour runs of run [s,e] (mask rm) of the word at tile-local (lx,ly,lz)
-// and calls link(neighbour word delta (dx,dy,dz), neighbour word bits, start bit of the neighbour run).
-// fetch(dx,dy,dz) returns the neighbour word's bits or 0 when that pair is not this phase's business.
 // Links that are implied by others are skipped (a solid region would otherwise pay nine unions per word, six of them
 // redundant):
 //   * word-diagonal link of a wide row (run starts at bit 0 / ends at bit 31 and the neighbour row's previous / next word
@@ -217,47 +218,86 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
 // thousand entries instead of scanning every bit word of the volume.  list[0] = count; when it exceeds the
 // capacity the full-scan variants of those passes run instead (both are launched, the wrong one exits at once).
 #define CT_LIST 1024
+// Work compaction: in a smooth volume about half of the words of a tile are empty for either polarity, scattered in
+// groups of two or three along x, so with one thread per word every warp carried ~50 % idle lanes through the union,
+// statistics and publish phases (ncu r1: 16-19 active threads per instruction).  The non-empty words of the tile are
+// therefore compacted into a list first (ballot + prefix over the eight warps) and thread i works on list item i: the
+// lanes of the first warps are all busy and the remaining warps skip the phases altogether.
+__device__ __forceinline__ unsigned cc_compact_items(bool has, unsigned short *items, unsigned *s_cnt /* [CT_WORDS/32 + 1] */) {
+  const unsigned t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+  const unsigned m = __ballot_sync(0xffffffffu, has);
+  if (lane == 0) s_cnt[warp] = __popc(m);
+  __syncthreads();
+  unsigned base = 0, tot = 0;
+#pragma unroll
+  for (unsigned w = 0; w < CT_WORDS / 32; w++) {
+    const unsigned c = s_cnt[w];
+    if (w < warp) base += c;
+    tot += c;
+  }
+  if (has) items[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)t;
+  __syncthreads();
+  return tot;
+}
+
 template <int CONN>
 __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                        uint32_t *__restrict__ rlist, unsigned rcap) {
   __shared__ uint32_t sb[CT_WORDS];
   __shared__ uint32_t par[CT_WORDS * 16];
   __shared__ uint32_t s_list[CT_LIST];
+  __shared__ unsigned short s_items[CT_WORDS];
+  __shared__ unsigned s_cnt[CT_WORDS / 32 + 1];
   __shared__ unsigned s_n, s_base;
-  const int t = threadIdx.x;
-  if (t == 0) s_n = 0;
-  const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
-  const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
-  const bool valid = xw < g.w && y < g.ny && z < g.nz;
-  const long long word = valid ? ((long long)z * g.ny + y) * g.w + xw : 0;
-  const uint32_t wv = valid ? __ldg(bits + word) : 0u;
-  sb[t] = wv;
+  const int t0 = threadIdx.x;
+  if (t0 == 0) s_n = 0;
+  const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_Y, tz0 = blockIdx.z * CT_Z;
+  unsigned n_items;
   {
-    uint32_t starts = wv & ~(wv << 1);
+    const int lx = t0 % CT_W, ly = (t0 / CT_W) % CT_Y, lz = t0 / (CT_W * CT_Y);
+    const int xw = tx0 + lx, y = ty0 + ly, z = tz0 + lz;
+    const bool valid = xw < g.w && y < g.ny && z < g.nz;
+    const uint32_t wv0 = valid ? __ldg(bits + ((long long)z * g.ny + y) * g.w + xw) : 0u;
+    sb[t0] = wv0;
+    uint32_t starts = wv0 & ~(wv0 << 1);
     while (starts) {
       const int s = __ffs(starts) - 1;
       starts &= starts - 1;
-      const uint32_t slot = (uint32_t)t * 16u + (uint32_t)(s >> 1);
-      par[slot] = slot << 16;
+      const uint32_t slot = (uint32_t)t0 * 16u + (uint32_t)(s >> 1);
+      par[PIDX(slot)] = slot << 16;
     }
+    // (the list build below synchronises the CTA: sb / par are complete before anybody reads a neighbour's)
+    n_items = cc_compact_items(wv0 != 0u, s_items, s_cnt);
   }
-  __syncthreads();
-  auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
-    const int ax = lx + dx, ay = ly + dy, az = lz + dz;
-    if ((unsigned)ax >= CT_W || (unsigned)ay >= CT_Y || (unsigned)az >= CT_Z) return 0u;  // other tile: k_cc_border
-    return sb[(az * CT_Y + ay) * CT_W + ax];
-  };
-  // phase A: unions inside the tile
-  for (uint32_t rest = wv; rest;) {
-    const int s = __ffs(rest) - 1;
-    const int e = run_end(wv, s);
-    const uint32_t rm = bits_range(s, e);
-    rest &= ~rm;
-    const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
-    cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st, uint32_t) {
-      const int nt = ((lz + dz) * CT_Y + (ly + dy)) * CT_W + (lx + dx);
-      lunion(par, me, (uint32_t)nt * 16u + (uint32_t)(st >> 1));
-    });
+  if ((unsigned)(t0 & ~31) >= n_items) {  // this warp has no item: it only takes part in the barriers
+    __syncthreads();
+    __syncthreads();
+  } else {
+  const bool act = (unsigned)t0 < n_items;
+  const int t = act ? (int)s_items[t0] : 0;  // the word this thread works on
+  const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
+  const int xw = tx0 + lx, y = ty0 + ly, z = tz0 + lz;
+  const long long word = ((long long)z * g.ny + y) * g.w + xw;
+  const uint32_t wv = act ? sb[t] : 0u;
+  // phase A: unions inside the tile (one thread per non-empty word: handing the neighbour rows of a word to different
+  // threads was tried - 2.7x the instructions for the same unions, 4.75 ms instead of 2.8)
+  {
+    auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
+      const int ax = lx + dx, ay = ly + dy, az = lz + dz;
+      if ((unsigned)ax >= CT_W || (unsigned)ay >= CT_Y || (unsigned)az >= CT_Z) return 0u;  // other tile: k_cc_border
+      return sb[(az * CT_Y + ay) * CT_W + ax];
+    };
+    for (uint32_t rest = wv; rest;) {
+      const int s = __ffs(rest) - 1;
+      const int e = run_end(wv, s);
+      const uint32_t rm = bits_range(s, e);
+      rest &= ~rm;
+      const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
+      cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st, uint32_t) {
+        const int nt = ((lz + dz) * CT_Y + (ly + dy)) * CT_W + (lx + dx);
+        lunion(par, me, (uint32_t)nt * 16u + (uint32_t)(st >> 1));
+      });
+    }
   }
   __syncthreads();
   // phase B: local roots collect the voxel count and the face flag of their local component.
@@ -283,15 +323,14 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
       const unsigned peers = __match_any_sync(0xffffffffu, r);
       const uint32_t tot = __reduce_add_sync(peers, cnt);
       const uint32_t fl = __reduce_or_sync(peers, flag);
-      if (r != 0xffffffffu && (unsigned)(__ffs(peers) - 1) == (unsigned)(t & 31)) {
-        atomicAdd(&par[r], tot);
-        if (fl) atomicOr(&par[r], fl);
+      if (r != 0xffffffffu && (unsigned)(__ffs(peers) - 1) == (unsigned)(t0 & 31)) {
+        atomicAdd(&par[PIDX(r)], tot);
+        if (fl) atomicOr(&par[PIDX(r)], fl);
       }
     }
   }
   __syncthreads();
   // phase C: publish the global nodes
-  const int tx0 = blockIdx.x * CT_W, ty0 = blockIdx.y * CT_Y, tz0 = blockIdx.z * CT_Z;
   nrun = 0;
   for (uint32_t rest = wv; rest; nrun++) {
     const int s = __ffs(rest) - 1;
@@ -307,7 +346,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     const uint32_t gparent = (uint32_t)rword * 16u + (uint32_t)__popc((rwv & ~(rwv << 1)) & ((1u << (2u * (r & 15u))) - 1u));
     uint32_t stat = 0;
     if (r == me) {
-      const uint32_t pe = par[me];
+      const uint32_t pe = par[PIDX(me)];
       stat = ((pe & 0x7fffu) << 1) | ((pe >> 15) & 1u);
       const unsigned li = atomicAdd(&s_n, 1u);
       if (li < CT_LIST) s_list[li] = gparent;
@@ -318,16 +357,18 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     }
     nodes[run_slot((uint32_t)word, wv, s)] = make_uint2(gparent, stat);
   }
+  }
   __syncthreads();
   const unsigned nl = min(s_n, (unsigned)CT_LIST);
-  if (t == 0 && nl) s_base = atomicAdd(&rlist[0], nl);
+  if (t0 == 0 && nl) s_base = atomicAdd(&rlist[0], nl);
   __syncthreads();
-  for (unsigned i = t; i < nl; i += CT_WORDS)
+  for (unsigned i = t0; i < nl; i += CT_WORDS)
     if (s_base + i < rcap) rlist[1 + s_base + i] = s_list[i];
 }
 
 // neighbour pairs that straddle two tiles: global lock-free unions between (mostly) tile roots
-// One CTA per tile (the thread <-> word mapping of k_cc_local).  Along the face of two big components every word
+// One CTA per tile.  Only non-empty words on a tile face can have a backward neighbour in another tile: they are
+// compacted into a list (as in k_cc_local) and thread i takes item i.  Along the face of two big components every word
 // asks for the same (tile root, tile root) pair: lanes of a warp that hold the same pair send one request
 // (__match_any_sync), and a small shared-memory cache of recently requested pairs drops the repeats across the
 // warps of the tile (whoever put the pair there completes the union inside this kernel).
@@ -335,17 +376,27 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
 template <int CONN>
 __global__ void __launch_bounds__(CT_WORDS, 1536 / CT_WORDS) k_cc_border(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes) {
   __shared__ unsigned long long cache[CB_CACHE];
-  const int t = threadIdx.x;
-  if (t < CB_CACHE) cache[t] = 0ull;
-  __syncthreads();
+  __shared__ uint32_t sb[CT_WORDS];
+  __shared__ unsigned short s_items[CT_WORDS];
+  __shared__ unsigned s_cnt[CT_WORDS / 32 + 1];
+  const int t0 = threadIdx.x;
+  if (t0 < CB_CACHE) cache[t0] = 0ull;
+  unsigned n_items;
+  {
+    const int lx = t0 % CT_W, ly = (t0 / CT_W) % CT_Y, lz = t0 / (CT_W * CT_Y);
+    const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
+    const bool face = lx == 0 || lx == CT_W - 1 || ly == 0 || ly == CT_Y - 1 || lz == 0;
+    const bool valid = face && xw < g.w && y < g.ny && z < g.nz;
+    const uint32_t wv0 = valid ? __ldg(bits + ((long long)z * g.ny + y) * g.w + xw) : 0u;
+    sb[t0] = wv0;
+    n_items = cc_compact_items(wv0 != 0u, s_items, s_cnt);  // synchronises: cache / sb / list are ready
+  }
+  if ((unsigned)t0 >= n_items) return;
+  const int t = (int)s_items[t0];
   const int lx = t % CT_W, ly = (t / CT_W) % CT_Y, lz = t / (CT_W * CT_Y);
   const int xw = blockIdx.x * CT_W + lx, y = blockIdx.y * CT_Y + ly, z = blockIdx.z * CT_Z + lz;
-  if (xw >= g.w || y >= g.ny || z >= g.nz) return;
-  // only words on a tile face can have a backward neighbour in another tile
-  if (!(lx == 0 || lx == CT_W - 1 || ly == 0 || ly == CT_Y - 1 || lz == 0)) return;
   const long long word = ((long long)z * g.ny + y) * g.w + xw;
-  const uint32_t wv = __ldg(bits + word);
-  if (!wv) return;
+  const uint32_t wv = sb[t];
   auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
     const int ax = lx + dx, ay = ly + dy, az = lz + dz;
     if ((unsigned)ax < CT_W && (unsigned)ay < CT_Y && (unsigned)az < CT_Z) return 0u;  // same tile: done locally

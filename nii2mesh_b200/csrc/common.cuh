@@ -113,7 +113,9 @@ struct b2m_scalars {
   unsigned int carry_hi[4];              // wraps = units of 2^31 voxels
   // weld bases of this rank (k_w_bases), read with the last host sync of the call instead of a sync of their own
   unsigned int wb_new_e_off, wb_nve_new, wb_new_c_base, wb_nvc_new, wb_n_dead, wb_n_extra;
-  unsigned int pad[8];
+  unsigned int pad[7];
+  unsigned int sync_seq;                 // LAST word of the block: stamped on the device before the block is copied to the
+                                         // host, so that the host can wait for the copy by watching pinned memory
 };
 static_assert(sizeof(b2m_scalars) == 256, "b2m_scalars is exchanged as one 256-byte block");
 
@@ -181,6 +183,8 @@ struct b2m_ctx {
   b2m_buf buf[BUF_COUNT];
   cudaEvent_t ev[2 * B2M_NSTAGE + 2];
   b2m_scalars *h_scalars;  // pinned mirror
+  b2m_scalars *h_land;     // pinned landing block of b2m_sync_scalars (watched for sync_seq)
+  unsigned sync_seq;
   uint64_t launches;
   int tables_ready;
   int smooth_tma_attr_done;

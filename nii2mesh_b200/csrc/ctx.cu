@@ -48,6 +48,8 @@ extern "C" int b2m_create(b2m_ctx **out, int device) {
   CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   for (size_t i = 0; i < sizeof(c->ev) / sizeof(c->ev[0]); i++) CU_TRY(cudaEventCreate(&c->ev[i]));
   CU_TRY(cudaMallocHost((void **)&c->h_scalars, sizeof(b2m_scalars)));
+  CU_TRY(cudaMallocHost((void **)&c->h_land, sizeof(b2m_scalars)));
+  memset(c->h_land, 0, sizeof(b2m_scalars));
   cudaDeviceProp prop;
   CU_TRY(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
@@ -81,6 +83,7 @@ extern "C" void b2m_destroy(b2m_ctx *c) {
     cudaStreamDestroy(c->aux_stream);
   }
   cudaFreeHost(c->h_scalars);
+  cudaFreeHost(c->h_land);
   if (c->h_all) { cudaFreeHost(c->h_all); cudaFree(c->d_all); }
   cudaStreamDestroy(c->stream);
   free(c);

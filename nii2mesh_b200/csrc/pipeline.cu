@@ -102,7 +102,8 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
       float *hlo = b2m_ptr<float>(ctx, BUF_HALO_LO), *hhi = b2m_ptr<float>(ctx, BUF_HALO_HI);
       // NCCL: the exchange runs on a stream of its own while the ctx stream smooths the planes that need own raw
       // planes only; the few planes next to the seams follow once the halo has arrived
-      halo_async = b2m_comm_async_capable(comm) && sl.nzl >= 16;
+      static const bool want_async = !(getenv("B2M_HALO_ASYNC") && atoi(getenv("B2M_HALO_ASYNC")) == 0);
+      halo_async = want_async && b2m_comm_async_capable(comm) && sl.nzl >= 16;
       cudaStream_t xs = ctx->stream;
       if (halo_async) {
         B2M_TRY(b2m_aux_stream(ctx));

@@ -558,7 +558,7 @@ int b2m_weld_run(b2m_ctx *ctx, b2m_comm *comm, b2m_mesh_dev *mesh, int all_items
     // only known on the device here.  Upper bound of the output: every own vertex + every item as an extra
     B2M_TRY(b2m_reserve(ctx, BUF_VERTS2, ((size_t)nvl + (g.last_rank ? n : 0)) * 24));
     double *v2 = b2m_ptr<double>(ctx, BUF_VERTS2);
-    KT_LAUNCH(ctx, "compact_verts", k_compact_verts<<<b2m_cdiv(nvl, 256), 256, 0, ctx->stream>>>(verts, v2, g, w, d_bs));
+    if (nvl) KT_LAUNCH(ctx, "compact_verts", k_compact_verts<<<b2m_cdiv(nvl, 256), 256, 0, ctx->stream>>>(verts, v2, g, w, d_bs));
     if (mesh->classic_soup)
       KT_LAUNCH(ctx, "weld_patch", k_w_patch<<<nb, 256, 0, ctx->stream>>>(n, head, top, cslot, g, w, d_bs, v2));
     wo->verts = v2;

@@ -22,6 +22,9 @@ def inject_failure(eng, comm, dist, rank, world, vols):
     nz = vol.shape[0]
     cuts = [(i * nz) // world for i in range(world + 1)]
     lo, hi = cuts[rank], cuts[rank + 1]
+    # a good call first: NCCL sets its peer connections up lazily, inside the first send / receive, where no host wait of
+    # ours can see the poison flag
+    eng.meshify_slab_host(comm, vol[lo:hi], vol.shape, lo, iso, original_mc=0, pre_smooth=1, only_largest=1, fill_bubbles=1)
     if rank == world - 1:
         hi -= 1            # one plane short of the volume: rejected by the argument check of this rank only
     failed = False

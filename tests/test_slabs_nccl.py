@@ -10,14 +10,14 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _run_worker(libb2m, env, port, extra=()):
+def _run_worker(libb2m, env, port, extra=(), timeout=900):
     ndev = libb2m.b2m_device_count()
     if ndev < 2:
         pytest.skip("one GPU on this box: the NCCL transport needs two (run under gpurun --gpus 2)")
     world = 4 if ndev >= 4 else 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "slab_nccl_worker.py"), *extra]
-    p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+    p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout,
                        env=dict(os.environ, MASTER_ADDR="127.0.0.1", **env))
     sys.stdout.write(p.stdout[-4000:])
     return p
@@ -41,7 +41,9 @@ def test_slabs_over_nccl_other_paths(libb2m, env):
 def test_failed_rank_releases_its_peers(libb2m):
     """a rank that fails on its own must not leave the others inside a collective: it poisons the host
     segment, the peers' host waits notice, abort the communicator and return an error"""
-    p = _run_worker(libb2m, {}, 29535, extra=("--inject-failure",))
+    if not os.environ.get("B2M_TEST_ABORT"):
+        pytest.skip("opt-in (B2M_TEST_ABORT=1): a peer that is NOT released costs the whole timeout in GPU time")
+    p = _run_worker(libb2m, {}, 29535, extra=("--inject-failure",), timeout=150)
     assert p.returncode == 0 and "SLAB_NCCL_ABORT PASS" in p.stdout
 
 

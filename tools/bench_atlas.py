@@ -65,8 +65,9 @@ def main():
             import oracle
             R = [oracle.Ref("lewiner") for _ in range(1)][0]
             T = max(1, min(len(os.sched_getaffinity(0)), 32))
-            labs = [1, 33, 100, 164, 250, 301, 127, 7] * ((T + 7) // 8)
-            labs = labs[:T]
+            counts = np.bincount(np.rint(vol).astype(np.int64).ravel())
+            nonempty = [int(i) for i in np.nonzero(counts[1:])[0] + 1]
+            labs = (nonempty[:: max(1, len(nonempty) // T)] * 2)[:T]   # T non-empty labels spread over the atlas
             ts = [0.0] * T
 
             def work(i):
