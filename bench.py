@@ -316,7 +316,8 @@ def main():
     ap.add_argument("--size", type=int, default=1024, help="cube edge of the per-GPU volume (multiple of 128)")
     ap.add_argument("--impl", default="b2m")
     ap.add_argument("--volume", type=int, default=0, help="strong scaling: ONE cube of this edge (e.g. 2048) cut into --gpus z-slabs")
-    ap.add_argument("--no-verify", action="store_true", help="skip the N > 1 parity pre-pass")
+    ap.add_argument("--no-verify", action="store_true", help="skip the N > 1 parity pass")
+    ap.add_argument("--verify-first", action="store_true", help="run the parity pass before the timed steps instead of after them")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -369,7 +370,7 @@ def main():
         comm = slabs.nccl_comm_from_torch(eng, dist, rank, world)
 
     parity = None
-    if world > 1 and not args.no_verify:
+    if world > 1 and not args.no_verify and args.verify_first:
         parity = verify_slabs(eng, comm, dist, rank, world, tile)
 
     def step():
@@ -411,6 +412,8 @@ def main():
         for name, ms in ks:
             ktot[name] = ktot.get(name, 0.0) + ms
             kcnt[name] = kcnt.get(name, 0) + 1
+    if world > 1 and not args.no_verify and not args.verify_first:
+        parity = verify_slabs(eng, comm, dist, rank, world, tile)
     nv, nt = r.nverts, r.ntris                      # global counts
     if world == 1:
         lnv, lnt = nv, nt

@@ -13,6 +13,14 @@
  *     B2M_CLASSIC_CUBES=1 or b2m_set_default_backend() (include/b2m.h).
  *   - *t and *p are malloc() blocks owned by the caller, exactly as in the reference
  *     (src/nii2mesh.c:353-354; quadric_simplify_mesh free()s them, src/quadric.c:402,412).
+ *   - ARRAY ORDER: triangles come in the reference's order (cube raster order, the removed ones dropped).  Vertices
+ *     come in the reference's marching-cubes EMISSION order with the welded-away ones dropped, whereas the reference's
+ *     unify_vertices() renumbers the vertices by its radix-sort key (distance from the first vertex) whenever at least
+ *     one pair merges (src/meshify.c:88-100).  The mesh is the same - same positions, same triangles after relabelling:
+ *     that is what the tests compare, after canonical sorting - but the arrays are not element-for-element identical, so
+ *     order-dependent consumers (the reference's quadric_simplify_mesh(), src/quadric.c:396-518, run for -r < 1) can
+ *     produce a different, equally valid simplification.  Sorting 43 M vertices by key and relabelling 87 M triangles
+ *     would cost about a third of the whole 1024^3 step, for an order no caller of meshify() depends on.
  */
 #ifndef MESHIFY_H
 #define MESHIFY_H

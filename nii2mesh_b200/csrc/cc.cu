@@ -180,6 +180,10 @@ __device__ __forceinline__ void cc_visit_neighbours(uint32_t rm, int s, int e, F
     uint32_t m = rm;
     if (wide) m |= (rm << 1) | (rm >> 1);
     uint32_t t = nw & m;
+    if (nw == 0xffffffffu) {  // a solid word is one run (the common neighbour inside a thick region): no bit scans
+      if (!(rm & covered)) link(0, dy, dz, 0, nw);
+      t = 0u;
+    }
     while (t) {
       const int b = __ffs(t) - 1;
       const int st = run_start(nw, b);
@@ -244,6 +248,9 @@ template <int CONN>
 __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restrict__ bits, cc_geom g, cc_nodes nodes,
                                                        uint32_t *__restrict__ rlist, unsigned rcap) {
   __shared__ uint32_t sb[CT_WORDS];
+  // the same words with a one-word border of zeros below / before / around (z-1, y-1 .. y+1, x-1 .. x+1): a neighbour
+  // fetch is one load at a constant offset, without bounds tests (words of other tiles read as empty: k_cc_border's job)
+  __shared__ uint32_t sbp[(CT_Z + 1) * (CT_Y + 2) * (CT_W + 2)];
   __shared__ uint32_t par[CT_WORDS * 16];
   __shared__ uint32_t s_list[CT_LIST];
   __shared__ unsigned short s_items[CT_WORDS];
@@ -259,6 +266,11 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
     const bool valid = xw < g.w && y < g.ny && z < g.nz;
     const uint32_t wv0 = valid ? __ldg(bits + ((long long)z * g.ny + y) * g.w + xw) : 0u;
     sb[t0] = wv0;
+    for (int i = t0; i < (CT_Z + 1) * (CT_Y + 2) * (CT_W + 2); i += CT_WORDS) {
+      const int px = i % (CT_W + 2), py = (i / (CT_W + 2)) % (CT_Y + 2), pz = i / ((CT_W + 2) * (CT_Y + 2));
+      if (px == 0 || px == CT_W + 1 || py == 0 || py == CT_Y + 1 || pz == 0) sbp[i] = 0u;
+    }
+    sbp[((lz + 1) * (CT_Y + 2) + (ly + 1)) * (CT_W + 2) + (lx + 1)] = wv0;
     uint32_t starts = wv0 & ~(wv0 << 1);
     while (starts) {
       const int s = __ffs(starts) - 1;
@@ -282,11 +294,8 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
   // phase A: unions inside the tile (one thread per non-empty word: handing the neighbour rows of a word to different
   // threads was tried - 2.7x the instructions for the same unions, 4.75 ms instead of 2.8)
   {
-    auto fetch = [&](int dx, int dy, int dz) -> uint32_t {
-      const int ax = lx + dx, ay = ly + dy, az = lz + dz;
-      if ((unsigned)ax >= CT_W || (unsigned)ay >= CT_Y || (unsigned)az >= CT_Z) return 0u;  // other tile: k_cc_border
-      return sb[(az * CT_Y + ay) * CT_W + ax];
-    };
+    const uint32_t *ctr = sbp + ((lz + 1) * (CT_Y + 2) + (ly + 1)) * (CT_W + 2) + (lx + 1);
+    auto fetch = [&](int dx, int dy, int dz) -> uint32_t { return ctr[(dz * (CT_Y + 2) + dy) * (CT_W + 2) + dx]; };
     for (uint32_t rest = wv; rest;) {
       const int s = __ffs(rest) - 1;
       const int e = run_end(wv, s);

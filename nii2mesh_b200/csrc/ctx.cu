@@ -1,5 +1,6 @@
 // ctx.cu — context, workspace arena, memory helpers of libb2m.
 #include <stdarg.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "common.cuh"
@@ -161,14 +162,21 @@ static bool host_is_pinned(const void *p) {
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
 }
+static int par_threads(void);
+static bool pool_feeder_sleeps(void) { return par_threads() <= 8; }
 static int stage_init(b2m_ctx *ctx) {
   for (int i = 0; i < 3; i++)
     if (!ctx->stage[i]) {
       CU_TRY(cudaMallocHost(&ctx->stage[i], B2M_STAGE_BYTES));
       CU_TRY(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     }
+  // few cores per rank (<= 8 copy threads): blocking-sync events - the thread that feeds the ring SLEEPS until the next
+  // chunk has landed instead of spinning, and one more copy worker takes its core
+  // (measured at G1024: with 4 threads the D2H leg takes 54 ms instead of 72; with 16 threads sleeping costs 10 ms, so
+  // a rank that has cores to spare keeps the spinning wait)
+  const unsigned evflags = cudaEventDisableTiming | (pool_feeder_sleeps() ? cudaEventBlockingSync : 0u);
   for (int i = 0; i < B2M_RING_SLOTS; i++)
-    if (!ctx->ring_ev[i]) CU_TRY(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+    if (!ctx->ring_ev[i]) CU_TRY(cudaEventCreateWithFlags(&ctx->ring_ev[i], evflags));
   return B2M_OK;
 }
 // multi-threaded memcpy (first-touch page faults of a fresh malloc() block dominate a single-threaded copy).
@@ -251,6 +259,7 @@ struct copy_pool {
   // done[slot] counts the copied slices of the chunk that occupies a ring slot
   char *const *ring = nullptr;
   long long spc = 0;
+  int nslots = B2M_RING_SLOTS;
   int widen = 0;  // the ring holds f32 values that land in dst as f64 (slices and p->n count OUTPUT bytes)
   std::atomic<int> ready{0};
   std::atomic<int> done[B2M_RING_SLOTS];
@@ -281,9 +290,9 @@ static void pool_work(copy_pool *p) {
         else futex_wait(&p->ready, r);  // returns at once if ready moved on in the meantime
       }
       const size_t o = (size_t)i * p->slice, oc = (size_t)(i - c * p->spc) * p->slice, len = p->n - o < p->slice ? p->n - o : p->slice;
-      if (p->widen) b2m_stream_widen((double *)(p->dst + o), (const float *)(p->ring[c % B2M_RING_SLOTS] + oc / 2), len / 8);
-      else b2m_stream_copy(p->dst + o, p->ring[c % B2M_RING_SLOTS] + oc, len);
-      p->done[c % B2M_RING_SLOTS].fetch_add(1, std::memory_order_release);
+      if (p->widen) b2m_stream_widen((double *)(p->dst + o), (const float *)(p->ring[c % p->nslots] + oc / 2), len / 8);
+      else b2m_stream_copy(p->dst + o, p->ring[c % p->nslots] + oc, len);
+      p->done[c % p->nslots].fetch_add(1, std::memory_order_release);
     } else if (p->src) {
       const size_t o = (size_t)i * p->slice;
       memcpy(p->dst + o, p->src + o, p->n - o < p->slice ? p->n - o : p->slice);
@@ -328,7 +337,8 @@ static void pool_acquire(copy_pool *p) {
 }
 static void pool_ensure_threads(copy_pool *p, int nt) {  // pool owned
   if (p->started) return;
-  for (int i = 0; i < nt - 1; i++) {
+  const int nworkers = pool_feeder_sleeps() ? nt : nt - 1;  // the caller copies too, unless it only feeds the ring and sleeps
+  for (int i = 0; i < nworkers; i++) {
     pthread_t t;
     if (pthread_create(&t, nullptr, pool_main, p) == 0) { pthread_detach(t); p->started++; }
   }
@@ -446,43 +456,48 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
     CU_TRY(cudaStreamSynchronize(ctx->stream));
     return B2M_OK;
   }
-  const size_t CH = B2M_RING_CHUNK << widen;  // output bytes per ring chunk
+  // DMA granule and ring depth: B2M_RING_CHUNK_KB (power of two, 1024 .. 32768; default 8192) x B2M_RING_SLOTS (2 .. 12;
+  // default 12).  A ring that fits the last-level cache keeps the DMA -> copy hand-over out of host DRAM.
+  static const size_t RCH = [] { const char *e = getenv("B2M_RING_CHUNK_KB"); long v = e ? atol(e) : 8192; if (v < 1024 || v > 32768 || (v & (v - 1))) v = 8192; return (size_t)v << 10; }();
+  static const int RSL = [] { const char *e = getenv("B2M_RING_SLOTS"); int v = e ? atoi(e) : B2M_RING_SLOTS; if (v < 2 || v > B2M_RING_SLOTS) v = B2M_RING_SLOTS; return v; }();
+  const size_t CH = RCH << widen;  // output bytes per ring chunk
   B2M_TRY(stage_init(ctx));
   copy_pool *p = &g_pool;
   char *ring[B2M_RING_SLOTS];
-  const int per_buf = (int)(B2M_STAGE_BYTES / B2M_RING_CHUNK);
-  for (int k = 0; k < B2M_RING_SLOTS; k++) ring[k] = (char *)ctx->stage[k / per_buf] + (size_t)(k % per_buf) * B2M_RING_CHUNK;
+  const int per_buf = (int)(B2M_STAGE_BYTES / RCH);
+  for (int k = 0; k < RSL; k++) ring[k] = (char *)ctx->stage[k / per_buf] + (size_t)(k % per_buf) * RCH;
   const long long nchunk = (long long)((bytes + CH - 1) / CH);
   auto chunk_bytes = [&](long long c) { const size_t o = (size_t)c * CH; return bytes - o < CH ? bytes - o : CH; };
   auto issue = [&](long long c) -> cudaError_t {
-    cudaError_t e = cudaMemcpyAsync(ring[c % B2M_RING_SLOTS], (const char *)d_src + (size_t)c * B2M_RING_CHUNK, chunk_bytes(c) >> widen,
+    cudaError_t e = cudaMemcpyAsync(ring[c % RSL], (const char *)d_src + (size_t)c * RCH, chunk_bytes(c) >> widen,
                                     cudaMemcpyDeviceToHost, ctx->stream);
     if (e != cudaSuccess) return e;
-    return cudaEventRecord(ctx->ring_ev[c % B2M_RING_SLOTS], ctx->stream);
+    return cudaEventRecord(ctx->ring_ev[c % RSL], ctx->stream);
   };
   const int nt = par_threads();
   pool_acquire(p);
   p->dst = (char *)h_dst; p->src = nullptr; p->n = bytes;
   p->nslices = (long long)((bytes + p->slice - 1) / p->slice);
-  p->ring = ring; p->spc = (long long)(CH / p->slice); p->widen = widen;
+  p->ring = ring; p->spc = (long long)(CH / p->slice); p->widen = widen; p->nslots = RSL;
   p->ready.store(0);
   for (int k = 0; k < B2M_RING_SLOTS; k++) p->done[k].store(0);
   long long issued = 0;
   cudaError_t err = cudaSuccess;
-  for (; issued < nchunk && issued < B2M_RING_SLOTS && err == cudaSuccess; issued++) err = issue(issued);
+  for (; issued < nchunk && issued < RSL && err == cudaSuccess; issued++) err = issue(issued);
   auto slot_free = [&](long long c) {  // every slice of chunk c has left its ring slot
     const long long need = (long long)((chunk_bytes(c) + p->slice - 1) / p->slice);
-    return p->done[c % B2M_RING_SLOTS].load(std::memory_order_acquire) >= need;
+    return p->done[c % RSL].load(std::memory_order_acquire) >= need;
   };
   auto refill = [&](bool must) {
     while (err == cudaSuccess && issued < nchunk) {
-      const long long prev = issued - B2M_RING_SLOTS;
+      const long long prev = issued - RSL;
       if (!slot_free(prev)) {
         if (!must) break;
-        cpu_relax();
+        struct timespec ts = {0, 20000};  // the copy threads are behind the DMA engine: leave them the core
+        nanosleep(&ts, nullptr);
         continue;
       }
-      p->done[prev % B2M_RING_SLOTS].store(0);
+      p->done[prev % RSL].store(0);
       err = issue(issued++);
       must = false;
     }
@@ -492,15 +507,15 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
   for (long long c = 0; c < nchunk && err == cudaSuccess; c++) {
     if (issued <= c) refill(true);
     if (err != cudaSuccess) break;
-    err = cudaEventSynchronize(ctx->ring_ev[c % B2M_RING_SLOTS]);
+    err = cudaEventSynchronize(ctx->ring_ev[c % RSL]);
     if (err != cudaSuccess) break;
     p->ready.store((int)(c + 1), std::memory_order_release);
     futex_wake_all(&p->ready);
     if (alone) {
       const size_t o = (size_t)c * CH;
-      if (widen) b2m_stream_widen((double *)((char *)h_dst + o), (const float *)ring[c % B2M_RING_SLOTS], chunk_bytes(c) / 8);
-      else b2m_stream_copy((char *)h_dst + o, ring[c % B2M_RING_SLOTS], chunk_bytes(c));
-      p->done[c % B2M_RING_SLOTS].store((int)p->spc);
+      if (widen) b2m_stream_widen((double *)((char *)h_dst + o), (const float *)ring[c % RSL], chunk_bytes(c) / 8);
+      else b2m_stream_copy((char *)h_dst + o, ring[c % RSL], chunk_bytes(c));
+      p->done[c % RSL].store((int)p->spc);
     }
     refill(false);
   }
