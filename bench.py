@@ -107,6 +107,16 @@ def known_counts(gshape):
     return f(79416, 15152, -470), f(158848, 30304, -944)
 
 
+def workload_string(world, n, gshape, strong=False):
+    """config.workload: the same string on the b2m arm and on the reference arm"""
+    if world == 1:
+        return f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])"
+    N = gshape[0] * gshape[1] * gshape[2] // world
+    return (f"gyroid+bumps {gshape[2]}x{gshape[1]}x{gshape[0]} f32 ({world} x {N} voxels), Lewiner MC33 "
+            f"-p1 -l1 -b1 iso 0, ONE volume in {world} z-slabs (BASELINE configs[4]" +
+            (" as written: the same cube at every GPU count)" if strong else " family; 2048^3 at 8 GPUs)"))
+
+
 def slab_volume(world, n):
     """global (nz, ny, nx) of the N-GPU workload: N * n^3 voxels, doubling x, then y, then z"""
     nz = ny = nx = n
@@ -254,8 +264,9 @@ def run_reference(args, rank, emit):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxels/s",
            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "gyroid+bumps f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2]); "
-                                  f"each step = {T} G{n} volumes of the same generator, one per host core (bounded sample)"},
+           "config": {"workload": workload_string(max(1, args.gpus), args.size, slab_volume(max(1, args.gpus), args.size)),
+                      "sample": f"each step = {T} G{n} volumes of the same generator and flags, one per host core (bounded sample "
+                                f"of the workload: the reference's per-voxel rate is flat in the volume size, BASELINE.md section 3)"},
            "cpu_baseline": {"value": val, "unit": "Gvoxels/s", "cores": T, "per_core_mvox_s": n ** 3 / dt / 1e6, "kind": kind, "cpu": cpu_model(),
                             "sample": f"{T} x G{n} ({n}^3 voxels) per step, {nv} verts {nt} tris each; meshify() is "
                                       f"single-threaded, one volume per core"},
@@ -496,8 +507,14 @@ def main():
         breakdown = None
         if world > 1:
             h, dv, dd = one.last
+            tt = torch.tensor([h, dv, dd], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(tt) for _ in range(world)]
+            dist.all_gather(allr, tt)
+            per_rank = [[round(float(x), 1) for x in a.tolist()] for a in allr]
             breakdown = {"h2d_ms": round(max_over_ranks(h), 2), "device_ms": round(max_over_ranks(dv), 2),
-                         "d2h_ms": round(max_over_ranks(dd), 2), "note": "max over ranks, last timed call"}
+                         "d2h_ms": round(max_over_ranks(dd), 2), "note": "max over ranks, last timed call; device_ms includes "
+                         "waiting in the collectives for ranks whose H2D finished later",
+                         "per_rank_h2d_device_d2h_ms": per_rank}
         if world == 1:
             # two untimed calls through b2m_meshify_host (what meshify() wraps) for the copy/compute breakdown
             r2 = lib.Result()
@@ -554,13 +571,10 @@ def main():
                  "source": "reference's pre-weld count law of the G family (exact fit on reference runs, tests/golden/golden_big.json)"}
         assert known["match"], f"pre-weld counts {r.pre_nverts}/{r.pre_ntris} differ from the reference's {exp}"
     if rank == 0:
+        workload = workload_string(world, n, gshape, strong)
         if world == 1:
-            workload = f"G{n} gyroid+bumps {n}^3 f32, Lewiner MC33 -p1 -l1 -b1 iso 0 (BASELINE configs[2])"
             par = "single GPU"
         else:
-            workload = (f"gyroid+bumps {gshape[2]}x{gshape[1]}x{gshape[0]} f32 ({world} x {N} voxels), Lewiner MC33 "
-                        f"-p1 -l1 -b1 iso 0, ONE volume in {world} z-slabs (BASELINE configs[4]" +
-                        (" as written: the same cube at every GPU count)" if strong else " family; 2048^3 at 8 GPUs)"))
             par = f"{world} z-slabs of {nzl} planes, one rank per GPU; NCCL halo/seam exchange (b2m_meshify_slab)"
         out = {"metric": METRIC, "value": value, "unit": "Gvoxels/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,

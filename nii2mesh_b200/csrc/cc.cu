@@ -122,10 +122,17 @@ __device__ __forceinline__ uint32_t bits_range(int s, int e) {  // ones at s..e 
 // the local roots the voxel count and face flag of the whole local component.  Only neighbour pairs
 // that straddle two tiles are left for the global union-find (k_cc_border), which therefore works
 // on a forest of a few tile-roots per tile instead of one node per run.
+#ifndef CT_W
 #define CT_W 8
+#endif
+#ifndef CT_Y
 #define CT_Y 8
+#endif
+#ifndef CT_Z
 #define CT_Z 4
+#endif
 #define CT_WORDS (CT_W * CT_Y * CT_Z)
+static_assert(CT_WORDS == 256, "the tile kernels assume 256 threads (eight warps)");
 
 // shared-memory entry of a run slot: parent local slot << 16 | face flag << 15 | voxel count (<= 16384).
 // A local slot is  word * 16 + (start bit >> 1);  its entry lives at PIDX(slot) = run-major: in smooth volumes nearly
@@ -277,6 +284,22 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
       starts &= starts - 1;
       const uint32_t slot = (uint32_t)t0 * 16u + (uint32_t)(s >> 1);
       par[PIDX(slot)] = slot << 16;
+    }
+    // uniform tiles: nothing to label in an empty one; a solid one (every word all ones, all inside the volume) is one
+    // component whose root is its first word - no unions, no statistics pass
+    const bool rowface0 = (y == 0) || (y == g.ny - 1) || (z == 0 && g.zface_lo) || (z == g.nz - 1 && g.zface_hi);
+    const int any = __syncthreads_or(wv0 != 0u);
+    if (!any) return;
+    if (__syncthreads_and(wv0 == 0xffffffffu)) {
+      const int faced = __syncthreads_or(rowface0 || xw == 0 || xw * 32 + 31 == g.nx - 1);
+      const uint32_t gparent = (uint32_t)(((long long)tz0 * g.ny + ty0) * g.w + tx0) * 16u;
+      const uint32_t stat = t0 == 0 ? (((uint32_t)CT_WORDS * 32u) << 1) | (faced ? 1u : 0u) : 0u;
+      nodes[(uint32_t)(((long long)z * g.ny + y) * g.w + xw) * 16u] = make_uint2(gparent, stat);
+      if (t0 == 0) {
+        const unsigned gi = atomicAdd(&rlist[0], 1u);
+        if (gi < rcap) rlist[1 + gi] = gparent;
+      }
+      return;
     }
     // (the list build below synchronises the CTA: sb / par are complete before anybody reads a neighbour's)
     n_items = cc_compact_items(wv0 != 0u, s_items, s_cnt);

@@ -235,6 +235,7 @@ bool b2m_host_is_pinned(const void *p);
 // start an asynchronous z-chunked H2D of a pinned volume; b2m_front_run waits chunk by chunk (ctx->pend_*)
 int b2m_h2d_chunked_begin(b2m_ctx *ctx, float *d_dst, const float *h_src, size_t nxy, int nz);
 int b2m_h2d_chunked_ms(b2m_ctx *ctx, float *ms);  // duration of the transfer started by the call above
+bool b2m_d2h_registers(void);  // the D2H of big pageable blocks registers the destination piecewise (few-threads mode)
 int b2m_copy_d2h_f32exact(b2m_ctx *ctx, double *h_dst, const double *d_src, size_t n, int *done);  // doubles that are all f32 values: 4 B each over PCIe
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb);
 void b2m_touch_wait(void);

@@ -525,7 +525,71 @@ static int copy_d2h_impl(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t by
   CU_TRY(err);
   return B2M_OK;
 }
-int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) { return copy_d2h_impl(ctx, h_dst, d_src, bytes, 0); }
+// EXPERIMENT, off unless B2M_D2H_REGISTER=1: the ring costs three passes over host DRAM (DMA into the ring, read it, write
+// the caller's block), and with eight ranks on a node the node's memory bandwidth, not PCIe, bounds the copy.  Here the
+// caller's block is registered piecewise and the DMA engine writes straight into it - ONE pass: 64 MiB pieces cut at
+// 2 MiB boundaries, a piece is registered while the previous ones are in flight and unregistered when its copy has
+// completed (the block goes back to the caller, who free()s it).  Correct (tests/test_gpu_parity.py::
+// test_registered_destination_d2h_path) but NOT faster on the B200 boxes of this pool: the isolated measurement
+// (tools/hostcopy_bench.cu: 2.7 ms per transparent-huge-page backed piece) does not carry over to the output blocks of a
+// real call - 693 ms for the 2 GB mesh of G1024 with 4 pool threads, 358 ms with 16, against 55 / 35 ms through the ring.
+static bool d2h_register_wanted(void) {
+  static const int v = [] { const char *e = getenv("B2M_D2H_REGISTER"); return e ? atoi(e) : -1; }();
+  return v > 0;
+}
+static int copy_d2h_registered(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, bool *done) {
+  *done = false;
+  const size_t PIECE = (size_t)64 << 20, PAGE = 4096;
+  enum { DEPTH = 3 };
+  const uintptr_t b0 = (uintptr_t)h_dst, b1 = b0 + bytes;
+  B2M_TRY(stage_init(ctx));  // the ring events serve as per-piece completion events
+  struct piece { uintptr_t r0, r1, c0, c1; };  // registered range (page aligned), copied range
+  piece win[DEPTH];
+  long long issued = 0, retired = 0;
+  cudaError_t err = cudaSuccess;
+  auto retire = [&]() {
+    piece &q = win[retired % DEPTH];
+    cudaError_t e = cudaEventSynchronize(ctx->ring_ev[retired % DEPTH]);
+    cudaError_t e2 = cudaHostUnregister((void *)q.r0);
+    retired++;
+    return e != cudaSuccess ? e : e2;
+  };
+  uintptr_t at = b0;
+  while (at < b1 && err == cudaSuccess) {
+    if (issued - retired == DEPTH) { err = retire(); if (err != cudaSuccess) break; }
+    piece q;
+    q.c0 = at;
+    q.r0 = at & ~(uintptr_t)(PAGE - 1);
+    uintptr_t end = ((at + PIECE) & ~(uintptr_t)(((size_t)2 << 20) - 1));  // pieces meet on 2 MiB boundaries: no shared page
+    if (end <= at || end > b1) end = b1;
+    q.c1 = end;
+    q.r1 = end == b1 ? ((b1 + PAGE - 1) & ~(uintptr_t)(PAGE - 1)) : end;
+    err = cudaHostRegister((void *)q.r0, q.r1 - q.r0, cudaHostRegisterDefault);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      if (issued == 0) return B2M_OK;  // this memory cannot be registered (nothing copied yet): the caller takes the ring
+      break;
+    }
+    err = cudaMemcpyAsync((void *)q.c0, (const char *)d_src + (q.c0 - b0), q.c1 - q.c0, cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaEventRecord(ctx->ring_ev[issued % DEPTH], ctx->stream);
+    win[issued % DEPTH] = q;
+    issued++;
+    at = end;
+  }
+  while (retired < issued) { const cudaError_t e = retire(); if (err == cudaSuccess) err = e; }
+  CU_TRY(err);
+  *done = true;
+  return B2M_OK;
+}
+int b2m_copy_d2h(b2m_ctx *ctx, void *h_dst, const void *d_src, size_t bytes) {
+  if (bytes >= ((size_t)64 << 20) && d2h_register_wanted() && !host_is_pinned(h_dst)) {
+    bool done = false;
+    B2M_TRY(copy_d2h_registered(ctx, h_dst, d_src, bytes, &done));
+    if (done) return B2M_OK;
+  }
+  return copy_d2h_impl(ctx, h_dst, d_src, bytes, 0);
+}
+bool b2m_d2h_registers(void) { return d2h_register_wanted(); }
 int b2m_copy_d2h_widen(b2m_ctx *ctx, double *h_dst, const float *d_src, size_t n) { return copy_d2h_impl(ctx, h_dst, d_src, n * 8, 1); }
 
 // f64 -> f32 copy of an array whose values are all exactly representable in f32 (Lewiner vertices are exported as

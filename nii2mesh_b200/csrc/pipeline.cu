@@ -398,8 +398,11 @@ static int host_out_finish(b2m_ctx *ctx, host_out *h, int rc, const void *d_vert
   if (rc == B2M_OK && nv) {
     // Lewiner positions are f32 values widened to f64: 12 instead of 24 bytes per vertex cross PCIe (checked on the
     // device; anything else - the classic back-end's FP64 positions - takes the plain copy)
+    // (in few-threads mode the doubles go straight into the registered block: one pass over host DRAM beats half the
+    // PCIe bytes when the node's memory bandwidth is the bound)
     int done = 0;
-    rc = b2m_copy_d2h_f32exact(ctx, (double *)h->v, (const double *)d_verts, nv * 3, &done);
+    if (!(b2m_d2h_registers() && nv * 24 >= ((size_t)64 << 20)))
+      rc = b2m_copy_d2h_f32exact(ctx, (double *)h->v, (const double *)d_verts, nv * 3, &done);
     if (rc == B2M_OK && !done) rc = b2m_copy_d2h(ctx, h->v, d_verts, nv * 24);
     h->pcie_bytes = nv * (done ? 12 : 24);
   }

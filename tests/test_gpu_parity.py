@@ -394,3 +394,29 @@ def test_pinned_input_overlapped_h2d(eng):
         assert np.array_equal(t, t2) and np.array_equal(v.view(np.uint64), v2.view(np.uint64))
     finally:
         L.b2m_host_free(hp)
+
+
+def test_registered_destination_d2h_path():
+    """few cores per rank (several ranks on one node): the output blocks are registered piecewise and the DMA engine
+    writes straight into them instead of going through the pinned ring.  Forced here with B2M_D2H_REGISTER=1 (read once
+    per process, hence the child process); G512: two blocks of 139 MB; the mesh must equal the recorded reference digest"""
+    import subprocess
+    import sys
+    code = (
+        "import json, sys, numpy as np\n"
+        "sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "from nii2mesh_b200 import lib, synth\n"
+        "from oracle.canon import topology_digest\n"
+        "eng = lib.Engine(0)\n"
+        "vol = np.tile(synth.gyroid_tile(128), (4, 4, 4))\n"
+        "for rep in range(2):\n"
+        "    v, t, r = eng.meshify(vol, 0.0, 0, 1, 1, 1, 0)\n"
+        "g = json.load(open('tests/golden/golden_big.json'))['gyroid']['512']\n"
+        "assert (len(v), len(t)) == (g['nverts'], g['ntris']), (len(v), len(t))\n"
+        "assert topology_digest(v, t)[2] == g['digest']\n"
+        "print('REGISTERED_D2H_OK', r.d2h_ms)\n")
+    from conftest import ROOT
+    import os
+    p = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, B2M_D2H_REGISTER="1"))
+    assert p.returncode == 0 and "REGISTERED_D2H_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
