@@ -58,10 +58,11 @@ def peaks():
 
 
 def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture
-    (profiles/r1_ncu_full_summary.csv: G1024, same flags; `ncu --set full`), or None"""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu capture of this
+    round's kernels (profiles/r2_ncu_full_summary.csv: G1024, same flags, `ncu --set full` of tools/profile_step.py;
+    a number taken under ncu can only be a committed one), or None"""
     import csv
-    p = ROOT / "profiles" / "r1_ncu_full_summary.csv"
+    p = ROOT / "profiles" / "r2_ncu_full_summary.csv"
     if not p.exists():
         return None
     try:
@@ -441,7 +442,9 @@ def main():
     step_bytes = 60 * GN + 24 * nv + 12 * nt
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None,
-                "traffic": ncu_traffic(top) if (world == 1 and n == 1024) else None, "peak_source": peak_src,
+                "traffic": ncu_traffic(top) if (world == 1 and n == 1024) else None,
+                "traffic_source": "profiles/r2_ncu_full_summary.csv (ncu --set full of the same kernels, G1024, committed with this code)",
+                "peak_source": peak_src,
                 "kernel_ms": top_ms, "kernel_share_of_step": ktot[top] / ms_step,
                 "algorithmic_bytes_per_launch": kb, "scope": "rank 0's GPU" if world > 1 else "the GPU",
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms_step * 1e-3) / 1e9,

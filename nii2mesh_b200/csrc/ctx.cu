@@ -378,7 +378,8 @@ static thread_local unsigned long long tl_touch_seq = 0;
 int b2m_touch_async(void *a, size_t na, void *b, size_t nb) {
   copy_pool *p = &g_pool;
   const int nt = par_threads();
-  if (nt <= 1 || na + nb < ((size_t)64 << 20)) return 0;
+  static const bool want = !(getenv("B2M_PREFAULT") && atoi(getenv("B2M_PREFAULT")) == 0);
+  if (!want || nt <= 1 || na + nb < ((size_t)64 << 20)) return 0;
   pool_acquire(p);
   p->src = nullptr; p->ring = nullptr;
   p->dst = (char *)a; p->n = na; p->dst2 = (char *)b; p->n2 = nb;

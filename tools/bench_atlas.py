@@ -26,6 +26,10 @@ from nii2mesh_b200 import lib, synth  # noqa: E402
 
 
 def main():
+    # ONE JSON line on stdout: the library prints the reference's own diagnostics there ("Suggested isolevel out of range
+    # ..." for the four labels whose isolevel is reset) - they go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--workers", default="1,4,8,16")
     ap.add_argument("--steps", type=int, default=5)
@@ -88,7 +92,7 @@ def main():
                                    "sample": f"{T} labels concurrently, one whole-volume meshify() each (the reference's OMP atlas loop)"}
         except Exception as ex:  # noqa: BLE001
             out["cpu_baseline"] = {"error": str(ex)}
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":
