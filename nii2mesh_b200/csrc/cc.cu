@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(CT_WORDS) k_cc_local(const uint32_t *__restric
       rest &= ~rm;
       const uint32_t me = (uint32_t)t * 16u + (uint32_t)(s >> 1);
       cc_visit_neighbours<CONN>(rm, s, e, fetch, [&](int dx, int dy, int dz, int st, uint32_t) {
-        const int nt = ((lz + dz) * CT_Y + (ly + dy)) * CT_W + (lx + dx);
+        const int nt = t + (dz * CT_Y + dy) * CT_W + dx;  // a constant offset at every (inlined) call site
         lunion(par, me, (uint32_t)nt * 16u + (uint32_t)(st >> 1));
       });
     }
