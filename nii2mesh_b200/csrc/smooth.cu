@@ -581,6 +581,160 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3_tma(const __grid_cons
   }
 }
 
+
+// ================================================================================================================
+// Warp-specialised variant (sm_100a; B2M_SMOOTH_WS=1): the two halves of the kernel above run in DIFFERENT warps with
+// different register budgets (`setmaxnreg`), so that 20 warps fit where the unified kernel holds 14 at 128 registers:
+//   warps 0..7   (two warpgroups, shrunk to 56 registers)   x pass: 3.5 staged rows per warp and plane, straight out of
+//                the TMA-fed raw ring; warp 0 also issues the tensor loads, two planes ahead
+//   warps 8..19  (three warpgroups, grown to 120 registers) y pass + streaming z pass of two output rows each, exactly
+//                as above (yz_pass2)
+// Hand-over through shared-memory rings with full / free mbarriers per slot (raw planes: 3 slots, x-pass planes: 4).
+#define WS_XW 8
+#define WS_CW (SX_TY / 2)
+#define WS_THREADS ((WS_XW + WS_CW) * 32)
+__device__ __forceinline__ void mbar_wait_k(unsigned long long *bar, int use) { mbar_wait(bar, (unsigned)use & 1u); }
+
+__global__ void __launch_bounds__(WS_THREADS, 1) k_smooth3_ws(const __grid_constant__ smooth_tmaps maps, const __grid_constant__ smooth_src src,
+                                                              float *__restrict__ out, int nx, int ny, int zc, unsigned int *__restrict__ mm_enc) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float *rawbuf = reinterpret_cast<float *>(smem_raw);
+  double2 *xs2 = reinterpret_cast<double2 *>(smem_raw + SXT_RAW * SXT_RAW_BYTES);
+  __shared__ float red[2][WS_CW];
+  __shared__ __align__(8) unsigned long long raw_full[SXT_RAW], raw_free[SXT_RAW], xs_full[SX_RING], xs_free[SX_RING];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
+  const int nz = src.gnz;
+  const int z0 = src.oz0 + blockIdx.z * zc, z1 = min(z0 + zc, src.oz0 + src.onz);
+  const int zs = max(z0 - 2, 0), ze = min(z1 + 2, nz);
+  const int np = ze - zs;  // planes this CTA walks
+  const int gx = x0 + lane * 4;
+  if (tid == 0) {
+    for (int k = 0; k < SXT_RAW; k++) { mbar_init(&raw_full[k], 1); mbar_init(&raw_free[k], WS_XW * 32); }
+    for (int k = 0; k < SX_RING; k++) { mbar_init(&xs_full[k], WS_XW * 32); mbar_init(&xs_free[k], WS_CW * 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  float vmin = INFINITY, vmax = -INFINITY;
+  if (warp < WS_XW) {
+    // ---------------- x-pass warps ----------------
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    const bool xedge = x0 == 0 || x0 + SX_TX > nx - 2;  // block-uniform
+    const int zb1 = src.rz0 + src.n_lo, zb2 = zb1 + src.n_main;
+    auto issue = [&](int i) {  // plane zs + i -> raw slot i % SXT_RAW
+      const int zp = zs + i, slot = i % SXT_RAW;
+      if (i >= SXT_RAW) mbar_wait_k(&raw_free[slot], i / SXT_RAW - 1);  // every x-pass thread has read the previous tenant
+      const CUtensorMap *m = zp < zb1 ? &maps.lo : (zp < zb2 ? &maps.main : &maps.hi);
+      const int q = zp < zb1 ? zp - src.rz0 : (zp < zb2 ? zp - zb1 : zp - zb2);
+      mbar_expect_tx(&raw_full[slot], SXT_RAW_BYTES);
+      tma_load_3d(rawbuf + (size_t)slot * (SXT_RAW_BYTES / 4), m, x0 - 4, y0 - 2, q, &raw_full[slot]);
+    };
+    if (tid == 0) { issue(0); if (np > 1) issue(1); }
+    for (int i = 0; i < np; i++) {
+      if (tid == 0 && i + 2 < np) issue(i + 2);
+      __syncwarp();
+      mbar_wait_k(&raw_full[i % SXT_RAW], i / SXT_RAW);
+      if (i >= SX_RING) mbar_wait_k(&xs_free[i % SX_RING], i / SX_RING - 1);  // the y/z warps are done with the slot's previous plane
+      const float *rp = rawbuf + (size_t)(i % SXT_RAW) * (SXT_RAW_BYTES / 4) + lane * 4 + 2;
+      double2 *buf = xs2 + (size_t)(i % SX_RING) * (SX_ROWS * 64);
+      for (int r = warp; r < SX_ROWS; r += WS_XW) {  // staged rows warp, warp + 8, ...
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 t = *reinterpret_cast<const float2 *>(rp + r * SXT_BW + 2 * k);
+          f[2 * k] = t.x; f[2 * k + 1] = t.y;
+        }
+        unsigned m = 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m = max(m, input_bias(f[k]));
+        bool warp_bad = false;
+        if (__any_sync(0xffffffffu, m >= 0x64000000u)) {
+          bool bad = false;
+#pragma unroll
+          for (int k = 0; k < 8; k++) bad |= input_unsafe(f[k]);
+          warp_bad = __any_sync(0xffffffffu, bad);
+        }
+        double2 *dst = buf + r * 64;
+        if (xedge) {
+          if (!warp_bad) x_pass_row_smem<true, true>(f, lane, gx, nx, dst);
+          else x_pass_row_smem<false, true>(f, lane, gx, nx, dst);
+        } else {
+          if (!warp_bad) x_pass_row_smem<true, false>(f, lane, gx, nx, dst);
+          else x_pass_row_smem<false, false>(f, lane, gx, nx, dst);
+        }
+      }
+      mbar_arrive(&raw_free[i % SXT_RAW]);
+      mbar_arrive(&xs_full[i % SX_RING]);
+    }
+  } else {
+    // ---------------- y / z-pass warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    const int cw = warp - WS_XW;  // 0 .. WS_CW-1: output rows y0 + 2 cw, y0 + 2 cw + 1
+    const size_t nxy = (size_t)nx * ny;
+    double S[2][4][4];
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) S[r][k][q] = 0.0;
+    const int oy0 = y0 + 2 * cw;
+    const bool yb0 = oy0 < 2 || oy0 >= ny - 2, yb1 = oy0 + 1 < 2 || oy0 + 1 >= ny - 2;
+    const bool ok0 = oy0 < ny && gx < nx, ok1 = oy0 + 1 < ny && gx < nx;
+    const bool yedge = y0 == 0 || y0 + SX_TY > ny - 2;  // block-uniform
+    float *outp = out + (size_t)oy0 * nx + gx;
+    long long zoff = (long long)(zs - src.oz0) * (long long)nxy;
+    for (int i = 0; i < np; i++, zoff += (long long)nxy) {
+      const int zp = zs + i;
+      mbar_wait_k(&xs_full[i % SX_RING], i / SX_RING);
+      const double2 *buf = xs2 + (size_t)(i % SX_RING) * (SX_ROWS * 64);
+      float ob[2][4], oi[2][4];
+      if (!yedge) yz_pass2<false>(buf, 2 * cw, lane, false, false, S, ob, oi);
+      else yz_pass2<true>(buf, 2 * cw, lane, yb0, yb1, S, ob, oi);
+      mbar_arrive(&xs_free[i % SX_RING]);  // (the staged rows are in registers / consumed: yz_pass2 returned their sums)
+      const bool zborder = zp < 2 || zp >= nz - 2;
+      const int zo = zp - 2;
+      const bool emit_border = zborder && zp >= z0 && zp < z1;
+      const bool emit_inner = zo >= z0 && zo < z1 && zo >= 2 && zo < nz - 2;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        if (r ? ok1 : ok0) {
+          if (emit_border) {
+            *reinterpret_cast<float4 *>(outp + zoff + (r ? nx : 0)) = make_float4(ob[r][0], ob[r][1], ob[r][2], ob[r][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { vmin = fminf(vmin, ob[r][k]); vmax = fmaxf(vmax, ob[r][k]); }
+          }
+          if (emit_inner) {
+            *reinterpret_cast<float4 *>(outp + (zoff - 2 * (long long)nxy) + (r ? nx : 0)) = make_float4(oi[r][0], oi[r][1], oi[r][2], oi[r][3]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { vmin = fminf(vmin, oi[r][k]); vmax = fmaxf(vmax, oi[r][k]); }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    }
+    if (lane == 0) { red[0][cw] = vmin; red[1][cw] = vmax; }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    vmin = tid < WS_CW ? red[0][tid] : INFINITY;
+    vmax = tid < WS_CW ? red[1][tid] : -INFINITY;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, d));
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    }
+    if (tid == 0 && vmin <= vmax) {
+      atomicMin(&mm_enc[0], f32_enc(vmin));
+      atomicMax(&mm_enc[1], f32_enc(vmax));
+    }
+  }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -773,7 +927,8 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
   // TMA path (B2M_SMOOTH_TMA=1; measured on B200 at G1024: 4.16 ms against 3.65 ms for the per-thread loads, so it is
   // not the default): needs what the vector path needs, a stride of the rows that is a multiple of 16 bytes, and a
   // driver that can encode tensor maps
-  static const bool want_tma = getenv("B2M_SMOOTH_TMA") && atoi(getenv("B2M_SMOOTH_TMA")) > 0;
+  static const bool want_ws = getenv("B2M_SMOOTH_WS") && atoi(getenv("B2M_SMOOTH_WS")) > 0;
+  static const bool want_tma = want_ws || (getenv("B2M_SMOOTH_TMA") && atoi(getenv("B2M_SMOOTH_TMA")) > 0);
   if (vec && want_tma && SX_STAGE_WARPS) {
     smooth_tmaps maps;
     memset(&maps, 0, sizeof(maps));
@@ -783,9 +938,13 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
     if (ok) {
       if (!ctx->smooth_tma_attr_done) {
         CU_TRY(cudaFuncSetAttribute(k_smooth3_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SXT_SMEM));
+        CU_TRY(cudaFuncSetAttribute(k_smooth3_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, SXT_SMEM));
         ctx->smooth_tma_attr_done = 1;
       }
-      KT_LAUNCH(ctx, "smooth3", k_smooth3_tma<<<grid, SX_THREADS, SXT_SMEM, ctx->stream>>>(maps, src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
+      if (want_ws)
+        KT_LAUNCH(ctx, "smooth3", k_smooth3_ws<<<grid, WS_THREADS, SXT_SMEM, ctx->stream>>>(maps, src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
+      else
+        KT_LAUNCH(ctx, "smooth3", k_smooth3_tma<<<grid, SX_THREADS, SXT_SMEM, ctx->stream>>>(maps, src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
       CU_TRY(cudaGetLastError());
       return B2M_OK;
     }
