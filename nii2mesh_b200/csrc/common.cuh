@@ -321,7 +321,16 @@ struct smooth_src {
   int gnz;                 // global NZ
   int oz0, onz;            // output: global planes [oz0, oz0+onz) -> d_out plane (z - oz0)
 };
-int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc);
+// optional by-product of the smooth: the threshold bit rows of its output planes for a GIVEN isolevel (see k_smooth3).
+// The pointers are offset to output plane 0 of the call, like d_out; bg may be null.
+struct smooth_bits {
+  uint32_t *fg, *bg, *mb;
+  float iso;
+  int classic;
+};
+// *bits_done = 1 when the call wrote the bit rows (vector path, nx % 32 == 0, default kernel), else 0
+int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc,
+                   const smooth_bits *bits = nullptr, int *bits_done = nullptr);
 int b2m_minmax_run(b2m_ctx *ctx, const float *d_in, size_t n, b2m_scalars *d_sc);
 // fg = v >= iso, bg = its complement (optional), mb = the marching-cubes comparison (optional):
 // Lewiner v - iso > -FLT_EPSILON (src/MarchingCubes.c:132-133 after :1112), classic v < iso (src/oldcubes.c:407-414)
@@ -336,6 +345,8 @@ struct b2m_front_out {
   float iso, vmin, vmax, edge_max;
   int lo[3], hi[3];        // widened bbox as handed to marching cubes (global)
   int iso_reset;
+  int bits_ready;          // the smooth already wrote fg / bg / mb for isolevel bits_iso (b2m_cc_run then skips k_threshold)
+  float bits_iso;
 };
 int b2m_cc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom &g, const b2m_opts *o, b2m_scalars *d_sc,
                b2m_front_out *fo);

@@ -283,7 +283,10 @@ __device__ __forceinline__ void mc_flush(const mc_params &p, uint4 *mybuf, unsig
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(MCB_THREADS) k_mc_classify(const __grid_constant__ mc_params p) {
+#ifndef MCB_MINB
+#define MCB_MINB 9  /* 56 registers, no spill; measured flat from 8 to 10, slower at 1 (117 registers) and at 12 (spills) */
+#endif
+__global__ void __launch_bounds__(MCB_THREADS, MCB_MINB) k_mc_classify(const __grid_constant__ mc_params p) {
   __shared__ uint4 rbuf[MCB_THREADS / 32][MCB_BUF];
   const unsigned lane = threadIdx.x & 31;
   uint4 *mybuf = rbuf[threadIdx.x >> 5];
@@ -585,7 +588,10 @@ __device__ __forceinline__ bool near_int(float f, float tol) { return fabsf(__fs
 __device__ __forceinline__ void flag_near(const mc_emit_params &e, uint32_t local) { atomicOr(e.nearbits + (local >> 5), 1u << (local & 31u)); }
 __device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f - rint(f)) < tol; }
 
-__global__ void __launch_bounds__(128, 12) k_mc_emit(mc_params p, mc_emit_params e) {
+#ifndef EMIT_MINB
+#define EMIT_MINB 12
+#endif
+__global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit_params e) {
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= e.n_active) return;
   const uint4 r = p.active[i];

@@ -92,6 +92,37 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
     src.main = d_img; src.n_main = sl.nzl; src.rz0 = sl.z0; src.gnz = sl.gnz;
     src.lo = src.hi = d_img;
     src.oz0 = sl.ez0; src.onz = sl.nze;
+    // threshold bit rows as a by-product of the smooth, for the isolevel the caller asked for.  Opt-in (B2M_SMOOTH_BITS=1):
+    // bit-exact (tests/test_gpu_parity.py::test_smooth_writes_the_threshold_bit_rows runs it), but on B200 at G1024 the
+    // smooth grows by 1.6-1.8 ms (it is issue-bound at 128 registers per thread) while k_threshold only costs 0.9 ms
+    const char *eb = getenv("B2M_SMOOTH_BITS");  // read per call: the test switches it inside one process
+    const bool want_bits = eb && atoi(eb) > 0;
+    smooth_bits sb;
+    memset(&sb, 0, sizeof(sb));
+    const bool try_bits = want_bits && g.nx % 32 == 0 && o->isolevel == o->isolevel;
+    const size_t pwords = (size_t)g.ny * g.w;
+    if (try_bits) {
+      B2M_TRY(b2m_reserve(ctx, BUF_FG, (size_t)g.nwords * 4));
+      B2M_TRY(b2m_reserve(ctx, BUF_MB, (size_t)g.nwords * 4));
+      if (o->fill_bubbles) B2M_TRY(b2m_reserve(ctx, BUF_BG, (size_t)g.nwords * 4));
+      sb.fg = b2m_ptr<uint32_t>(ctx, BUF_FG);
+      sb.mb = b2m_ptr<uint32_t>(ctx, BUF_MB);
+      sb.bg = o->fill_bubbles ? b2m_ptr<uint32_t>(ctx, BUF_BG) : nullptr;
+      sb.iso = o->isolevel;
+      sb.classic = o->backend == B2M_BACKEND_CLASSIC;
+    }
+    int bits_all = try_bits ? 1 : 0;
+    // one launch of the smooth over the output planes src.oz0 .. (first of them = plane `p0` of S)
+    auto smooth_planes = [&](const smooth_src &sv, size_t p0) -> int {
+      if (!try_bits) return b2m_smooth_run(ctx, sv, S + p0 * nxy, g, d_sc);
+      smooth_bits b = sb;
+      b.fg += p0 * pwords; b.mb += p0 * pwords;
+      if (b.bg) b.bg += p0 * pwords;
+      int done = 0;
+      const int rc = b2m_smooth_run(ctx, sv, S + p0 * nxy, g, d_sc, &b, &done);
+      bits_all &= done;
+      return rc;
+    };
     bool halo_async = false;
     if (slabs) {
       // 3 raw planes from each neighbour: the halo plane of S is recomputed here bit-for-bit (2 for the
@@ -126,7 +157,7 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
         const int zend = avail >= sl.gnz ? sl.gnz : avail - 2;
         if (zend > zdone) {
           src.oz0 = zdone; src.onz = zend - zdone;
-          B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)zdone * nxy, g, d_sc));
+          B2M_TRY(smooth_planes(src, (size_t)zdone));
           zdone = zend;
         }
       }
@@ -135,20 +166,22 @@ int b2m_front_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const float 
       // output planes [ia, ib) read own raw planes only (z-2 .. z+2 inside [z0, z0+nzl), or clipped by the volume)
       const int ia = sl.hl ? sl.z0 + 2 : sl.ez0, ib = sl.hh ? sl.z0 + sl.nzl - 2 : sl.ez0 + sl.nze;
       src.oz0 = ia; src.onz = ib - ia;
-      B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)(ia - sl.ez0) * nxy, g, d_sc));
+      B2M_TRY(smooth_planes(src, (size_t)(ia - sl.ez0)));
       CU_TRY(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[1], 0));
       if (sl.hl) {
         src.oz0 = sl.ez0; src.onz = ia - sl.ez0;
-        B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));
+        B2M_TRY(smooth_planes(src, 0));
       }
       if (sl.hh) {
         src.oz0 = ib; src.onz = sl.ez0 + sl.nze - ib;
-        B2M_TRY(b2m_smooth_run(ctx, src, S + (size_t)(ib - sl.ez0) * nxy, g, d_sc));
+        B2M_TRY(smooth_planes(src, (size_t)(ib - sl.ez0)));
       }
     } else {
-      B2M_TRY(b2m_smooth_run(ctx, src, S, g, d_sc));  // range reduction fused (halo planes are other ranks' planes: harmless)
+      B2M_TRY(smooth_planes(src, 0));  // range reduction fused (halo planes are other ranks' planes: harmless)
     }
     fo->S = S;
+    fo->bits_ready = bits_all;
+    fo->bits_iso = sb.iso;
     B2M_TRY(stage_end(ctx, B2M_T_SMOOTH));
   } else {
     if (ctx->pend_n > 0) {  // no smooth to overlap with: wait for the whole volume

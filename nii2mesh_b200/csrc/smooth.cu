@@ -32,6 +32,9 @@
 #define SX_THREADS (32 * SX_WARPS)
 #define SX_RING 4                 /* planes of x-pass results in shared memory */
 #define SX_SMEM (SX_RING * SX_ROWS * SX_TX * 8)
+/* 448 threads get 128 registers each: the register file is handed out as if the CTA had 16 warps (__maxnreg__(144)
+   compiles without spills and then fails to launch: "too many resources requested") */
+#define SX_BOUNDS __launch_bounds__(SX_THREADS, 1)
 
 // mbarrier (shared-memory arrive/wait barrier with phases): split arrive / wait lets warps run one plane apart
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -131,9 +134,18 @@ __device__ __forceinline__ void x_pass_row(const float raw[4], const float hal[2
 
 // y pass (2 adjacent rows x 4 voxels per lane out of 6 staged rows) + z streaming accumulators
 // YEDGE: the tile holds rows y < 2 or y >= ny-2 (block-uniform); yb0 / yb1 say which of the two rows pass through
-template <bool YEDGE>
+// nobody in the kernel reads what this writes: no "memory" clobber, so it does not pin the loads around it
+__device__ __forceinline__ void st_global_if(unsigned *p, unsigned v, bool on) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.u32 [%0], %1;\n}" ::"l"(p), "r"(v), "r"((unsigned)on));
+}
+struct yz_no_hook {
+  __device__ __forceinline__ void operator()() const {}
+};
+// hook(): independent work of the caller placed INSIDE this straight-line block (after the first shared-memory loads
+// have been issued) so that the compiler can interleave it with the FP64 chains - see the bit rows of k_smooth3
+template <bool YEDGE, class HOOK = yz_no_hook>
 __device__ __forceinline__ void yz_pass2(const double2 *__restrict__ buf, int r0, int lane, bool yb0, bool yb1,
-                                         double S[2][4][4], float ob[2][4], float oi[2][4]) {
+                                         double S[2][4][4], float ob[2][4], float oi[2][4], HOOK hook = HOOK()) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     double c[6][2];
@@ -142,6 +154,7 @@ __device__ __forceinline__ void yz_pass2(const double2 *__restrict__ buf, int r0
       const double2 pj = buf[(r0 + j) * 64 + h * 32 + lane];
       c[j][0] = pj.x; c[j][1] = pj.y;
     }
+    if (h == 0) hook();
 #pragma unroll
     for (int kk = 0; kk < 2; kk++) {
       const int k = 2 * h + kk;
@@ -195,13 +208,19 @@ __device__ __forceinline__ void x_pass_rows(const float raw[3][4], const float h
   if (has3) x_pass_row<FAST, XEDGE>(raw[2], hal[2], lane, gx, nx, buf + (2 * SX_WARPS + warp) * 64);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant__ smooth_src src, float *__restrict__ out, int nx,
-                                                           int ny, int zc, unsigned int *__restrict__ mm_enc) {
+// BITS: the kernel also writes the threshold bit rows of its output planes (what k_threshold would compute from them:
+// fg = v >= iso, bg = ~fg, mb = the marching-cubes comparison) for the isolevel the caller ASKED for - the 4 GB re-read
+// of the smoothed volume by k_threshold goes away whenever that isolevel survives the range check, which needs the
+// min/max this very kernel produces (src/meshify.c:316-319); if it does not survive, k_threshold runs as before.
+// Needs nx % 32 == 0 (a bit word is then wholly inside or wholly outside the volume) and the vector path.
+template <bool VEC, bool BITS>
+__global__ void SX_BOUNDS k_smooth3(const __grid_constant__ smooth_src src, float *__restrict__ out, int nx,
+                                                           int ny, int zc, unsigned int *__restrict__ mm_enc,
+                                                           const smooth_bits sb) {
   extern __shared__ double2 xs2[];  // [SX_RING][SX_ROWS][2][32]
   __shared__ float red[2][SX_WARPS];
   __shared__ __align__(8) unsigned long long mbar[2];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = BITS ? __shfl_sync(0xffffffffu, tid >> 5, 0) : tid >> 5;  // BITS: known to be warp-uniform
   const int x0 = blockIdx.x * SX_TX, y0 = blockIdx.y * SX_TY;
   const int nz = src.gnz;
   const int z0 = src.oz0 + blockIdx.z * zc, z1 = min(z0 + zc, src.oz0 + src.onz);
@@ -234,6 +253,65 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
   const bool xedge = x0 == 0 || x0 + SX_TX > nx - 2;  // block-uniform
   const bool yedge = y0 == 0 || y0 + SX_TY > ny - 2;  // block-uniform
   float *outp = out + (size_t)oy0 * nx + gx;  // + (z - oz0) * nxy (+ nx for the second row)
+  // ---- BITS: threshold bit rows --------------------------------------------------------------------------------
+  // Lanes 8j .. 8j+7 hold the 32 voxels of word j of a tile row, two rows per warp.  Each lane turns its 4 + 4 voxels
+  // into two nibbles; three exchanges (xor 4 - which also hands row 0 to lanes 8j..8j+3 and row 1 to lanes 8j+4..8j+7 -
+  // then xor 1, xor 2) leave word j of row 0 in lane 8j and of row 1 in lane 8j+4, which store them.
+  // The exchanges are latency this kernel's 3.5 warps per scheduler cannot hide at the end of a trip and instructions
+  // it cannot afford (it is issue-bound), so: (1) the nibbles are PARKED and gathered + stored one trip later, inside
+  // the straight-line block of the next y/z pass (flush_bits as the hook of yz_pass2); (2) mb is not computed per
+  // voxel: it follows from fg (Lewiner: the same bit; classic: the opposite bit) unless some voxel of the warp's rows
+  // is within FLT_EPSILON of the isolevel or a NaN, which one screening compare per voxel and a vote detect - only
+  // then are the exact mb bits computed and gathered (park_bits, cold path).  Word offsets are 32-bit (a slab has
+  // fewer than 2^28 words).
+  const int bw = nx >> 5;                                   // words per row (BITS: nx % 32 == 0)
+  const int bpw = ny * bw;                                  // words per plane
+  const bool brow1 = (lane & 4) != 0;                       // this lane ends up with row 1
+  const int bsh = (lane & 7) * 4;
+  const int bidx_lane = (oy0 + (brow1 ? 1 : 0)) * bw + (x0 >> 5) + (lane >> 3);  // + (z - oz0) * bpw
+  const bool bst_lane = (lane & 3) == 0 && (brow1 ? ok1 : ok0);
+  auto gather2 = [&](unsigned a0, unsigned a1) {  // nibbles of row 0 / row 1 -> the word of this lane's row
+    const unsigned mine = (brow1 ? a1 : a0) << bsh, other = (brow1 ? a0 : a1) << bsh;
+    unsigned x = mine | __shfl_xor_sync(0xffffffffu, other, 4);
+    x |= __shfl_xor_sync(0xffffffffu, x, 1);
+    x |= __shfl_xor_sync(0xffffffffu, x, 2);
+    return x;
+  };
+  auto fg_nibble = [&](const float v[4]) {
+    return (v[0] >= sb.iso ? 1u : 0u) | (v[1] >= sb.iso ? 2u : 0u) | (v[2] >= sb.iso ? 4u : 0u) | (v[3] >= sb.iso ? 8u : 0u);
+  };
+  auto mb_nibble = [&](const float v[4]) {
+    unsigned m = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      m |= ((sb.classic ? v[k] < sb.iso : __fsub_rn(v[k], sb.iso) > -FLT_EPSILON) ? 1u : 0u) << k;
+    return m;
+  };
+  unsigned pf0 = 0u, pf1 = 0u;     // parked fg nibbles of the two rows
+  int pidx = 0;                    // word offset of this lane's parked word
+  bool pst = false, pmb = false;   // this lane stores the parked word; its mb word follows from fg
+  auto flush_bits = [&]() {  // branch-free: every lane shuffles (garbage when nothing is parked), the stores are predicated
+    const unsigned x = gather2(pf0, pf1);
+    // predicated stores written out: as C++ ifs they became branches that cut the y/z block in pieces
+    st_global_if(sb.fg + pidx, x, pst);
+    st_global_if(sb.bg + pidx, ~x, pst && sb.bg != nullptr);
+    st_global_if(sb.mb + pidx, sb.classic ? ~x : x, pst && pmb);
+  };
+  auto park_bits = [&](const float v0[4], const float v1[4], int plane_off) {
+    pf0 = fg_nibble(v0); pf1 = fg_nibble(v1);
+    bool near = false;  // !(|v - iso| >= eps): inside the band where mb may differ from fg, or a NaN
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      near |= !(fabsf(__fsub_rn(v0[k], sb.iso)) >= FLT_EPSILON);
+      near |= !(fabsf(__fsub_rn(v1[k], sb.iso)) >= FLT_EPSILON);
+    }
+    const bool odd = __any_sync(0xffffffffu, near);
+    pidx = plane_off + bidx_lane; pst = bst_lane; pmb = !odd;
+    if (odd) {  // cold
+      const unsigned m = gather2(mb_nibble(v0), mb_nibble(v1));
+      if (bst_lane) sb.mb[pidx] = m;
+    }
+  };
 
   // raw rows of the plane being staged, prefetched one plane ahead
   // hal: lane 0 = left halo pair (x0-2, x0-1), lane 31 = right halo pair (gx+4, gx+5), fetched by ONE load per register
@@ -330,10 +408,13 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
     // ---- y pass + z pass ----
     if (!SX_STAGE_WARPS || warp < SX_TY / 2) {
       float ob[2][4], oi[2][4];
-      if (!yedge) {
-        yz_pass2<false>(buf, 2 * warp, lane, false, false, S, ob, oi);
+      if (!BITS) {
+        if (!yedge) yz_pass2<false>(buf, 2 * warp, lane, false, false, S, ob, oi);
+        else yz_pass2<true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
       } else {
-        yz_pass2<true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi);
+        if (!yedge) yz_pass2<false>(buf, 2 * warp, lane, false, false, S, ob, oi, flush_bits);
+        else yz_pass2<true>(buf, 2 * warp, lane, yb0, yb1, S, ob, oi, flush_bits);
+        pst = false;
       }
       const bool zborder = zp < 2 || zp >= nz - 2;
       const int zo = zp - 2;
@@ -364,8 +445,18 @@ __global__ void __launch_bounds__(SX_THREADS, 1) k_smooth3(const __grid_constant
           }
         }
       }
+      if (BITS) {  // emit_border / emit_inner are block-uniform (the shuffles need the whole warp)
+        if (emit_inner) park_bits(oi[0], oi[1], (zp - 2 - src.oz0) * bpw);
+        if (emit_border) {  // at most four planes of the volume: parked rows out first, then these the same way
+          flush_bits();
+          park_bits(ob[0], ob[1], (zp - src.oz0) * bpw);
+          flush_bits();
+          pst = false;
+        }
+      }
     }
   }
+  if (BITS && (!SX_STAGE_WARPS || warp < SX_TY / 2)) flush_bits();  // the last plane's rows
   // block reduction of the range
 #pragma unroll
   for (int d = 16; d; d >>= 1) {
@@ -898,7 +989,9 @@ __global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in,
   }
 }
 
-int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc) {
+int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_geom &g, b2m_scalars *d_sc,
+                   const smooth_bits *bits, int *bits_done) {
+  if (bits_done) *bits_done = 0;
   const unsigned tx = b2m_cdiv(g.nx, SX_TX), ty = b2m_cdiv(g.ny, SX_TY);
   const int onz = src.onz;
   // z chunks: one CTA per SM at a time, so the step takes ceil(CTAs / SMs) rounds of (zc + 4) planes each; take the
@@ -920,8 +1013,9 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
   // more than 48 KB of dynamic shared memory: opt in once PER DEVICE (function attributes belong to the device's
   // context; one process may drive several GPUs - local slab groups, atlas threads)
   if (!ctx->smooth_attr_done) {  // per ctx (= per host thread and device): no shared flag to race on
-    CU_TRY(cudaFuncSetAttribute(k_smooth3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
-    CU_TRY(cudaFuncSetAttribute(k_smooth3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_smooth3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_smooth3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
+    CU_TRY(cudaFuncSetAttribute(k_smooth3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SX_SMEM));
     ctx->smooth_attr_done = 1;
   }
   // TMA path (B2M_SMOOTH_TMA=1; measured on B200 at G1024: 4.16 ms against 3.65 ms for the per-thread loads, so it is
@@ -949,10 +1043,15 @@ int b2m_smooth_run(b2m_ctx *ctx, const smooth_src &src, float *d_out, const b2m_
       return B2M_OK;
     }
   }
-  if (vec)
-    KT_LAUNCH(ctx, "smooth3", k_smooth3<true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
+  smooth_bits nob;
+  memset(&nob, 0, sizeof(nob));
+  if (vec && bits && g.nx % 32 == 0) {
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<true, true><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc, *bits));
+    if (bits_done) *bits_done = 1;
+  } else if (vec)
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<true, false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc, nob));
   else
-    KT_LAUNCH(ctx, "smooth3", k_smooth3<false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc));
+    KT_LAUNCH(ctx, "smooth3", k_smooth3<false, false><<<grid, SX_THREADS, SX_SMEM, ctx->stream>>>(src, d_out, g.nx, g.ny, zc, &d_sc->vmin_enc, nob));
   CU_TRY(cudaGetLastError());
   return B2M_OK;
 }

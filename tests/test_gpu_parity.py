@@ -365,6 +365,43 @@ def test_narrow_volumes(eng, orc):
             assert bits_differ(a["img"], b["img"]) == 0 and a["lo"] == b["lo"] and a["hi"] == b["hi"], (name, ps, ol, fb)
 
 
+@pytest.mark.parametrize("shape", [(40, 50, 96), (19, 24, 128), (23, 70, 160), (12, 9, 32)])
+def test_smooth_writes_the_threshold_bit_rows(eng, orc, shape, monkeypatch):
+    """B2M_SMOOTH_BITS=1 (opt-in: correct but slower on B200), nx % 32 == 0: k_smooth3 writes
+    fg / bg / mb for the requested isolevel and k_threshold is skipped (csrc/smooth.cu, csrc/pipeline.cu b2m_front_run).  Partial tiles in x and y, an isolevel one ulp above a smoothed voxel (that voxel
+    is outside for `>= iso` but inside for marching cubes' `v - iso > -FLT_EPSILON`), an isolevel the range check
+    replaces (the speculated rows are then discarded), both table sets."""
+    monkeypatch.setenv("B2M_SMOOTH_BITS", "1")
+    rng = np.random.default_rng(shape[2] * 7 + shape[0])
+    vol = rng.standard_normal(shape).astype(np.float32)
+    vol[shape[0] // 3: shape[0] // 2, 2:-2, 3:-3] += 2.0  # one big bright block + speckle
+    S = orc.smooth(vol)
+    cand = S[(np.abs(S) > 0.25) & (np.abs(S) < 0.5)]
+    near = np.nextafter(np.float32(cand[len(cand) // 2]), np.float32(np.inf))
+    for iso in (0.3, float(near), 1.0, 1e9, -1e9):
+        for ps, ol, fb in ((1, 1, 1), (1, 0, 0), (1, 1, 0), (1, 0, 1)):
+            a, b = eng.front(vol, iso, ps, ol, fb), orc.front(vol, iso, ps, ol, fb)
+            tag = (shape, iso, ps, ol, fb)
+            assert (a["iso"], a["lo"], a["hi"]) == (b["iso"], b["lo"], b["hi"]), tag
+            if ol or fb:
+                assert np.array_equal(a["mask"] != 0, b["mask"] != 0), tag
+            assert bits_differ(a["img"], b["img"]) == 0, tag
+        for backend in (0, 1):
+            gv, gt, r = eng.meshify(vol, iso, 0, 1, 1, 1, backend)
+            o = orc.meshify(vol, iso, 0, 1, 1, 1, backend)
+            assert (r.pre_nverts, r.pre_ntris) == (o["pre_nv"], o["pre_nt"]), (shape, iso, backend)
+            assert_same_mesh(gv, gt, o["verts"], o["tris"], POS_RTOL)
+        # the path under test really ran: no k_threshold launch unless the range check replaced the isolevel
+        eng.set_profile(True)
+        try:
+            d = eng.upload(vol)
+            eng.meshify_device(d, iso, 0, 1, 1, 1, 0, fetch=False)
+            names = [k for k, _ in eng.kernel_times()]
+        finally:
+            eng.set_profile(False)
+        assert ("threshold" in names) == (abs(iso) > 1e8), (shape, iso, names)
+
+
 def test_pinned_input_overlapped_h2d(eng):
     """a pinned host volume >= 256 MiB goes up in z-chunks on a second stream while the smooth follows the transfer
     (b2m_meshify_host); the mesh equals the device-resident path bit for bit"""
