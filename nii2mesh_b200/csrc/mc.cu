@@ -588,13 +588,40 @@ __device__ __forceinline__ bool near_int(float f, float tol) { return fabsf(__fs
 __device__ __forceinline__ void flag_near(const mc_emit_params &e, uint32_t local) { atomicOr(e.nearbits + (local >> 5), 1u << (local & 31u)); }
 __device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f - rint(f)) < tol; }
 
+/* CTAs per SM the register budget is cut for.  The kernel waits on dependent L2 round trips, so resident warps beat
+   spill-free code: Lewiner 3.26 ms of marching cubes at 16 (32 registers, spills), 3.31 at 12, 3.44 at 10 (48 registers,
+   no spills); classic keeps 12 (FP64 positions) */
 #ifndef EMIT_MINB
-#define EMIT_MINB 12
+#define EMIT_MINB (CLASSIC ? 12 : 16)
 #endif
+// Lewiner output goes through a per-warp shared-memory stage (EMIT_STAGE): consecutive active records are consecutive
+// voxels of a row, so the vertices / triangles of a warp's 32 records are a few contiguous runs of the output arrays;
+// written straight from the threads that compute them they are 8- and 4-byte stores at 24..72-byte strides - 5.6 partial
+// writes per 32-byte sector in L2 (ncu r2: 368 M write sectors for 65 M sectors of output) and, since a partial write
+// to a sector that is not resident makes L2 FETCH it, 2 GB of DRAM reads for data that is only ever overwritten.
+// Staged, a store instruction covers 256 (vertices) / 128 (triangles) contiguous bytes.
+#ifndef EMIT_STAGE
+#define EMIT_STAGE 0
+#endif
+#define EM_VCAP 96   /* 32 records x 3 edge vertices */
+#define EM_TCAP 128  /* triangles staged per warp; a warp with more (of 32 x 12 possible) stores them directly */
+// CLASSIC as a template parameter: with a run-time flag the Lewiner path carried the classic path's dynamically indexed
+// corner array (local memory) and its FP64 registers
+template <bool CLASSIC>
 __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit_params e) {
+#if EMIT_STAGE
+  __shared__ float s_v[4][EM_VCAP * 3];
+  __shared__ uint32_t s_vg[4][EM_VCAP];
+  __shared__ int s_t[4][EM_TCAP * 3];
+  __shared__ uint32_t s_tg[4][EM_TCAP];
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#endif
+  __shared__ uint32_t s_ev[13][128];
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= e.n_active) return;
-  const uint4 r = p.active[i];
+  const bool staged = EMIT_STAGE && !CLASSIC;  // block-uniform
+  const bool live = i < e.n_active;
+  if (!live && !staged) return;
+  const uint4 r = live ? p.active[i] : make_uint4(0u, 0u, 0u, 0u);  // a dead lane of a staged warp: no edges, no triangles
   const size_t row = r.x;
   const int x = r.y & 0xffff;
   const bool ex = (r.y >> 16) & 1, ey = (r.y >> 17) & 1, ez = (r.y >> 18) & 1;
@@ -604,13 +631,13 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
   const int z = zl + p.zs0;  // sub-volume plane (global); row / sidx index this rank's segment arrays
   const size_t sidx = row * p.segs + (x >> 5);
   // corner values (only the ones that exist inside the sub-volume)
-  const bool vx1 = x + 1 < p.sx, vy1 = y + 1 < p.sy, vz1 = z + 1 < p.sz;
+  const bool vx1 = live && x + 1 < p.sx, vy1 = live && y + 1 < p.sy, vz1 = live && z + 1 < p.sz;
   float c[8];
-  c[0] = mc_data(p, x, y, z);
+  c[0] = live ? mc_data(p, x, y, z) : 0.f;
   c[1] = vx1 ? mc_data(p, x + 1, y, z) : c[0];
   c[3] = vy1 ? mc_data(p, x, y + 1, z) : c[0];
   c[4] = vz1 ? mc_data(p, x, y, z + 1) : c[0];
-  if (ntri && (p.classic || hasc)) {  // Lewiner needs the far corners only for a centroid vertex
+  if (ntri && (CLASSIC || hasc)) {  // Lewiner needs the far corners only for a centroid vertex
     c[2] = mc_data(p, x + 1, y + 1, z);
     c[5] = mc_data(p, x + 1, y, z + 1);
     c[6] = mc_data(p, x + 1, y + 1, z + 1);
@@ -623,7 +650,11 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
   // Looked up BEFORE the vertex stores below (r1: validated on the single-volume and slab suites, 2.10 -> 2.06 ms): behind them (and behind the `ntri == 0` exit) the segment-record loads
   // started only after the corner values had arrived and the vertices were written - a third dependent round trip
   // through L2 per thread.  One record load serves every edge that shares a (row, segment): <= 4 loads instead of 12.
-  uint32_t ev[13];
+  // the 12 edge-vertex ids (+ the centroid's) are indexed by table entries: as a per-thread array they lived in LOCAL
+  // memory - 13 write-through stores and up to 36 loads per thread, 70 % of the kernel's L2 write sectors (ncu r2:
+  // 289 M write sectors with the output itself staged down to 79 M) and 1.3 GB of DRAM write-backs.  Shared memory,
+  // one column per thread (bank = lane).
+#define ev(k) s_ev[(k)][threadIdx.x]
   const unsigned lut = r.w;  // inside bits of the corners = the cube index the classify pass built from the inside-bit rows
   const bool in0 = lut & 1u, in1 = (lut >> 1) & 1u, in2 = (lut >> 2) & 1u, in3 = (lut >> 3) & 1u;
   const bool in4 = (lut >> 4) & 1u, in5 = (lut >> 5) & 1u, in6 = (lut >> 6) & 1u, in7 = (lut >> 7) & 1u;
@@ -646,69 +677,77 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
       const uint32_t q0 = Cr.w + __popc(Cr.x & m0) + __popc(Cr.y & m0) + __popc(Cr.z & m0);
       const uint32_t q1 = Cr.w + __popc(Cr.x & m1) + __popc(Cr.y & m1) + __popc(Cr.z & m1);
       const uint32_t d0 = D.w + __popc(D.x & m0) + __popc(D.y & m0) + __popc(D.z & m0);
-      ev[0] = c0 ? a0 : 0xffffffffu;
-      ev[1] = c1 ? a1 + ((A.x >> l1) & 1u) : 0xffffffffu;
-      ev[2] = c2 ? b0 : 0xffffffffu;
-      ev[3] = c3 ? a0 + ((A.x >> l0) & 1u) : 0xffffffffu;
-      ev[4] = c4 ? q0 : 0xffffffffu;
-      ev[5] = c5 ? q1 + ((Cr.x >> l1) & 1u) : 0xffffffffu;
-      ev[6] = c6 ? d0 : 0xffffffffu;
-      ev[7] = c7 ? q0 + ((Cr.x >> l0) & 1u) : 0xffffffffu;
-      ev[8] = c8 ? a0 + ((A.x >> l0) & 1u) + ((A.y >> l0) & 1u) : 0xffffffffu;
-      ev[9] = c9 ? a1 + ((A.x >> l1) & 1u) + ((A.y >> l1) & 1u) : 0xffffffffu;
-      ev[10] = c10 ? b1 + ((B.x >> l1) & 1u) + ((B.y >> l1) & 1u) : 0xffffffffu;
-      ev[11] = c11 ? b0 + ((B.x >> l0) & 1u) + ((B.y >> l0) & 1u) : 0xffffffffu;
+      ev(0) = c0 ? a0 : 0xffffffffu;
+      ev(1) = c1 ? a1 + ((A.x >> l1) & 1u) : 0xffffffffu;
+      ev(2) = c2 ? b0 : 0xffffffffu;
+      ev(3) = c3 ? a0 + ((A.x >> l0) & 1u) : 0xffffffffu;
+      ev(4) = c4 ? q0 : 0xffffffffu;
+      ev(5) = c5 ? q1 + ((Cr.x >> l1) & 1u) : 0xffffffffu;
+      ev(6) = c6 ? d0 : 0xffffffffu;
+      ev(7) = c7 ? q0 + ((Cr.x >> l0) & 1u) : 0xffffffffu;
+      ev(8) = c8 ? a0 + ((A.x >> l0) & 1u) + ((A.y >> l0) & 1u) : 0xffffffffu;
+      ev(9) = c9 ? a1 + ((A.x >> l1) & 1u) + ((A.y >> l1) & 1u) : 0xffffffffu;
+      ev(10) = c10 ? b1 + ((B.x >> l1) & 1u) + ((B.y >> l1) & 1u) : 0xffffffffu;
+      ev(11) = c11 ? b0 + ((B.x >> l0) & 1u) + ((B.y >> l0) & 1u) : 0xffffffffu;
     } else {  // x+1 opens the next segment of its row: one lookup per edge
       const size_t rowY = row + 1, rowZ = row + p.sy, rowYZ = row + p.sy + 1;
-      ev[0] = c0 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
-      ev[1] = c1 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
-      ev[2] = c2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
-      ev[3] = c3 ? mc_vidx(p, row, x, 1) : 0xffffffffu;
-      ev[4] = c4 ? mc_vidx(p, rowZ, x, 0) : 0xffffffffu;
-      ev[5] = c5 ? mc_vidx(p, rowZ, x + 1, 1) : 0xffffffffu;
-      ev[6] = c6 ? mc_vidx(p, rowYZ, x, 0) : 0xffffffffu;
-      ev[7] = c7 ? mc_vidx(p, rowZ, x, 1) : 0xffffffffu;
-      ev[8] = c8 ? mc_vidx(p, row, x, 2) : 0xffffffffu;
-      ev[9] = c9 ? mc_vidx(p, row, x + 1, 2) : 0xffffffffu;
-      ev[10] = c10 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
-      ev[11] = c11 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
+      ev(0) = c0 ? mc_vidx(p, row, x, 0) : 0xffffffffu;
+      ev(1) = c1 ? mc_vidx(p, row, x + 1, 1) : 0xffffffffu;
+      ev(2) = c2 ? mc_vidx(p, rowY, x, 0) : 0xffffffffu;
+      ev(3) = c3 ? mc_vidx(p, row, x, 1) : 0xffffffffu;
+      ev(4) = c4 ? mc_vidx(p, rowZ, x, 0) : 0xffffffffu;
+      ev(5) = c5 ? mc_vidx(p, rowZ, x + 1, 1) : 0xffffffffu;
+      ev(6) = c6 ? mc_vidx(p, rowYZ, x, 0) : 0xffffffffu;
+      ev(7) = c7 ? mc_vidx(p, rowZ, x, 1) : 0xffffffffu;
+      ev(8) = c8 ? mc_vidx(p, row, x, 2) : 0xffffffffu;
+      ev(9) = c9 ? mc_vidx(p, row, x + 1, 2) : 0xffffffffu;
+      ev(10) = c10 ? mc_vidx(p, rowY, x + 1, 2) : 0xffffffffu;
+      ev(11) = c11 ? mc_vidx(p, rowY, x, 2) : 0xffffffffu;
     }
-    ev[12] = 0xffffffffu;
+    ev(12) = 0xffffffffu;
   }
   // ---- own edge vertices ----
+#if EMIT_STAGE
+  // exclusive offsets of this lane's edge vertices / triangles in the warp's stage (one packed scan: sums <= 96 / 480)
+  unsigned voff = 0, toff = 0, vtot = 0, ttot = 0;
+  if (staged) {
+    const unsigned mine = (unsigned)(ex + ey + ez) | ((unsigned)ntri << 16);
+    unsigned inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned up = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= (unsigned)d) inc += up;
+    }
+    const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+    voff = (inc - mine) & 0xffffu; toff = (inc - mine) >> 16;
+    vtot = tot & 0xffffu; ttot = tot >> 16;
+  }
+#endif
   if (ex | ey | ez) {
     uint32_t vid = __ldg(&p.segbits[sidx].w) + (uint32_t)pv;
-    if (!p.classic) {
+    if (!CLASSIC) {
       const float fx = (float)x, fy = (float)y, fz = (float)z;
-      if (ex) {
-        float px = __fadd_rn(__fadd_rn(fx, lew_u(c[0], c[1])), flo0);
+      const float ox = __fadd_rn(fx, flo0), oy = __fadd_rn(fy, flo1), oz = __fadd_rn(fz, flo2);
+      // one edge vertex: into the warp's stage (or straight to verts[]), flag / weld item when it sits near a grid corner
+      auto put = [&](float qx, float qy, float qz, float qfree) {
+#if EMIT_STAGE
+        float *sv = s_v[wid] + 3 * voff;
+        sv[0] = qx; sv[1] = qy; sv[2] = qz;
+        s_vg[wid][voff] = vid - e.e_off;
+        voff++;
+#else
         double *o = e.verts + 3 * (size_t)(vid - e.e_off);
-        o[0] = (double)px; o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(px, B2M_NEAR_TOL)) {
+        o[0] = (double)qx; o[1] = (double)qy; o[2] = (double)qz;
+#endif
+        if (near_int(qfree, B2M_NEAR_TOL)) {
           flag_near(e, vid - e.e_off);
-          if (near_int(px, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
+          if (near_int(qfree, 2e-5f)) push_item(p, e, (double)qx, (double)qy, (double)qz, vid, vid);
         }
         vid++;
-      }
-      if (ey) {
-        float py = __fadd_rn(__fadd_rn(fy, lew_u(c[0], c[3])), flo1);
-        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
-        o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)py; o[2] = (double)__fadd_rn(fz, flo2);
-        if (near_int(py, B2M_NEAR_TOL)) {
-          flag_near(e, vid - e.e_off);
-          if (near_int(py, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
-        }
-        vid++;
-      }
-      if (ez) {
-        float pz = __fadd_rn(__fadd_rn(fz, lew_u(c[0], c[4])), flo2);
-        double *o = e.verts + 3 * (size_t)(vid - e.e_off);
-        o[0] = (double)__fadd_rn(fx, flo0); o[1] = (double)__fadd_rn(fy, flo1); o[2] = (double)pz;
-        if (near_int(pz, B2M_NEAR_TOL)) {
-          flag_near(e, vid - e.e_off);
-          if (near_int(pz, 2e-5f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
-        }
-      }
+      };
+      if (ex) { const float px = __fadd_rn(__fadd_rn(fx, lew_u(c[0], c[1])), flo0); put(px, oy, oz, px); }
+      if (ey) { const float py = __fadd_rn(__fadd_rn(fy, lew_u(c[0], c[3])), flo1); put(ox, py, oz, py); }
+      if (ez) { const float pz = __fadd_rn(__fadd_rn(fz, lew_u(c[0], c[4])), flo2); put(ox, oy, pz, pz); }
     } else {
       // classic: FP64, mu = (iso - v1)/(v2 - v1), p = p1 + mu*(p2-p1) (src/oldcubes.c:35-38) with the
       // direction of the LAST cube (raster order) that touches the edge: that soup copy has the
@@ -747,8 +786,18 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
       }
     }
   }
+#if EMIT_STAGE
+  if (staged) {  // the warp's edge vertices, 32 consecutive doubles (256 bytes inside a run) per store instruction
+    __syncwarp();
+    for (unsigned wd = lane; wd < 3u * vtot; wd += 32) {
+      const unsigned j = (wd * 43691u) >> 17;  // wd / 3 (wd < 288)
+      e.verts[3 * (size_t)s_vg[wid][j] + (wd - 3u * j)] = (double)s_v[wid][wd];
+    }
+    if (ttot == 0) return;  // warp-uniform
+  } else
+#endif
   if (!ntri) return;
-  if (hasc) {
+  if (ntri && hasc) {
     // centroid of the cube's existing edge vertices, summed in edge-code order in f32 local
     // coordinates, divided by the f32 count (src/MarchingCubes.c:1042-1071); then + lo in f32.
     const float fx = (float)x, fy = (float)y, fz = (float)z;
@@ -775,9 +824,9 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
     double *o = e.verts + 3 * (size_t)(e.nv_edge_l + cl);
     o[0] = (double)ox; o[1] = (double)oy; o[2] = (double)oz;
     if (near_int(ox, 1e-4f) || near_int(oy, 1e-4f) || near_int(oz, 1e-4f)) push_item(p, e, o[0], o[1], o[2], vid, vid);
-    ev[12] = vid;
+    ev(12) = vid;
   }
-  if (p.classic && (((unsigned long long)((size_t)z * p.sy + y) << 16) | (unsigned long long)x) == e.first_cube) {
+  if (CLASSIC && (((unsigned long long)((size_t)z * p.sy + y) << 16) | (unsigned long long)x) == e.first_cube) {
     // pts[0] of the reference's soup: first table edge of the first active cube, interpolated in
     // THAT cube's direction (src/oldcubes.c:428-451, :22-40)
     const int a0 = p.tab[off];
@@ -791,15 +840,31 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
     p.sc->pts0[2] = __dadd_rn(az, __dmul_rn(mu, bz - az));
   }
   // ---- triangles ----
-  const size_t tl0 = (size_t)__ldg(p.segt + sidx) + (size_t)pt;  // index in the own triangle array
-  int *t = e.tris + 3 * tl0;
+  const size_t tl0 = ntri ? (size_t)__ldg(p.segt + sidx) + (size_t)pt : 0;  // index in the own triangle array
   const signed char *tl = p.tab + off;
+#if EMIT_STAGE
+  if (staged && ttot <= EM_TCAP) {  // warp-uniform
+    int *st = s_t[wid] + 3 * toff;
+    for (int k = 0; k < ntri; k++) {
+      const int a = tl[3 * k], b = tl[3 * k + 1], cc = tl[3 * k + 2];
+      st[3 * k] = (int)ev(cc); st[3 * k + 1] = (int)ev(b); st[3 * k + 2] = (int)ev(a);  // reversed (:1134-1136)
+      s_tg[wid][toff + k] = (uint32_t)(tl0 + k);
+    }
+    __syncwarp();
+    for (unsigned wd = lane; wd < 3u * ttot; wd += 32) {
+      const unsigned j = (wd * 43691u) >> 17;  // wd / 3 (wd < 384)
+      e.tris[3 * (size_t)s_tg[wid][j] + (wd - 3u * j)] = s_t[wid][wd];
+    }
+    return;
+  }
+#endif
+  int *t = e.tris + 3 * tl0;
   for (int k = 0; k < ntri; k++) {
     int a = tl[3 * k], b = tl[3 * k + 1], cc = tl[3 * k + 2];
-    if (p.classic) { t[3 * k] = (int)ev[a]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[cc]; }
-    else { t[3 * k] = (int)ev[cc]; t[3 * k + 1] = (int)ev[b]; t[3 * k + 2] = (int)ev[a]; }  // reversed (:1134-1136)
+    if (CLASSIC) { t[3 * k] = (int)ev(a); t[3 * k + 1] = (int)ev(b); t[3 * k + 2] = (int)ev(cc); }
+    else { t[3 * k] = (int)ev(cc); t[3 * k + 1] = (int)ev(b); t[3 * k + 2] = (int)ev(a); }  // reversed (:1134-1136)
   }
-  if (p.classic) {
+  if (CLASSIC) {
     // weld items of the classic back-end are SOUP COPIES (the reference welds the soup, so equal keys are
     // ordered by soup index and an edge vertex can be split between clusters, src/meshify.c:60-79):
     // every triangle corner whose position, interpolated in THIS cube's direction (src/oldcubes.c:22-40,
@@ -825,12 +890,14 @@ __global__ void __launch_bounds__(128, EMIT_MINB) k_mc_emit(mc_params p, mc_emit
           const double px = __dadd_rn(ax, __dmul_rn(mu, bx - ax)), py = __dadd_rn(ay, __dmul_rn(mu, by - ay)), pz = __dadd_rn(az, __dmul_rn(mu, bz - az));
           const double free_axis = a >= 8 ? pz : ((a & 1) ? py : px);
           if (near_int_d(free_axis, 2e-5))
-            push_item(p, e, px, py, pz, 3u * (uint32_t)(e.t_off + tl0 + k) + (uint32_t)q, ev[a]);
+            push_item(p, e, px, py, pz, 3u * (uint32_t)(e.t_off + tl0 + k) + (uint32_t)q, ev(a));
         }
       }
     }
   }
 }
+
+#undef ev
 
 // Per-cube-index summary tables derived from the case tables, uploaded after the blob:
 //   info = table offset | ntri << 16 | (needs the MC33 face/interior tests) << 31
@@ -1033,7 +1100,10 @@ int b2m_mc_run(b2m_ctx *ctx, b2m_comm *comm, const b2m_slab &sl, const b2m_geom 
     e.t_off = t_off;
     e.first_cube = first_cube;
     CU_TRY(cudaMemsetAsync(&d_sc->n_cand, 0, 4, ctx->stream));
-    if (n_active) KT_LAUNCH(ctx, "mc_emit", k_mc_emit<<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
+    if (n_active) {
+      if (p.classic) KT_LAUNCH(ctx, "mc_emit", k_mc_emit<true><<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
+      else KT_LAUNCH(ctx, "mc_emit", k_mc_emit<false><<<b2m_cdiv(n_active, 128), 128, 0, ctx->stream>>>(p, e));
+    }
     CU_TRY(cudaGetLastError());
     if (W > 1 && !p.classic && tot_v + tot_c > 0)
       CU_TRY(cudaMemcpyAsync(d_sc->v0, e.verts, 24, cudaMemcpyDeviceToDevice, ctx->stream));
