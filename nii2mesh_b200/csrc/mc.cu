@@ -481,7 +481,11 @@ __global__ void __launch_bounds__(1024) k_scan3_single(uint32_t *part, size_t nb
 // being numbered), so only those are written: ~5 % of the segments of a smooth volume instead of three scattered
 // 4-byte stores per segment.  force_idx: one more vertex base that is read directly (first segment of the second own
 // plane = slabs' n_first).
-__global__ void __launch_bounds__(S3_THREADS) k_scan3_apply(uint4 *__restrict__ seg, const uint32_t *__restrict__ segcnt, size_t n,
+/* measured on G1024: 0.326 ms at 1 (all the registers it wants), 0.354 unconstrained, 0.368 at 8 */
+#ifndef S3A_MINB
+#define S3A_MINB 1
+#endif
+__global__ void __launch_bounds__(S3_THREADS, S3A_MINB) k_scan3_apply(uint4 *__restrict__ seg, const uint32_t *__restrict__ segcnt, size_t n,
                                                             const uint32_t *__restrict__ part, size_t nblk,
                                                             uint32_t *__restrict__ segt, uint32_t *__restrict__ segc, uint32_t voff,
                                                             size_t force_idx) {

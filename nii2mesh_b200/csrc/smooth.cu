@@ -901,7 +901,12 @@ __global__ void __launch_bounds__(256) k_minmax(const float *__restrict__ in, si
 // lanes 0..THR_WPW-1 store the words (the one-word-per-warp first version ran at 1.2 TB/s: too few
 // bytes in flight).
 #define THR_WPW 8
-__global__ void __launch_bounds__(256) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
+/* measured on G1024: 0.770 ms at 6 CTAs per SM (40 registers), 0.810 at 5, 0.883 unconstrained (58 registers), 1.02 at 1;
+   8 spills the eight values a warp trip holds */
+#ifndef THR_MINB
+#define THR_MINB 6
+#endif
+__global__ void __launch_bounds__(256, THR_MINB) k_threshold(const float *__restrict__ in, int nx, int w, long long nwords,
                                                    float iso, uint32_t *__restrict__ fg, uint32_t *__restrict__ bg,
                                                    uint32_t *__restrict__ mb, int classic) {
   const unsigned lane = threadIdx.x & 31;
