@@ -598,12 +598,12 @@ __device__ __forceinline__ bool near_int_d(double f, double tol) { return fabs(f
 #ifndef EMIT_MINB
 #define EMIT_MINB (CLASSIC ? 12 : 16)
 #endif
-// Lewiner output goes through a per-warp shared-memory stage (EMIT_STAGE): consecutive active records are consecutive
-// voxels of a row, so the vertices / triangles of a warp's 32 records are a few contiguous runs of the output arrays;
-// written straight from the threads that compute them they are 8- and 4-byte stores at 24..72-byte strides - 5.6 partial
-// writes per 32-byte sector in L2 (ncu r2: 368 M write sectors for 65 M sectors of output) and, since a partial write
-// to a sector that is not resident makes L2 FETCH it, 2 GB of DRAM reads for data that is only ever overwritten.
-// Staged, a store instruction covers 256 (vertices) / 128 (triangles) contiguous bytes.
+// EMIT_STAGE=1 (compiled out: measured slower): Lewiner output through a per-warp shared-memory stage.  Consecutive
+// active records are consecutive voxels of a row, so the vertices / triangles of a warp's 32 records are a few
+// contiguous runs of the output arrays; written straight from the threads that compute them they are 8- and 4-byte
+// stores at 24..72-byte strides.  Staged, a store instruction covers 256 (vertices) / 128 (triangles) contiguous bytes:
+// 335 M -> 79 M L1 store sectors on G1024 - and 2.07 -> 2.49 ms, with the same DRAM traffic.  The write sectors that
+// crowded L2 were not these stores but the local-memory array of edge ids (now shared memory, see ev() below).
 #ifndef EMIT_STAGE
 #define EMIT_STAGE 0
 #endif
